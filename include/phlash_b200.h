@@ -1,0 +1,122 @@
+/* phlash_b200 - B200-native (sm_100a) replacement for the data-parallel hot path of
+ * jthlab/phlash: the PSMC coalescent-HMM log-likelihood and its gradient for every
+ * (chunk x SVGD particle) pair.
+ *
+ * This header is the drop-in boundary: a plain C ABI (pointers and sizes, no C++ / torch / jax
+ * types).  Each entry point names the reference interface it replaces, relative to the
+ * reference tree (jthlab/phlash, src/phlash/...).  INTEGRATION.md shows the binding a phlash
+ * maintainer would add on the Python/JAX side.
+ *
+ * Conventions
+ *   M       number of hidden states (time intervals); supported: 4, 8, 16, 32, 64.
+ *   FLOAT   float, or double when the kernel was created with double_precision != 0
+ *           (reference: `typedef ... FLOAT`, gpu.py:132-136).
+ *   params  7 rows of M values in the order b, d, u, v, emis0, emis1, pi
+ *           (reference: PSMCParams, params.py:16-23; device layout gpu.py:483-502).
+ *   dlog    same 7 x M shape: d ll / d log(theta) for rows b, d, u, v, emis0, emis1 and
+ *           pi * d ll / d pi for the pi row; exactly zero where the parameter is zero.  The v row
+ *           is returned in its FINAL position (entry j belongs to v[j]): the reference kernel
+ *           stores it shifted by one and rolls it back on the host (gpu.py:303-313); that roll is
+ *           already applied here.
+ *   ll      always double (reference: gpu.py:216, 535, 583).
+ *
+ * Error handling: every function returns PHB_OK (0) or a negative PHB_E_* code and never
+ * throws; phb_last_error() returns a thread-local message for the last failure
+ * (reference: CudaError / AssertionError / MemoryError raised from gpu.py:23-46, 106-124, 197-214).
+ */
+#ifndef PHLASH_B200_H
+#define PHLASH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHB_OK 0
+#define PHB_E_INVALID (-1) /* bad argument: shape, M, index out of range, non-finite parameter */
+#define PHB_E_CUDA (-2)    /* a CUDA runtime call failed (message has the CUDA error string) */
+#define PHB_E_NOMEM (-3)   /* device allocation failed (reference: MemoryError, gpu.py:118-124) */
+#define PHB_E_DATA (-4)    /* data matrix violates the reference's checks (gpu.py:106-113) */
+
+typedef struct phb_kernel phb_kernel; /* opaque; owns the device copy of the data, stream, scratch */
+
+/* ABI version of this header (bumped on any signature change). */
+int phb_abi_version(void);
+
+/* Thread-local description of the most recent error in this thread ("" if none). */
+const char *phb_last_error(void);
+
+/* Number of visible CUDA devices (<0: error code).  Replaces cuDeviceGetCount, gpu.py:373. */
+int phb_device_count(void);
+
+/* Create a kernel object on `device` holding its own device copy of the observation matrix.
+ * Replaces _PSMCKernelBase.__init__ (gpu.py:104-151): `data` is host int8 [N, L] row-major with
+ * values >= -1 (-1 = missing); values > 1 are clipped to 1; a row with no non-missing entry is
+ * rejected with PHB_E_DATA. */
+int phb_create(int M, const int8_t *data, int64_t N, int64_t L, int double_precision, int device,
+               phb_kernel **out);
+
+/* Replaces _PSMCKernelBase.__del__ (gpu.py:153-174).  NULL is allowed. */
+void phb_destroy(phb_kernel *k);
+
+/* Introspection (reference: PSMCKernel.M / .double_precision / .float_type, gpu.py:343-357). */
+int phb_M(const phb_kernel *k);
+int phb_double_precision(const phb_kernel *k);
+int64_t phb_num_rows(const phb_kernel *k);
+int64_t phb_row_length(const phb_kernel *k);
+int phb_device(const phb_kernel *k);
+
+/* Tuning knob, mainly for tests: force the number of threads that cooperate on one
+ * (chunk, particle) pair (0 = choose automatically from the number of pairs). */
+int phb_set_threads_per_pair(phb_kernel *k, int threads_per_pair);
+
+/* HOST-buffer evaluation; blocking.  Replaces _PSMCKernelBase.__call__ (gpu.py:182-325) for
+ * pa of shape [B, S, 7, M]: pair (b, s) scores data row inds[s] with parameter block
+ * params[b, s].  ll is [B, S]; dlog is [B, S, 7, M] and may be NULL together with
+ * want_grad == 0, which selects the forward-only path (reference: the `loglik` kernel,
+ * gpu.py:529-573, but with every pair using its own parameter block).
+ * Checks 0 <= inds[s] < N and that all parameters are finite (gpu.py:197-199, 214). */
+int phb_loglik_host(phb_kernel *k, const void *params, const int64_t *inds, int64_t B, int64_t S,
+                    int want_grad, double *ll, void *dlog);
+
+/* Same evaluation when the 6 rows b, d, u, v, emis0, emis1 are shared by all S chunks of a
+ * particle and only pi differs per pair - how the reference actually calls the kernel
+ * (model.py:52-57: pps = pp._replace(pi=pis)).  params6 is [B, 6, M], pi is [B, S, M] (or
+ * [B, M] when pi_per_pair == 0).  Outputs as above. */
+int phb_loglik_shared_host(phb_kernel *k, const void *params6, const void *pi, int pi_per_pair,
+                           const int64_t *inds, int64_t B, int64_t S, int want_grad, double *ll,
+                           void *dlog);
+
+/* DEVICE-buffer evaluation, asynchronous on `stream` (a cudaStream_t, NULL = the kernel
+ * object's own stream): the entry an XLA FFI custom call binds (replaces the
+ * jax.pure_callback round trip, gpu.py:441-465).  All pointers are device pointers valid on
+ * the kernel object's device.  params_stride_s == 0 selects the shared-parameter fast path:
+ *   params6 + b * params_stride_b + s * params_stride_s  -> [6, M] block of pair (b, s)
+ *   pi      + b * pi_stride_b     + s * pi_stride_s      -> [M]    initial distribution
+ * (strides in elements of FLOAT).  Index and finiteness checks are done on the device:
+ * a violation makes the affected ll entries NaN and is reported by phb_sync(). */
+int phb_loglik_device(phb_kernel *k, const void *params6, int64_t params_stride_b,
+                      int64_t params_stride_s, const void *pi, int64_t pi_stride_b,
+                      int64_t pi_stride_s, const int64_t *inds, int64_t B, int64_t S,
+                      int want_grad, double *ll, void *dlog, void *stream);
+
+/* Wait for the kernel object's own stream and report deferred device-side errors. */
+int phb_sync(phb_kernel *k);
+
+/* Device pointer to the resident observation matrix and its row pitch in bytes (read-only;
+ * for callers that want to fuse their own kernels, and for tests). */
+const int8_t *phb_device_data(const phb_kernel *k, int64_t *pitch);
+
+/* Timing of the most recent evaluation on this object, measured with CUDA events on the
+ * launching stream around the compute kernel only (milliseconds; <0 if unavailable).
+ * Blocks until that kernel has finished. */
+float phb_last_kernel_ms(phb_kernel *k);
+
+/* Number of kernels this library has launched on this object since creation. */
+int64_t phb_launch_count(const phb_kernel *k);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHLASH_B200_H */

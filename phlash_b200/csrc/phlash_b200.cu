@@ -1,0 +1,457 @@
+// C-ABI of phlash_b200 (see include/phlash_b200.h): owns the device copy of the observation
+// matrix, scratch buffers and stream, validates inputs the way the reference's host class does
+// (src/phlash/gpu.py:104-151, 182-237) and dispatches to the sm_100a kernels in
+// psmc_kernels.cuh.  No CPU fallback: every evaluation is a CUDA kernel launch or an error.
+#include "../../include/phlash_b200.h"
+#include "psmc_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define PHB_CUDA(call)                                                                           \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return fail(e_ == cudaErrorMemoryAllocation ? PHB_E_NOMEM : PHB_E_CUDA, "%s: %s",    \
+                        #call, cudaGetErrorString(e_));                                          \
+    } while (0)
+
+struct DeviceBuffer {
+    void *ptr = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return PHB_OK;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        // grow geometrically so that alternating call sizes do not reallocate every time
+        size_t want = std::max(bytes, size_t(256));
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e != cudaSuccess) {
+            ptr = nullptr;
+            cudaGetLastError();
+            return fail(PHB_E_NOMEM, "cudaMalloc(%zu bytes): %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        return PHB_OK;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+using LaunchFn = int (*)(phb_kernel *, const phb::KernelArgs &, int n_slots_needed, cudaStream_t);
+
+struct Variant {
+    int M, T, K;
+    bool dbl, grad;
+    const void *func;
+    size_t smem_fixed;      // bytes excluding parameter slots
+    size_t smem_per_slot;   // bytes per parameter slot
+    int64_t ckpt_bytes_per_site_block;  // sizeof(F) * MT * kThreads
+};
+
+}  // namespace
+
+struct phb_kernel {
+    int M = 0;
+    int dbl = 0;
+    int device = 0;
+    int64_t N = 0, L = 0, pitch = 0;
+    int8_t *d_data = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    int *d_err = nullptr;
+    int force_T = 0;
+    int num_sms = 0;
+    int64_t launches = 0;
+    DeviceBuffer params, inds, ll, dlog, ckpt;
+    size_t elem() const { return dbl ? sizeof(double) : sizeof(float); }
+};
+
+namespace {
+
+template <typename F, int MT, int T, int K, bool GRAD, int MINB> Variant make_variant() {
+    Variant v;
+    v.M = MT * T;
+    v.T = T;
+    v.K = K;
+    v.dbl = sizeof(F) == 8;
+    v.grad = GRAD;
+    v.func = reinterpret_cast<const void *>(&phb::psmc_loglik_kernel<F, MT, T, K, GRAD, MINB>);
+    v.smem_fixed = phb::smem_bytes<F, MT, T, K>(0);
+    v.smem_per_slot = sizeof(F) * phb::Slot<MT * T>::kStride;
+    v.ckpt_bytes_per_site_block = int64_t(sizeof(F)) * MT * phb::kThreads;
+    return v;
+}
+
+// Every (precision, M, threads-per-pair) combination that is compiled.  Within one (precision, M)
+// the entries are ordered by increasing T; the dispatcher takes the first one that fills the GPU.
+const std::vector<Variant> &variants() {
+    static const std::vector<Variant> table = [] {
+        std::vector<Variant> t;
+#define PHB_BOTH(F, MT, T, K, MINB)                       \
+    t.push_back(make_variant<F, MT, T, K, true, MINB>()); \
+    t.push_back(make_variant<F, MT, T, K, false, MINB>());
+        // float
+        PHB_BOTH(float, 4, 1, 16, 4)    // M = 4
+        PHB_BOTH(float, 8, 1, 16, 4)    // M = 8
+        PHB_BOTH(float, 4, 2, 16, 4)
+        PHB_BOTH(float, 16, 1, 8, 2)    // M = 16
+        PHB_BOTH(float, 8, 2, 16, 3)
+        PHB_BOTH(float, 4, 4, 16, 4)
+        PHB_BOTH(float, 16, 2, 8, 2)    // M = 32
+        PHB_BOTH(float, 8, 4, 16, 3)
+        PHB_BOTH(float, 4, 8, 16, 4)
+        PHB_BOTH(float, 16, 4, 8, 2)    // M = 64
+        PHB_BOTH(float, 8, 8, 16, 3)
+        PHB_BOTH(float, 4, 16, 16, 4)
+        // double
+        PHB_BOTH(double, 4, 1, 8, 3)    // M = 4
+        PHB_BOTH(double, 8, 1, 8, 2)    // M = 8
+        PHB_BOTH(double, 4, 2, 8, 3)
+        PHB_BOTH(double, 8, 2, 8, 2)    // M = 16
+        PHB_BOTH(double, 4, 4, 8, 3)
+        PHB_BOTH(double, 8, 4, 8, 2)    // M = 32
+        PHB_BOTH(double, 4, 8, 8, 2)
+        PHB_BOTH(double, 8, 8, 8, 2)    // M = 64
+        PHB_BOTH(double, 4, 16, 8, 2)
+#undef PHB_BOTH
+        return t;
+    }();
+    return table;
+}
+
+const Variant *pick_variant(const phb_kernel *k, bool grad, int64_t n_pairs) {
+    const Variant *last = nullptr;
+    const int64_t fill = int64_t(k->num_sms) * 2 * phb::kThreads;
+    for (const Variant &v : variants()) {
+        if (v.M != k->M || v.dbl != (k->dbl != 0) || v.grad != grad) continue;
+        if (k->force_T > 0) {
+            if (v.T == k->force_T) return &v;
+            continue;
+        }
+        last = &v;
+        if (n_pairs * v.T >= fill) return &v;
+    }
+    return last;
+}
+
+int check_handle(const phb_kernel *k) {
+    if (!k) return fail(PHB_E_INVALID, "kernel handle is NULL");
+    return PHB_OK;
+}
+
+// Launch on `stream`; all pointers in `a` are device pointers except the ones filled in here.
+int launch(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream) {
+    const int64_t n_pairs = a.B * a.S;
+    if (n_pairs == 0) return PHB_OK;
+    const Variant *v = pick_variant(k, grad, n_pairs);
+    if (!v) return fail(PHB_E_INVALID, "no kernel variant for M=%d, threads_per_pair=%d", k->M, k->force_T);
+    const int pairs_per_cta = phb::kThreads / v->T;
+    a.n_groups = (n_pairs + pairs_per_cta - 1) / pairs_per_cta;
+    // parameter slots: one per pair, or - when the 6 rows are shared by the chunks of a particle -
+    // one per particle that a CTA's pairs can touch
+    int64_t slots = pairs_per_cta;
+    if (a.pstride_s == 0) slots = std::min<int64_t>(pairs_per_cta, (pairs_per_cta - 1) / a.S + 2);
+    a.n_slots = int(slots);
+    const size_t smem = v->smem_fixed + v->smem_per_slot * size_t(slots);
+    PHB_CUDA(cudaFuncSetAttribute(v->func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int occ = 0;
+    PHB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v->func, phb::kThreads, smem));
+    if (occ < 1) return fail(PHB_E_CUDA, "kernel does not fit on an SM (smem %zu bytes)", smem);
+    const int64_t grid = std::min<int64_t>(a.n_groups, int64_t(occ) * k->num_sms);
+    if (grad) {
+        const int64_t n_seg = (a.L + v->K - 1) / v->K;
+        const size_t need = size_t(grid) * size_t(n_seg) * size_t(v->ckpt_bytes_per_site_block);
+        int rc = k->ckpt.reserve(need);
+        if (rc != PHB_OK) return rc;
+        a.ckpt = k->ckpt.ptr;
+    }
+    a.err_flag = k->d_err;
+    void *kargs[] = {&a};
+    PHB_CUDA(cudaEventRecord(k->ev0, stream));
+    PHB_CUDA(cudaLaunchKernel(v->func, dim3(unsigned(grid)), dim3(phb::kThreads), kargs, smem, stream));
+    PHB_CUDA(cudaEventRecord(k->ev1, stream));
+    k->timed = true;
+    k->launches += 1;
+    return PHB_OK;
+}
+
+template <typename F> bool all_finite(const F *p, size_t n) {
+    for (size_t i = 0; i < n; ++i)
+        if (!std::isfinite(p[i])) return false;
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int phb_abi_version(void) { return 1; }
+
+const char *phb_last_error(void) { return g_err.c_str(); }
+
+int phb_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PHB_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return n;
+}
+
+int phb_create(int M, const int8_t *data, int64_t N, int64_t L, int double_precision, int device,
+               phb_kernel **out) {
+    if (!out) return fail(PHB_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!(M == 4 || M == 8 || M == 16 || M == 32 || M == 64))
+        return fail(PHB_E_INVALID, "M=%d is not supported (4, 8, 16, 32 or 64)", M);
+    if (!data || N <= 0 || L <= 0) return fail(PHB_E_INVALID, "data must be a non-empty [N, L] int8 matrix");
+    // the reference's constructor checks (gpu.py:106-113)
+    for (int64_t i = 0; i < N; ++i) {
+        const int8_t *row = data + i * L;
+        bool any = false;
+        for (int64_t j = 0; j < L; ++j) {
+            if (row[j] < -1) return fail(PHB_E_DATA, "data[%lld, %lld] = %d < -1", (long long)i, (long long)j, row[j]);
+            any |= row[j] > -1;
+        }
+        if (!any) return fail(PHB_E_DATA, "data contains observations with all missing values (row %lld)", (long long)i);
+    }
+    int ndev = 0;
+    PHB_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(PHB_E_INVALID, "device %d out of range (%d visible)", device, ndev);
+    PHB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PHB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(PHB_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+
+    phb_kernel *k = new (std::nothrow) phb_kernel();
+    if (!k) return fail(PHB_E_NOMEM, "host allocation failed");
+    k->M = M;
+    k->dbl = double_precision ? 1 : 0;
+    k->device = device;
+    k->N = N;
+    k->L = L;
+    k->pitch = (L + 15) / 16 * 16;
+    k->num_sms = prop.multiProcessorCount;
+    auto cleanup = [&](int rc) {
+        phb_destroy(k);
+        return rc;
+    };
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&k->d_data), size_t(N) * size_t(k->pitch));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return cleanup(fail(PHB_E_NOMEM, "While trying to allocate %lld bytes on GPU: %s", (long long)(N * k->pitch), cudaGetErrorString(e)));
+    }
+    // clip to [-1, 1] on the way in (gpu.py:108-110); padding columns are never read as sites
+    {
+        std::vector<int8_t> staged(size_t(N) * size_t(k->pitch), int8_t(-1));
+        for (int64_t i = 0; i < N; ++i) {
+            const int8_t *src = data + i * L;
+            int8_t *dst = staged.data() + i * k->pitch;
+            for (int64_t j = 0; j < L; ++j) dst[j] = src[j] > 1 ? int8_t(1) : src[j];
+        }
+        e = cudaMemcpy(k->d_data, staged.data(), staged.size(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return cleanup(fail(PHB_E_CUDA, "cudaMemcpy(data): %s", cudaGetErrorString(e)));
+    }
+    if ((e = cudaStreamCreateWithFlags(&k->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&k->ev0)) != cudaSuccess || (e = cudaEventCreate(&k->ev1)) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void **>(&k->d_err), sizeof(int))) != cudaSuccess ||
+        (e = cudaMemset(k->d_err, 0, sizeof(int))) != cudaSuccess)
+        return cleanup(fail(PHB_E_CUDA, "stream/event setup: %s", cudaGetErrorString(e)));
+    *out = k;
+    return PHB_OK;
+}
+
+void phb_destroy(phb_kernel *k) {
+    if (!k) return;
+    cudaSetDevice(k->device);
+    if (k->stream) cudaStreamSynchronize(k->stream);
+    k->params.release();
+    k->inds.release();
+    k->ll.release();
+    k->dlog.release();
+    k->ckpt.release();
+    if (k->d_data) cudaFree(k->d_data);
+    if (k->d_err) cudaFree(k->d_err);
+    if (k->ev0) cudaEventDestroy(k->ev0);
+    if (k->ev1) cudaEventDestroy(k->ev1);
+    if (k->stream) cudaStreamDestroy(k->stream);
+    delete k;
+}
+
+int phb_M(const phb_kernel *k) { return k ? k->M : 0; }
+int phb_double_precision(const phb_kernel *k) { return k ? k->dbl : 0; }
+int64_t phb_num_rows(const phb_kernel *k) { return k ? k->N : 0; }
+int64_t phb_row_length(const phb_kernel *k) { return k ? k->L : 0; }
+int phb_device(const phb_kernel *k) { return k ? k->device : -1; }
+int64_t phb_launch_count(const phb_kernel *k) { return k ? k->launches : 0; }
+
+const int8_t *phb_device_data(const phb_kernel *k, int64_t *pitch) {
+    if (!k) return nullptr;
+    if (pitch) *pitch = k->pitch;
+    return k->d_data;
+}
+
+int phb_set_threads_per_pair(phb_kernel *k, int threads_per_pair) {
+    if (int rc = check_handle(k)) return rc;
+    if (threads_per_pair != 0) {
+        bool ok = false;
+        for (const Variant &v : variants()) ok |= (v.M == k->M && v.dbl == (k->dbl != 0) && v.T == threads_per_pair);
+        if (!ok) return fail(PHB_E_INVALID, "threads_per_pair=%d is not compiled for M=%d", threads_per_pair, k->M);
+    }
+    k->force_T = threads_per_pair;
+    return PHB_OK;
+}
+
+int phb_loglik_device(phb_kernel *k, const void *params6, int64_t params_stride_b, int64_t params_stride_s,
+                      const void *pi, int64_t pi_stride_b, int64_t pi_stride_s, const int64_t *inds,
+                      int64_t B, int64_t S, int want_grad, double *ll, void *dlog, void *stream) {
+    if (int rc = check_handle(k)) return rc;
+    if (B < 0 || S < 0) return fail(PHB_E_INVALID, "negative batch shape");
+    if (B == 0 || S == 0) return PHB_OK;
+    if (!params6 || !pi || !inds || !ll) return fail(PHB_E_INVALID, "NULL device pointer");
+    if (want_grad && !dlog) return fail(PHB_E_INVALID, "want_grad is set but dlog is NULL");
+    PHB_CUDA(cudaSetDevice(k->device));
+    phb::KernelArgs a{};
+    a.data = k->d_data;
+    a.pitch = k->pitch;
+    a.n_rows = k->N;
+    a.L = k->L;
+    a.inds = inds;
+    a.B = B;
+    a.S = S;
+    a.params6 = params6;
+    a.pstride_b = params_stride_b;
+    a.pstride_s = params_stride_s;
+    a.pi = pi;
+    a.pistride_b = pi_stride_b;
+    a.pistride_s = pi_stride_s;
+    a.ll = ll;
+    a.dlog = want_grad ? dlog : nullptr;
+    a.alpha_out = nullptr;
+    return launch(k, a, want_grad != 0, stream ? static_cast<cudaStream_t>(stream) : k->stream);
+}
+
+int phb_sync(phb_kernel *k) {
+    if (int rc = check_handle(k)) return rc;
+    PHB_CUDA(cudaSetDevice(k->device));
+    PHB_CUDA(cudaStreamSynchronize(k->stream));
+    int flag = 0;
+    PHB_CUDA(cudaMemcpy(&flag, k->d_err, sizeof flag, cudaMemcpyDeviceToHost));
+    if (flag) PHB_CUDA(cudaMemset(k->d_err, 0, sizeof(int)));
+    if (flag & 1) return fail(PHB_E_INVALID, "index out of range: need 0 <= inds < N=%lld", (long long)k->N);
+    return PHB_OK;
+}
+
+float phb_last_kernel_ms(phb_kernel *k) {
+    if (!k || !k->timed) return -1.f;
+    cudaSetDevice(k->device);
+    if (cudaEventSynchronize(k->ev1) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, k->ev0, k->ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+static int host_eval(phb_kernel *k, const void *params, size_t params_elems, int64_t pstride_b, int64_t pstride_s,
+                     int64_t pi_offset, int64_t pistride_b, int64_t pistride_s, const void *pi_host,
+                     size_t pi_elems, const int64_t *inds, int64_t B, int64_t S, int want_grad, double *ll,
+                     void *dlog) {
+    const size_t es = k->elem();
+    const int M = k->M;
+    for (int64_t s = 0; s < S; ++s)
+        if (inds[s] < 0 || inds[s] >= k->N)
+            return fail(PHB_E_INVALID, "0 <= inds[%lld]=%lld < N=%lld violated", (long long)s, (long long)inds[s], (long long)k->N);
+    const bool fin = k->dbl ? (all_finite(static_cast<const double *>(params), params_elems) &&
+                               (!pi_host || all_finite(static_cast<const double *>(pi_host), pi_elems)))
+                            : (all_finite(static_cast<const float *>(params), params_elems) &&
+                               (!pi_host || all_finite(static_cast<const float *>(pi_host), pi_elems)));
+    if (!fin) return fail(PHB_E_INVALID, "not all parameters finite");
+    PHB_CUDA(cudaSetDevice(k->device));
+    int rc;
+    if ((rc = k->params.reserve((params_elems + pi_elems) * es)) != PHB_OK) return rc;
+    if ((rc = k->inds.reserve(size_t(S) * sizeof(int64_t))) != PHB_OK) return rc;
+    if ((rc = k->ll.reserve(size_t(B) * S * sizeof(double))) != PHB_OK) return rc;
+    if (want_grad && (rc = k->dlog.reserve(size_t(B) * S * 7 * M * es)) != PHB_OK) return rc;
+    char *d_params = static_cast<char *>(k->params.ptr);
+    PHB_CUDA(cudaMemcpyAsync(d_params, params, params_elems * es, cudaMemcpyHostToDevice, k->stream));
+    const char *d_pi = d_params + size_t(pi_offset) * es;
+    if (pi_host) {
+        PHB_CUDA(cudaMemcpyAsync(d_params + params_elems * es, pi_host, pi_elems * es, cudaMemcpyHostToDevice, k->stream));
+        d_pi = d_params + params_elems * es;
+    }
+    PHB_CUDA(cudaMemcpyAsync(k->inds.ptr, inds, size_t(S) * sizeof(int64_t), cudaMemcpyHostToDevice, k->stream));
+    rc = phb_loglik_device(k, d_params, pstride_b, pstride_s, d_pi, pistride_b, pistride_s,
+                           static_cast<const int64_t *>(k->inds.ptr), B, S, want_grad,
+                           static_cast<double *>(k->ll.ptr), want_grad ? k->dlog.ptr : nullptr, k->stream);
+    if (rc != PHB_OK) return rc;
+    PHB_CUDA(cudaMemcpyAsync(ll, k->ll.ptr, size_t(B) * S * sizeof(double), cudaMemcpyDeviceToHost, k->stream));
+    if (want_grad)
+        PHB_CUDA(cudaMemcpyAsync(dlog, k->dlog.ptr, size_t(B) * S * 7 * M * es, cudaMemcpyDeviceToHost, k->stream));
+    return phb_sync(k);
+}
+
+int phb_loglik_host(phb_kernel *k, const void *params, const int64_t *inds, int64_t B, int64_t S, int want_grad,
+                    double *ll, void *dlog) {
+    if (int rc = check_handle(k)) return rc;
+    if (B < 0 || S < 0) return fail(PHB_E_INVALID, "negative batch shape");
+    if (B == 0 || S == 0) return PHB_OK;
+    if (!params || !inds || !ll) return fail(PHB_E_INVALID, "NULL pointer");
+    if (want_grad && !dlog) return fail(PHB_E_INVALID, "want_grad is set but dlog is NULL");
+    const int M = k->M;
+    const size_t es = k->elem();
+    const int64_t blk = 7 * M;
+    // Are rows b..emis1 identical across the S chunks of every particle (the way the reference
+    // builds its argument, model.py:55)?  Then the kernel can keep one copy per particle.
+    bool shared = true;
+    const char *p = static_cast<const char *>(params);
+    for (int64_t b = 0; b < B && shared; ++b)
+        for (int64_t s = 1; s < S; ++s)
+            if (memcmp(p + (b * S) * blk * es, p + (b * S + s) * blk * es, size_t(6) * M * es) != 0) {
+                shared = false;
+                break;
+            }
+    return host_eval(k, params, size_t(B) * S * blk, S * blk, shared ? 0 : blk, 6 * M, S * blk, blk, nullptr, 0,
+                     inds, B, S, want_grad, ll, dlog);
+}
+
+int phb_loglik_shared_host(phb_kernel *k, const void *params6, const void *pi, int pi_per_pair,
+                           const int64_t *inds, int64_t B, int64_t S, int want_grad, double *ll, void *dlog) {
+    if (int rc = check_handle(k)) return rc;
+    if (B < 0 || S < 0) return fail(PHB_E_INVALID, "negative batch shape");
+    if (B == 0 || S == 0) return PHB_OK;
+    if (!params6 || !pi || !inds || !ll) return fail(PHB_E_INVALID, "NULL pointer");
+    if (want_grad && !dlog) return fail(PHB_E_INVALID, "want_grad is set but dlog is NULL");
+    const int M = k->M;
+    const size_t pi_elems = pi_per_pair ? size_t(B) * S * M : size_t(B) * M;
+    return host_eval(k, params6, size_t(B) * 6 * M, 6 * M, 0, 0, pi_per_pair ? S * M : M, pi_per_pair ? M : 0, pi,
+                     pi_elems, inds, B, S, want_grad, ll, dlog);
+}
+
+}  // extern "C"

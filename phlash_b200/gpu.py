@@ -1,0 +1,275 @@
+"""Host-side mirror of ``phlash.gpu`` (reference: src/phlash/gpu.py:101-438): the same
+``PSMCKernel`` constructor / ``__call__`` / ``loglik`` / ``float_type`` surface, backed by the
+sm_100a kernels behind the C ABI in ``include/phlash_b200.h``.
+
+Differences from the reference, all deliberate:
+  * no NVRTC: the kernels are compiled ahead of time for sm_100a;
+  * no fallback: a missing library, a missing GPU or a CUDA failure raises;
+  * scratch buffers grow with the call (the reference sizes them by the first call, gpu.py:222-237);
+  * ``num_gpus > 1`` splits the *chunk* axis S across devices and joins on that axis (the
+    reference joins on the particle axis, gpu.py:425-429, which is only right for B == 1);
+  * the forward-only path gives every pair its own parameter block (the reference's ``loglik``
+    kernel silently uses the parameters of s == 0 for the whole block, gpu.py:548-551).
+"""
+
+from __future__ import annotations
+
+import ctypes
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+from phlash_b200 import _native
+from phlash_b200.params import PSMCParams
+
+
+class CudaError(RuntimeError):
+    """Raised for CUDA runtime failures (reference: gpu.py:23-32)."""
+
+
+def _check(rc: int) -> None:
+    if rc == _native.PHB_OK:
+        return
+    msg = _native.last_error()
+    if rc == _native.PHB_E_NOMEM:
+        raise MemoryError(msg)
+    if rc == _native.PHB_E_CUDA:
+        raise CudaError(msg)
+    # PHB_E_INVALID / PHB_E_DATA: the reference signals these with bare asserts
+    raise AssertionError(msg)
+
+
+def _ptr(a: np.ndarray) -> ctypes.c_void_p:
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class _PSMCKernelBase:
+    "PSMC kernel running on a single GPU (reference: gpu.py:101-325)"
+
+    def __init__(self, M: int, data: np.ndarray, double_precision: bool = False, device: int = 0):
+        data = np.asarray(data)
+        assert data.ndim == 2
+        assert data.dtype == np.int8
+        assert data.min() >= -1
+        data = np.ascontiguousarray(data.clip(-1, 1))
+        assert np.all(data.max(axis=1) > -1), "data contains observations with all missing values"
+        self.double_precision = bool(double_precision)
+        self._N, self._L = data.shape
+        self._M = int(M)
+        self._lib = _native.lib()
+        handle = ctypes.c_void_p()
+        _check(
+            self._lib.phb_create(
+                self._M, _ptr(data), self._N, self._L, int(self.double_precision), int(device), ctypes.byref(handle)
+            )
+        )
+        self._handle = handle
+        self.device = int(device)
+
+    def __del__(self):
+        handle = getattr(self, "_handle", None)
+        if handle is not None and handle.value:
+            self._lib.phb_destroy(handle)
+            self._handle = None
+
+    @property
+    def float_type(self):
+        return np.float64 if self.double_precision else np.float32
+
+    def set_threads_per_pair(self, t: int) -> None:
+        _check(self._lib.phb_set_threads_per_pair(self._handle, int(t)))
+
+    @property
+    def last_kernel_ms(self) -> float:
+        return float(self._lib.phb_last_kernel_ms(self._handle))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.phb_launch_count(self._handle))
+
+    def evaluate(self, pa: np.ndarray, inds: np.ndarray, grad: bool):
+        """pa [B, S, 7, M] (any float dtype), inds [S] -> ll [B, S] (, dlog [B, S, 7, M])."""
+        M = self._M
+        B, S = pa.shape[:2]
+        assert pa.shape == (B, S, 7, M)
+        assert inds.shape == (S,)
+        assert np.all(0 <= inds) & np.all(inds < self._N), f"0 <= {inds.min()=} < {inds.max()=} < N"
+        assert np.isfinite(pa).all(), "not all parameters finite"
+        pa = np.ascontiguousarray(pa, dtype=self.float_type)
+        inds = np.ascontiguousarray(inds, dtype=np.int64)
+        ll = np.zeros([B, S], dtype=np.float64)
+        dlog = np.zeros([B, S, 7, M], dtype=self.float_type) if grad else None
+        _check(
+            self._lib.phb_loglik_host(
+                self._handle, _ptr(pa), _ptr(inds), B, S, int(grad), _ptr(ll), _ptr(dlog) if grad else None
+            )
+        )
+        return (ll, dlog) if grad else ll
+
+    def evaluate_shared(self, params6: np.ndarray, pi: np.ndarray, inds: np.ndarray, grad: bool):
+        """params6 [B, 6, M] shared by the S chunks of a particle, pi [B, S, M] or [B, M]."""
+        M = self._M
+        B = params6.shape[0]
+        S = inds.shape[0]
+        assert params6.shape == (B, 6, M)
+        assert pi.shape in ((B, S, M), (B, M))
+        assert np.all(0 <= inds) & np.all(inds < self._N)
+        assert np.isfinite(params6).all() and np.isfinite(pi).all(), "not all parameters finite"
+        params6 = np.ascontiguousarray(params6, dtype=self.float_type)
+        pi_c = np.ascontiguousarray(pi, dtype=self.float_type)
+        inds = np.ascontiguousarray(inds, dtype=np.int64)
+        ll = np.zeros([B, S], dtype=np.float64)
+        dlog = np.zeros([B, S, 7, M], dtype=self.float_type) if grad else None
+        _check(
+            self._lib.phb_loglik_shared_host(
+                self._handle, _ptr(params6), _ptr(pi_c), int(pi.ndim == 3), _ptr(inds), B, S, int(grad),
+                _ptr(ll), _ptr(dlog) if grad else None,
+            )
+        )
+        return (ll, dlog) if grad else ll
+
+    # ---- device-resident entry (torch tensors are only used as device buffers here)
+    def evaluate_device(self, params6, pi, inds, grad: bool, ll=None, dlog=None, stream=None):
+        """Asynchronous evaluation on device buffers (torch CUDA tensors on this kernel's device).
+        params6: [B, 6, M] (shared across chunks) or [B, S, 6, M]; pi: [B, M] or [B, S, M];
+        inds: int64 [S].  Returns (ll [B, S] float64, dlog [B, S, 7, M] or None)."""
+        import torch
+
+        M = self._M
+        S = int(inds.shape[0])
+        B = int(params6.shape[0])
+        tdtype = torch.float64 if self.double_precision else torch.float32
+        assert params6.is_cuda and pi.is_cuda and inds.is_cuda and params6.device.index == self.device
+        assert params6.dtype == tdtype and pi.dtype == tdtype and inds.dtype == torch.int64
+        assert params6.is_contiguous() and pi.is_contiguous() and inds.is_contiguous()
+        if params6.dim() == 3:
+            assert params6.shape == (B, 6, M)
+            ps_b, ps_s = 6 * M, 0
+        else:
+            assert params6.shape == (B, S, 6, M)
+            ps_b, ps_s = S * 6 * M, 6 * M
+        if pi.dim() == 2:
+            assert pi.shape == (B, M)
+            pis_b, pis_s = M, 0
+        else:
+            assert pi.shape == (B, S, M)
+            pis_b, pis_s = S * M, M
+        if ll is None:
+            ll = torch.empty((B, S), dtype=torch.float64, device=params6.device)
+        if grad and dlog is None:
+            dlog = torch.empty((B, S, 7, M), dtype=tdtype, device=params6.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(params6.device).cuda_stream
+        _check(
+            self._lib.phb_loglik_device(
+                self._handle, params6.data_ptr(), ps_b, ps_s, pi.data_ptr(), pis_b, pis_s, inds.data_ptr(),
+                B, S, int(grad), ll.data_ptr(), dlog.data_ptr() if grad else None, ctypes.c_void_p(stream),
+            )
+        )
+        return ll, (dlog if grad else None)
+
+    def sync(self) -> None:
+        _check(self._lib.phb_sync(self._handle))
+
+
+def _normalise_call(pp: PSMCParams, index, M: int):
+    """Bring (pp, index) to pa [B, S, 7, M], inds [S] the way the reference does
+    (gpu.py:186-213) and remember which axes were added."""
+    pa = np.stack([np.asarray(a) for a in pp], -2)
+    index = np.asarray(index)
+    assert index.ndim in (0, 1)
+    inds = np.atleast_1d(index)
+    added_S = False
+    if index.ndim == 0:
+        added_S = True
+        assert pa.shape == (7, M)
+        pa = pa[None]
+    S = inds.shape[0]
+    added_B = False
+    if pa.ndim == 2:
+        assert pa.shape == (7, M)
+        pa = np.repeat(pa[None, None], S, axis=1)
+        added_B = True
+    if pa.ndim == 3:
+        assert pa.shape == (S, 7, M)
+        pa = pa[None]
+        added_B = True
+    assert pa.ndim == 4
+    assert pa.shape[1:] == (S, 7, M)
+    return pa, inds, added_B, added_S
+
+
+class PSMCKernel:
+    """Evaluate the PSMC HMM log-likelihood (and gradient) of rows of ``data`` on B200 GPUs.
+
+    Args (same as the reference, gpu.py:328-351):
+        - M: discretization level (4, 8, 16, 32 or 64; the reference supports 16).
+        - data: int8 data matrix [N, L], -1 = missing.
+        - double_precision: if True, use float64 on the GPU.
+        - num_gpus: number of devices to spread the chunk axis over (default: all visible).
+    """
+
+    def __init__(self, M, data, double_precision=False, num_gpus: int = None):
+        if num_gpus is not None:
+            assert num_gpus > 0
+        self.double_precision = bool(double_precision)
+        self.M = int(M)
+        n = _native.lib().phb_device_count()
+        if n <= 0:
+            raise CudaError(_native.last_error() or "no CUDA device is visible")
+        if num_gpus is not None:
+            n = min(num_gpus, n)
+        self.devices = list(range(n))
+        self.gpu_kernels = [_PSMCKernelBase(M, data, double_precision, device=d) for d in self.devices]
+        self._pool = ThreadPoolExecutor(max_workers=n) if n > 1 else None
+
+    @property
+    def float_type(self):
+        return np.float64 if self.double_precision else np.float32
+
+    def set_threads_per_pair(self, t: int) -> None:
+        for k in self.gpu_kernels:
+            k.set_threads_per_pair(t)
+
+    def loglik(self, pp: PSMCParams, index):
+        """Log-likelihood of data[index] (reference: gpu.py:359-362; there it is the
+        JAX-differentiable scalar, here the value - use ``__call__(..., grad=True)`` for the
+        gradient that the reference's custom_vjp consumes)."""
+        return self(pp, index, grad=False)
+
+    def __call__(self, pp: PSMCParams, index, grad: bool):
+        for a in pp:
+            assert np.isfinite(a).all()
+        pa, inds, added_B, added_S = _normalise_call(pp, index, self.M)
+        D = len(self.gpu_kernels)
+        if D == 1 or inds.shape[0] < D:
+            res = self.gpu_kernels[0].evaluate(pa, inds, grad)
+        else:
+            parts = np.array_split(np.arange(inds.shape[0]), D)
+            futs = [
+                self._pool.submit(kern.evaluate, pa[:, sel], inds[sel], grad)
+                for kern, sel in zip(self.gpu_kernels, parts)
+            ]
+            outs = [f.result() for f in futs]
+            if grad:
+                res = (np.concatenate([o[0] for o in outs], 1), np.concatenate([o[1] for o in outs], 1))
+            else:
+                res = np.concatenate(outs, 1)
+        if grad:
+            ll, dlog = res
+            ret = (ll, PSMCParams.from_block(dlog))
+        else:
+            ret = res
+
+        def strip(a):
+            if added_B and added_S:
+                return a[0, 0, ...]
+            if added_B:
+                return a[0, ...]
+            if added_S:
+                return a[:, 0, ...]
+            return a
+
+        if grad:
+            return strip(ret[0]), PSMCParams(*(strip(a) for a in ret[1]))
+        return strip(ret)

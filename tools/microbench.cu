@@ -1,0 +1,188 @@
+// Pipe-rate microbenchmarks for B200 (sm_100a): the FP32 FMA peak this project's roofline is
+// quoted against is not in MEASURED_PEAKS.json, so it is measured here, together with the rates
+// that decide the lane layout of the HMM kernel (warp shuffles, broadcast shared-memory loads).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench tools/microbench.cu
+// Output: one JSON object on stdout.
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#define CHECK(x)                                                                  \
+    do {                                                                          \
+        cudaError_t e = (x);                                                      \
+        if (e != cudaSuccess) {                                                   \
+            fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e));               \
+            return 1;                                                             \
+        }                                                                         \
+    } while (0)
+
+__device__ __forceinline__ float4 lds128(const void *p) {
+    float4 v;
+    unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(p));
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+
+constexpr int kIters = 4096;
+constexpr int kChains = 16;
+
+// a_i = a_i * b + c : b, c shared by all chains (2 of 3 operands repeat; reuse cache can help)
+__global__ void ffma_shared_operands(float *out, float b, float c) {
+    float a[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) a[i] = threadIdx.x * 1e-3f + i;
+    for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) a[i] = fmaf(a[i], b, c);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) s += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// a_i = a_i * b_i + c_i : three distinct registers per FMA
+__global__ void ffma_distinct_operands(float *out, const float *in) {
+    float a[kChains], b[kChains], c[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) {
+        a[i] = threadIdx.x * 1e-3f + i;
+        b[i] = in[i];
+        c[i] = in[kChains + i];
+    }
+    for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) a[i] = fmaf(a[i], b[i], c[i]);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) s += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// acc_i += x_i * y_i with x, y changing: the accumulate pattern of the gradient sums
+__global__ void ffma_accumulate(float *out, const float *in) {
+    float acc[kChains], x[kChains], y[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) {
+        acc[i] = 0.f;
+        x[i] = in[i] + threadIdx.x * 1e-6f;
+        y[i] = in[kChains + i];
+    }
+    for (int it = 0; it < kIters / 2; ++it) {
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) acc[i] = fmaf(x[i], y[i], acc[i]);
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) x[i] = fmaf(y[i], 0.999f, x[i]);  // immediate-operand form
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) s += acc[i] + x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void shfl_rate(float *out) {
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = threadIdx.x + i;
+    for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = __shfl_xor_sync(0xffffffffu, a[i], 1);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// broadcast LDS.128 (all lanes read the same 16 bytes) feeding FMAs
+__global__ void lds_broadcast_rate(float *out) {
+    __shared__ float4 tab[64];
+    if (threadIdx.x < 64) tab[threadIdx.x] = make_float4(1.f, 0.5f, 0.25f, 0.125f);
+    __syncthreads();
+    float acc[4] = {0, 0, 0, 0};
+    for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            float4 v = lds128(&tab[(it + i) & 63]);
+            acc[0] += v.x;
+            acc[1] += v.y;
+            acc[2] += v.z;
+            acc[3] += v.w;
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc[0] + acc[1] + acc[2] + acc[3];
+}
+
+// per-lane LDS.128 (each lane its own 16 bytes, conflict-free)
+__global__ void lds_private_rate(float *out) {
+    extern __shared__ float4 buf[];
+    for (int i = threadIdx.x; i < 8 * blockDim.x; i += blockDim.x) buf[i] = make_float4(1.f, 0.5f, 0.25f, 0.125f);
+    __syncthreads();
+    float acc[4] = {0, 0, 0, 0};
+    for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float4 v = lds128(&buf[i * blockDim.x + threadIdx.x]);
+            acc[0] += v.x;
+            acc[1] += v.y;
+            acc[2] += v.z;
+            acc[3] += v.w;
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc[0] + acc[1] + acc[2] + acc[3];
+}
+
+template <typename Launch> float time_ms(Launch launch, int reps) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int i = 0; i < 3; ++i) launch();
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int r = 0; r < reps; ++r) {
+        cudaEventRecord(e0);
+        launch();
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        best = ms < best ? ms : best;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return best;
+}
+
+int main() {
+    cudaDeviceProp prop;
+    CHECK(cudaGetDeviceProperties(&prop, 0));
+    const int sms = prop.multiProcessorCount;
+    const int threads = 256, ctas = sms * 8;
+    float *out, *in;
+    CHECK(cudaMalloc(&out, sizeof(float) * threads * ctas));
+    CHECK(cudaMalloc(&in, sizeof(float) * 64));
+    float h[64];
+    for (int i = 0; i < 64; ++i) h[i] = 0.5f + 1e-3f * i;
+    CHECK(cudaMemcpy(in, h, sizeof h, cudaMemcpyHostToDevice));
+    const double lanes = double(threads) * ctas;
+    const double fma_ops = lanes * kIters * kChains;
+    float t1 = time_ms([&] { ffma_shared_operands<<<ctas, threads>>>(out, 0.999f, 1e-3f); }, 10);
+    float t2 = time_ms([&] { ffma_distinct_operands<<<ctas, threads>>>(out, in); }, 10);
+    float t3 = time_ms([&] { ffma_accumulate<<<ctas, threads>>>(out, in); }, 10);
+    float t4 = time_ms([&] { shfl_rate<<<ctas, threads>>>(out); }, 10);
+    float t5 = time_ms([&] { lds_broadcast_rate<<<ctas, threads>>>(out); }, 10);
+    CHECK(cudaFuncSetAttribute(lds_private_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * threads * 16));
+    float t6 = time_ms([&] { lds_private_rate<<<ctas, threads, 8 * threads * 16>>>(out); }, 10);
+    CHECK(cudaGetLastError());
+    int clock_khz = 0;
+    cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, 0);
+    printf("{\"device\": \"%s\", \"sms\": %d, \"clock_khz_attr\": %d,\n", prop.name, sms, clock_khz);
+    printf(" \"ffma_shared_operands_tflops\": %.2f,\n", 2 * fma_ops / (t1 * 1e-3) / 1e12);
+    printf(" \"ffma_distinct_operands_tflops\": %.2f,\n", 2 * fma_ops / (t2 * 1e-3) / 1e12);
+    printf(" \"ffma_accumulate_mix_tflops\": %.2f,\n", 2 * fma_ops / (t3 * 1e-3) / 1e12);
+    printf(" \"shfl_warp_instr_per_sec\": %.4g,\n", lanes / 32 * kIters * 8 / (t4 * 1e-3));
+    printf(" \"shfl_warp_instr_per_clk_per_sm_at_1965MHz\": %.3f,\n", lanes / 32 * kIters * 8 / (t4 * 1e-3) / sms / 1.965e9);
+    printf(" \"lds128_broadcast_warp_instr_per_clk_per_sm_at_1965MHz\": %.3f,\n", lanes / 32 * kIters * 16 / (t5 * 1e-3) / sms / 1.965e9);
+    printf(" \"lds128_private_warp_instr_per_clk_per_sm_at_1965MHz\": %.3f}\n", lanes / 32 * kIters * 8 / (t6 * 1e-3) / sms / 1.965e9);
+    return 0;
+}
