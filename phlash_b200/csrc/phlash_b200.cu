@@ -62,15 +62,12 @@ struct DeviceBuffer {
     }
 };
 
-using LaunchFn = int (*)(phb_kernel *, const phb::KernelArgs &, int n_slots_needed, cudaStream_t);
-
 struct Variant {
     int M, T, K;
     bool dbl, grad;
     const void *func;
-    size_t smem_fixed;      // bytes excluding parameter slots
-    size_t smem_per_slot;   // bytes per parameter slot
-    int64_t ckpt_bytes_per_site_block;  // sizeof(F) * MT * kThreads
+    size_t smem;                                  // dynamic shared memory per CTA
+    int64_t (*ckpt_bytes_per_warp)(int64_t L);    // checkpoint scratch per resident warp
 };
 
 }  // namespace
@@ -102,62 +99,77 @@ template <typename F, int MT, int T, int K, bool GRAD, int MINB> Variant make_va
     v.dbl = sizeof(F) == 8;
     v.grad = GRAD;
     v.func = reinterpret_cast<const void *>(&phb::psmc_loglik_kernel<F, MT, T, K, GRAD, MINB>);
-    v.smem_fixed = phb::smem_bytes<F, MT, T, K>(0);
-    v.smem_per_slot = sizeof(F) * phb::Slot<MT * T>::kStride;
-    v.ckpt_bytes_per_site_block = int64_t(sizeof(F)) * MT * phb::kThreads;
+    v.smem = phb::smem_bytes<F, MT, K>();
+    v.ckpt_bytes_per_warp = [](int64_t L) { return phb::ckpt_bytes_per_warp<F, MT, K>(L); };
     return v;
 }
 
-// Every (precision, M, threads-per-pair) combination that is compiled.  Within one (precision, M)
-// the entries are ordered by increasing T; the dispatcher takes the first one that fills the GPU.
+// Every (precision, M, threads-per-pair) combination that is compiled.  Within one
+// (precision, M, grad) the entries are ordered by increasing T; the dispatcher takes the first
+// one that fills the GPU.  The gradient kernel keeps 6*MT parameters and 6*MT accumulators in
+// registers, so it is built for MT <= 8; the forward-only kernel also for MT = 16.
 const std::vector<Variant> &variants() {
     static const std::vector<Variant> table = [] {
         std::vector<Variant> t;
-#define PHB_BOTH(F, MT, T, K, MINB)                       \
-    t.push_back(make_variant<F, MT, T, K, true, MINB>()); \
-    t.push_back(make_variant<F, MT, T, K, false, MINB>());
-        // float
-        PHB_BOTH(float, 4, 1, 16, 4)    // M = 4
-        PHB_BOTH(float, 8, 1, 16, 4)    // M = 8
-        PHB_BOTH(float, 4, 2, 16, 4)
-        PHB_BOTH(float, 16, 1, 8, 2)    // M = 16
-        PHB_BOTH(float, 8, 2, 16, 3)
-        PHB_BOTH(float, 4, 4, 16, 4)
-        PHB_BOTH(float, 16, 2, 8, 2)    // M = 32
-        PHB_BOTH(float, 8, 4, 16, 3)
-        PHB_BOTH(float, 4, 8, 16, 4)
-        PHB_BOTH(float, 16, 4, 8, 2)    // M = 64
-        PHB_BOTH(float, 8, 8, 16, 3)
-        PHB_BOTH(float, 4, 16, 16, 4)
-        // double
-        PHB_BOTH(double, 4, 1, 8, 3)    // M = 4
-        PHB_BOTH(double, 8, 1, 8, 2)    // M = 8
-        PHB_BOTH(double, 4, 2, 8, 3)
-        PHB_BOTH(double, 8, 2, 8, 2)    // M = 16
-        PHB_BOTH(double, 4, 4, 8, 3)
-        PHB_BOTH(double, 8, 4, 8, 2)    // M = 32
-        PHB_BOTH(double, 4, 8, 8, 2)
-        PHB_BOTH(double, 8, 8, 8, 2)    // M = 64
-        PHB_BOTH(double, 4, 16, 8, 2)
-#undef PHB_BOTH
+#define PHB_GRAD(F, MT, T, K, MINB) t.push_back(make_variant<F, MT, T, K, true, MINB>());
+#define PHB_FWD(F, MT, T, K, MINB) t.push_back(make_variant<F, MT, T, K, false, MINB>());
+        // ---- float, loglik + grad
+        PHB_GRAD(float, 4, 1, 16, 4)   // M = 4
+        PHB_GRAD(float, 8, 1, 16, 3)   // M = 8
+        PHB_GRAD(float, 4, 2, 16, 4)
+        PHB_GRAD(float, 8, 2, 16, 3)   // M = 16
+        PHB_GRAD(float, 4, 4, 16, 4)
+        PHB_GRAD(float, 8, 4, 16, 3)   // M = 32
+        PHB_GRAD(float, 4, 8, 16, 4)
+        PHB_GRAD(float, 8, 8, 16, 3)   // M = 64
+        PHB_GRAD(float, 4, 16, 16, 4)
+        // ---- float, forward only
+        PHB_FWD(float, 4, 1, 16, 4)    // M = 4
+        PHB_FWD(float, 8, 1, 16, 4)    // M = 8
+        PHB_FWD(float, 4, 2, 16, 4)
+        PHB_FWD(float, 16, 1, 8, 3)    // M = 16
+        PHB_FWD(float, 8, 2, 16, 4)
+        PHB_FWD(float, 4, 4, 16, 4)
+        PHB_FWD(float, 16, 2, 8, 3)    // M = 32
+        PHB_FWD(float, 8, 4, 16, 4)
+        PHB_FWD(float, 4, 8, 16, 4)
+        PHB_FWD(float, 16, 4, 8, 3)    // M = 64
+        PHB_FWD(float, 8, 8, 16, 4)
+        PHB_FWD(float, 4, 16, 16, 4)
+        // ---- double, loglik + grad
+        PHB_GRAD(double, 4, 1, 8, 2)   // M = 4
+        PHB_GRAD(double, 4, 2, 8, 2)   // M = 8
+        PHB_GRAD(double, 4, 4, 8, 2)   // M = 16
+        PHB_GRAD(double, 4, 8, 8, 2)   // M = 32
+        PHB_GRAD(double, 4, 16, 8, 2)  // M = 64
+        // ---- double, forward only
+        PHB_FWD(double, 4, 1, 8, 3)    // M = 4
+        PHB_FWD(double, 8, 1, 8, 3)    // M = 8
+        PHB_FWD(double, 4, 2, 8, 3)
+        PHB_FWD(double, 8, 2, 8, 3)    // M = 16
+        PHB_FWD(double, 4, 4, 8, 3)
+        PHB_FWD(double, 8, 4, 8, 3)    // M = 32
+        PHB_FWD(double, 4, 8, 8, 3)
+        PHB_FWD(double, 8, 8, 8, 3)    // M = 64
+        PHB_FWD(double, 4, 16, 8, 3)
+#undef PHB_GRAD
+#undef PHB_FWD
         return t;
     }();
     return table;
 }
 
 const Variant *pick_variant(const phb_kernel *k, bool grad, int64_t n_pairs) {
-    const Variant *last = nullptr;
+    const Variant *last = nullptr, *forced = nullptr, *first_fill = nullptr;
     const int64_t fill = int64_t(k->num_sms) * 2 * phb::kThreads;
     for (const Variant &v : variants()) {
         if (v.M != k->M || v.dbl != (k->dbl != 0) || v.grad != grad) continue;
-        if (k->force_T > 0) {
-            if (v.T == k->force_T) return &v;
-            continue;
-        }
+        if (v.T == k->force_T) forced = &v;
         last = &v;
-        if (n_pairs * v.T >= fill) return &v;
+        if (!first_fill && n_pairs * v.T >= fill) first_fill = &v;
     }
-    return last;
+    if (forced) return forced;  // a forced T that is not compiled for this path falls back to auto
+    return first_fill ? first_fill : last;
 }
 
 int check_handle(const phb_kernel *k) {
@@ -173,20 +185,14 @@ int launch(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream) {
     if (!v) return fail(PHB_E_INVALID, "no kernel variant for M=%d, threads_per_pair=%d", k->M, k->force_T);
     const int pairs_per_cta = phb::kThreads / v->T;
     a.n_groups = (n_pairs + pairs_per_cta - 1) / pairs_per_cta;
-    // parameter slots: one per pair, or - when the 6 rows are shared by the chunks of a particle -
-    // one per particle that a CTA's pairs can touch
-    int64_t slots = pairs_per_cta;
-    if (a.pstride_s == 0) slots = std::min<int64_t>(pairs_per_cta, (pairs_per_cta - 1) / a.S + 2);
-    a.n_slots = int(slots);
-    const size_t smem = v->smem_fixed + v->smem_per_slot * size_t(slots);
+    const size_t smem = v->smem;
     PHB_CUDA(cudaFuncSetAttribute(v->func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int occ = 0;
     PHB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v->func, phb::kThreads, smem));
     if (occ < 1) return fail(PHB_E_CUDA, "kernel does not fit on an SM (smem %zu bytes)", smem);
     const int64_t grid = std::min<int64_t>(a.n_groups, int64_t(occ) * k->num_sms);
     if (grad) {
-        const int64_t n_seg = (a.L + v->K - 1) / v->K;
-        const size_t need = size_t(grid) * size_t(n_seg) * size_t(v->ckpt_bytes_per_site_block);
+        const size_t need = size_t(grid) * phb::kWarps * size_t(v->ckpt_bytes_per_warp(a.L));
         int rc = k->ckpt.reserve(need);
         if (rc != PHB_OK) return rc;
         a.ckpt = k->ckpt.ptr;

@@ -5,22 +5,26 @@
 // and the gradient contract of the reference's loglik_grad kernel (gpu.py:575-692, host roll
 // :303-313).  How it is computed is new:
 //
-//  * thread-per-pair (T = 1) or T lanes per pair, each lane holding MT = M / T consecutive
-//    states of the forward vector in registers.  The prefix / suffix sums of the structured
-//    transition are serial FMA chains inside a lane, stitched across the T lanes of a pair with
-//    log2(T) shuffles.  The lanes of a warp are different chunks of (normally) the same
-//    particle, so the parameter block is read from shared memory as broadcast 128-bit loads.
+//  * T lanes cooperate on one (chunk, particle) pair; each lane owns MT = M / T consecutive hidden
+//    states and keeps its slice of the forward vector AND of the six parameter rows in registers
+//    for the whole chunk.  The prefix / suffix sums of the structured transition are serial FMA
+//    chains inside a lane; lane totals are combined across the T lanes with a few shuffles
+//    ("totals first": reduce, shuffle, then run the chains starting from the offsets).
+//    (v1 of this kernel streamed the parameters from shared memory with broadcast LDS.128; on
+//    B200 that is bound by the ~0.4 LDS.128/clk/SM register-fill rate - see profiles/.)
 //  * the gradient is the adjoint (backward) recursion, O(M) per site instead of the reference's
 //    O(7 M^2) forward-mode sensitivities.  The forward vectors it needs are not kept for the whole
 //    chunk: pass 1 stores a checkpoint every K sites to HBM (4*M/K bytes per site and pair);
 //    pass 2 walks the segments backwards, re-runs the K forward steps of a segment into a
-//    shared-memory ring private to the thread, then runs the K adjoint steps, accumulating
-//    d ll / d (b, d, u, v, emis0, emis1) in registers.
-//  * persistent grid: one CTA slot per resident CTA, looping over groups of pairs; checkpoint
-//    scratch is indexed by CTA slot, so its size depends on the GPU, not on the problem.
+//    shared-memory ring private to the lane (conflict-free 128-bit accesses), then runs the K
+//    adjoint steps, accumulating d ll / d (b, d, u, v, emis0, emis1) in registers.
+//  * persistent grid: every resident CTA loops over groups of 128 / T pairs; the warps of a CTA
+//    never synchronise (no block-level barrier anywhere).  Checkpoint scratch is indexed by warp slot, so its
+//    size depends on the GPU, not on the problem.
 //
-// Per site and pair (M = 16): ~7.5 M forward + 7.5 M recompute + 16 M adjoint FMA-pipe
-// instructions, 1 B of observations, 2 * 4 * M / K B of checkpoint traffic.
+// Per site and pair: ~9 M FMA-pipe instructions forward (twice with the recompute) and ~20 M for
+// the adjoint step, 1 B of observations, 2 * 4 * M / K B of checkpoint traffic,
+// 2 * 4 * (M + 1) B of shared-memory traffic.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -29,6 +33,7 @@
 namespace phb {
 
 constexpr int kThreads = 128;  // threads per CTA
+constexpr int kWarps = kThreads / 32;
 
 struct KernelArgs {
     const int8_t *data;  // [N, pitch]
@@ -44,9 +49,8 @@ struct KernelArgs {
     double *ll;          // [B, S]
     void *dlog;          // [B, S, 7, M] or nullptr
     void *alpha_out;     // [B, S, M] filtered distribution after the last site, or nullptr
-    void *ckpt;          // checkpoint scratch: gridDim.x * n_seg * M/T... see ckpt_elems()
+    void *ckpt;          // checkpoint scratch, see ckpt_bytes_per_warp()
     int64_t n_groups;    // ceil(B*S / pairs-per-CTA)
-    int n_slots;         // parameter slots in shared memory per CTA
     int *err_flag;       // bit 0: index out of range, bit 1: non-finite result
 };
 
@@ -70,31 +74,39 @@ __device__ __forceinline__ float4 pack(const float *o) { return make_float4(o[0]
 __device__ __forceinline__ double2 pack(const double *o) { return make_double2(o[0], o[1]); }
 
 // ---- sums across the T lanes that share a pair (lane index inside the pair = sub) ----
+// sum of `mine` over the lanes with a smaller sub
 template <typename F, int T> __device__ __forceinline__ F lanes_before(F mine, int sub) {
     if constexpr (T == 1) {
         return F(0);
+    } else if constexpr (T == 2) {
+        const F other = __shfl_xor_sync(0xffffffffu, mine, 1, T);
+        return sub == 0 ? F(0) : other;
     } else {
         F incl = mine;
 #pragma unroll
         for (int o = 1; o < T; o <<= 1) {
-            F t = __shfl_up_sync(0xffffffffu, incl, o, T);
+            const F t = __shfl_up_sync(0xffffffffu, incl, o, T);
             if (sub >= o) incl += t;
         }
-        F ex = __shfl_up_sync(0xffffffffu, incl, 1, T);
+        const F ex = __shfl_up_sync(0xffffffffu, incl, 1, T);
         return sub == 0 ? F(0) : ex;
     }
 }
+// sum of `mine` over the lanes with a larger sub
 template <typename F, int T> __device__ __forceinline__ F lanes_after(F mine, int sub) {
     if constexpr (T == 1) {
         return F(0);
+    } else if constexpr (T == 2) {
+        const F other = __shfl_xor_sync(0xffffffffu, mine, 1, T);
+        return sub == 0 ? other : F(0);
     } else {
         F incl = mine;
 #pragma unroll
         for (int o = 1; o < T; o <<= 1) {
-            F t = __shfl_down_sync(0xffffffffu, incl, o, T);
+            const F t = __shfl_down_sync(0xffffffffu, incl, o, T);
             if (sub + o < T) incl += t;
         }
-        F ex = __shfl_down_sync(0xffffffffu, incl, 1, T);
+        const F ex = __shfl_down_sync(0xffffffffu, incl, 1, T);
         return sub == T - 1 ? F(0) : ex;
     }
 }
@@ -111,64 +123,114 @@ template <typename F> __device__ __forceinline__ F log2_of(F x);
 template <> __device__ __forceinline__ float log2_of<float>(float x) { return log2f(x); }
 template <> __device__ __forceinline__ double log2_of<double>(double x) { return log2(x); }
 
-// Shared-memory image of one parameter slot: rows b, d, u, v, emis0, emis1, ones (7 * M values,
-// the last three double as the emission look-up table indexed by the observation), padded so that
-// different slots start in different banks.
-template <int M> struct Slot {
-    static constexpr int kRowB = 0, kRowD = M, kRowU = 2 * M, kRowV = 3 * M, kRowE = 4 * M;
-    static constexpr int kStride = 7 * M + 4;
+// This lane's slice of the six parameter rows, register resident.
+template <typename F, int MT> struct Params {
+    F b[MT], d[MT], u[MT], v[MT], e0[MT], e1[MT];
+    __device__ __forceinline__ void load(const F *__restrict__ src, int M) {
+#pragma unroll
+        for (int k = 0; k < MT; ++k) {
+            b[k] = src[0 * M + k];
+            d[k] = src[1 * M + k];
+            u[k] = src[2 * M + k];
+            v[k] = src[3 * M + k];
+            e0[k] = src[4 * M + k];
+            e1[k] = src[5 * M + k];
+        }
+    }
 };
 
-// One forward step for this lane's MT states: x <- (x A) .* emis(ob), returns sum over the pair.
-template <typename F, int MT, int T>
-__device__ __forceinline__ F forward_site(F (&x)[MT], const F *__restrict__ prm, int ob_row, int sub) {
-    constexpr int M = MT * T;
-    using V = typename Vec<F>::type;
-    constexpr int W = Vec<F>::W;
-    F pre[MT], suf[MT];
-    F run = F(0);
+// T == 2 only.  The lower lane of a pair needs the upper lane's totals of (x, v.*w) as suffix
+// offsets; the upper lane needs the lower lane's totals of (u.*x, b.*w) as prefix offsets.  Each
+// lane therefore only has to PRODUCE the two totals its partner consumes: one FMA chain per vector
+// with lane-dependent coefficients, one shuffle each (instead of two chains and two shuffles).
+template <typename F, int MT, int T, bool GRAD> struct PartnerCoef {
+    __device__ __forceinline__ void init(const Params<F, MT> &, int) {}
+};
+template <typename F, int MT> struct PartnerCoef<F, MT, 2, false> {
+    F cx[MT];  // sub 0: u (partner wants sum u.*x);  sub 1: 1 (partner wants sum x)
+    __device__ __forceinline__ void init(const Params<F, MT> &p, int sub) {
 #pragma unroll
-    for (int q = 0; q < MT / W; ++q) {
-        F u[W];
-        unpack<F>(*reinterpret_cast<const V *>(prm + Slot<M>::kRowU + q * W), u);
+        for (int k = 0; k < MT; ++k) cx[k] = sub == 0 ? p.u[k] : F(1);
+    }
+};
+template <typename F, int MT> struct PartnerCoef<F, MT, 2, true> {
+    F cx[MT];  // as above
+    F cw[MT];  // sub 0: b (partner wants sum b.*w);  sub 1: v (partner wants sum v.*w)
+    __device__ __forceinline__ void init(const Params<F, MT> &p, int sub) {
 #pragma unroll
-        for (int r = 0; r < W; ++r) {
-            pre[q * W + r] = run;
-            run = fma(u[r], x[q * W + r], run);
+        for (int k = 0; k < MT; ++k) {
+            cx[k] = sub == 0 ? p.u[k] : F(1);
+            cw[k] = sub == 0 ? p.b[k] : p.v[k];
         }
     }
-    F tail = F(0);
+};
+
+// Branch-free choice of the emission probability.  Written as bit arithmetic (two LOP3 on the
+// otherwise idle integer pipe) because the obvious ternary is compiled into one divergent branch
+// per state, which serialises the warp: the lanes of a warp hold different chunks.
+struct ObsMask {
+    uint32_t is0, is1;  // all-ones when the observation is 0 / is 1; both zero when it is missing
+    __device__ __forceinline__ explicit ObsMask(int ob) : is0(ob == 0 ? 0xffffffffu : 0u), is1(ob == 1 ? 0xffffffffu : 0u) {}
+};
+__device__ __forceinline__ float bit_select(uint32_t mask, float a, float b) {
+    return __uint_as_float((__float_as_uint(a) & mask) | (__float_as_uint(b) & ~mask));
+}
+__device__ __forceinline__ double bit_select(uint32_t mask, double a, double b) {
+    const uint64_t m = (uint64_t(mask) << 32) | mask;
+    return __longlong_as_double((__double_as_longlong(a) & m) | (__double_as_longlong(b) & ~m));
+}
+// emission probability of the observation behind `m` in state k (missing -> 1)
+template <typename F, int MT> __device__ __forceinline__ F emis(const Params<F, MT> &p, int k, const ObsMask &m) {
+    return bit_select(m.is0, p.e0[k], bit_select(m.is1, p.e1[k], F(1)));
+}
+
+// One forward step for this lane's MT states: x <- (x A) .* emis(ob).  No rescaling here: the
+// callers renormalise every kNorm sites (lazy scaling), which is exact for the log-likelihood and
+// the gradient as long as the bookkeeping uses the same factors.
+template <typename F, int MT, int T, bool GRAD>
+__device__ __forceinline__ void forward_site(F (&x)[MT], const Params<F, MT> &p, const PartnerCoef<F, MT, T, GRAD> &pc,
+                                             int ob, int sub) {
+    const ObsMask om(ob);
+    F pre_run = F(0), suf_run = F(0);
+    if constexpr (T == 2) {
+        F t[2] = {F(0), F(0)};
+#pragma unroll
+        for (int k = 0; k < MT; ++k) t[k & 1] = fma(pc.cx[k], x[k], t[k & 1]);
+        const F other = __shfl_xor_sync(0xffffffffu, t[0] + t[1], 1, 2);
+        pre_run = sub == 0 ? F(0) : other;
+        suf_run = sub == 0 ? other : F(0);
+    } else if constexpr (T > 2) {
+        F tu[2] = {F(0), F(0)}, tx[2] = {F(0), F(0)};
+#pragma unroll
+        for (int k = 0; k < MT; ++k) {
+            tu[k & 1] = fma(p.u[k], x[k], tu[k & 1]);
+            tx[k & 1] += x[k];
+        }
+        pre_run = lanes_before<F, T>(tu[0] + tu[1], sub);
+        suf_run = lanes_after<F, T>(tx[0] + tx[1], sub);
+    }
+    F suf[MT];
 #pragma unroll
     for (int k = MT - 1; k >= 0; --k) {
-        suf[k] = tail;
-        tail += x[k];
+        suf[k] = suf_run;
+        suf_run += x[k];
     }
-    const F pre_off = lanes_before<F, T>(run, sub);
-    const F suf_off = lanes_after<F, T>(tail, sub);
+#pragma unroll
+    for (int k = 0; k < MT; ++k) {
+        const F xk = x[k];
+        F o = p.d[k] * xk;
+        o = fma(p.v[k], pre_run, o);
+        o = fma(p.b[k], suf[k], o);
+        pre_run = fma(p.u[k], xk, pre_run);
+        x[k] = o * emis(p, k, om);
+    }
+}
+
+// sum of x over the whole pair
+template <typename F, int MT, int T> __device__ __forceinline__ F pair_sum(const F (&x)[MT]) {
     F part[4] = {F(0), F(0), F(0), F(0)};
 #pragma unroll
-    for (int q = 0; q < MT / W; ++q) {
-        F d[W], v[W], b[W], e[W];
-        unpack<F>(*reinterpret_cast<const V *>(prm + Slot<M>::kRowD + q * W), d);
-        unpack<F>(*reinterpret_cast<const V *>(prm + Slot<M>::kRowV + q * W), v);
-        unpack<F>(*reinterpret_cast<const V *>(prm + Slot<M>::kRowB + q * W), b);
-        unpack<F>(*reinterpret_cast<const V *>(prm + Slot<M>::kRowE + ob_row * M + q * W), e);
-#pragma unroll
-        for (int r = 0; r < W; ++r) {
-            const int k = q * W + r;
-            F o = d[r] * x[k];
-            if constexpr (T == 1) {
-                o = fma(v[r], pre[k], o);
-                o = fma(b[r], suf[k], o);
-            } else {
-                o = fma(v[r], pre[k] + pre_off, o);
-                o = fma(b[r], suf[k] + suf_off, o);
-            }
-            o *= e[r];
-            x[k] = o;
-            part[k & 3] += o;
-        }
-    }
+    for (int k = 0; k < MT; ++k) part[k & 3] += x[k];
     return lanes_total<F, T>((part[0] + part[1]) + (part[2] + part[3]));
 }
 
@@ -195,115 +257,74 @@ __device__ __forceinline__ void posterior_to_emission(const F (&beta)[MT], const
     }
 }
 
-// One adjoint step for site t.  On entry beta is the adjoint vector after site t (normalised so
-// that beta . alpha_t == 1); x = forward vector before the site (alpha_{t-1}); inv_c = 1 / (forward
-// normaliser of the site).  On exit beta is the adjoint vector before the site (beta . x == 1), and
-// the posterior x .* beta of site t-1 has been added to the emission row of ob_prev (the
-// observation at site t-1; pass -1 when there is none).
+// One adjoint step for site t.  Invariant: beta . alpha == 1 at every site, where alpha is the
+// (lazily scaled) forward vector the forward passes actually carried.  On entry beta belongs to
+// "after site t" (the caller has already multiplied it by the factor the forward pass applied to
+// its vector right after this site, if any); x = forward vector before the site.  On exit beta
+// belongs to "before site t" (beta . x == 1), and the posterior x .* beta of site t-1 has been added
+// to the emission row of ob_prev (the observation at site t-1; -1 when there is none).
+//
+// With w = emis(ob) .* beta:  beta'_i = sum_{j<i} b_j w_j + d_i w_i + u_i sum_{j>i} v_j w_j
+//   d ll/d b_j += (sum_{i>j} x_i) w_j      d ll/d d_j += x_j w_j
+//   d ll/d u_i += x_i sum_{j>i} v_j w_j    d ll/d v_j += (sum_{i<j} u_i x_i) w_j
 template <typename F, int MT, int T>
-__device__ __forceinline__ void backward_site(F (&beta)[MT], const F (&x)[MT], F inv_c, int ob, int ob_prev,
-                                              const F *__restrict__ prm, int sub, Grad<F, MT> &g) {
-    constexpr int M = MT * T;
-    using V = typename Vec<F>::type;
-    constexpr int W = Vec<F>::W;
-    const int ob_row = ob < 0 ? 2 : ob;
+__device__ __forceinline__ void backward_site(F (&beta)[MT], const F (&x)[MT], int ob, int ob_prev,
+                                              const Params<F, MT> &p, const PartnerCoef<F, MT, T, true> &pc, int sub,
+                                              Grad<F, MT> &g) {
+    const ObsMask om(ob);
     F w[MT];
 #pragma unroll
-    for (int q = 0; q < MT / W; ++q) {
-        F e[W];
-        unpack<F>(*reinterpret_cast<const V *>(prm + Slot<M>::kRowE + ob_row * M + q * W), e);
+    for (int k = 0; k < MT; ++k) w[k] = emis(p, k, om) * beta[k];
+    F q_run = F(0), s_run = F(0), b_run = F(0), x_run = F(0);
+    if constexpr (T == 2) {
+        F tw[2] = {F(0), F(0)}, tx[2] = {F(0), F(0)};
 #pragma unroll
-        for (int r = 0; r < W; ++r) w[q * W + r] = (e[r] * inv_c) * beta[q * W + r];
+        for (int k = 0; k < MT; ++k) {
+            tw[k & 1] = fma(pc.cw[k], w[k], tw[k & 1]);
+            tx[k & 1] = fma(pc.cx[k], x[k], tx[k & 1]);
+        }
+        const F ow = __shfl_xor_sync(0xffffffffu, tw[0] + tw[1], 1, 2);
+        const F ox = __shfl_xor_sync(0xffffffffu, tx[0] + tx[1], 1, 2);
+        q_run = sub == 0 ? ow : F(0);
+        s_run = sub == 0 ? ox : F(0);
+        b_run = sub == 0 ? F(0) : ow;
+        x_run = sub == 0 ? F(0) : ox;
+    } else if constexpr (T > 2) {
+        F tq = F(0), ts = F(0), tb = F(0), tx = F(0);
+#pragma unroll
+        for (int k = 0; k < MT; ++k) {
+            tq = fma(p.v[k], w[k], tq);
+            ts += x[k];
+            tb = fma(p.b[k], w[k], tb);
+            tx = fma(p.u[k], x[k], tx);
+        }
+        q_run = lanes_after<F, T>(tq, sub);
+        s_run = lanes_after<F, T>(ts, sub);
+        b_run = lanes_before<F, T>(tb, sub);
+        x_run = lanes_before<F, T>(tx, sub);
     }
-    if constexpr (T == 1) {
-        // descending sweep: tails  Q_k = sum_{j>k} v_j w_j  and  S_k = sum_{j>k} x_j
-        F q_run = F(0), s_run = F(0);
+    // descending sweep: tails  Q_k = sum_{j>k} v_j w_j  and  S_k = sum_{j>k} x_j
 #pragma unroll
-        for (int q = MT / W - 1; q >= 0; --q) {
-            F v[W], u[W];
-            unpack<F>(*reinterpret_cast<const V *>(prm + Slot<M>::kRowV + q * W), v);
-            unpack<F>(*reinterpret_cast<const V *>(prm + Slot<M>::kRowU + q * W), u);
+    for (int k = MT - 1; k >= 0; --k) {
+        beta[k] = p.u[k] * q_run;
+        g.u[k] = fma(x[k], q_run, g.u[k]);
+        g.b[k] = fma(s_run, w[k], g.b[k]);
+        q_run = fma(p.v[k], w[k], q_run);
+        s_run += x[k];
+    }
+    // ascending sweep: heads  Pb_k = sum_{j<k} b_j w_j  and  Px_k = sum_{j<k} u_j x_j
 #pragma unroll
-            for (int r = W - 1; r >= 0; --r) {
-                const int k = q * W + r;
-                beta[k] = u[r] * q_run;
-                g.u[k] = fma(x[k], q_run, g.u[k]);
-                g.b[k] = fma(s_run, w[k], g.b[k]);
-                q_run = fma(v[r], w[k], q_run);
-                s_run += x[k];
-            }
-        }
-        // ascending sweep: heads  Pb_k = sum_{j<k} b_j w_j  and  Px_k = sum_{j<k} u_j x_j
-        F b_run = F(0), x_run = F(0);
-#pragma unroll
-        for (int q = 0; q < MT / W; ++q) {
-            F b[W], d[W], u[W];
-            unpack<F>(*reinterpret_cast<const V *>(prm + Slot<M>::kRowB + q * W), b);
-            unpack<F>(*reinterpret_cast<const V *>(prm + Slot<M>::kRowD + q * W), d);
-            unpack<F>(*reinterpret_cast<const V *>(prm + Slot<M>::kRowU + q * W), u);
-#pragma unroll
-            for (int r = 0; r < W; ++r) {
-                const int k = q * W + r;
-                beta[k] = fma(d[r], w[k], beta[k] + b_run);
-                g.d[k] = fma(x[k], w[k], g.d[k]);
-                g.v[k] = fma(x_run, w[k], g.v[k]);
-                b_run = fma(b[r], w[k], b_run);
-                x_run = fma(u[r], x[k], x_run);
-            }
-        }
-    } else {
-        F qs[MT], ss[MT], bs[MT], xs[MT];
-        F q_run = F(0), s_run = F(0), b_run = F(0), x_run = F(0);
-#pragma unroll
-        for (int q = MT / W - 1; q >= 0; --q) {
-            F v[W];
-            unpack<F>(*reinterpret_cast<const V *>(prm + Slot<M>::kRowV + q * W), v);
-#pragma unroll
-            for (int r = W - 1; r >= 0; --r) {
-                const int k = q * W + r;
-                qs[k] = q_run;
-                ss[k] = s_run;
-                q_run = fma(v[r], w[k], q_run);
-                s_run += x[k];
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < MT / W; ++q) {
-            F b[W], u[W];
-            unpack<F>(*reinterpret_cast<const V *>(prm + Slot<M>::kRowB + q * W), b);
-            unpack<F>(*reinterpret_cast<const V *>(prm + Slot<M>::kRowU + q * W), u);
-#pragma unroll
-            for (int r = 0; r < W; ++r) {
-                const int k = q * W + r;
-                bs[k] = b_run;
-                xs[k] = x_run;
-                b_run = fma(b[r], w[k], b_run);
-                x_run = fma(u[r], x[k], x_run);
-            }
-        }
-        const F q_off = lanes_after<F, T>(q_run, sub);
-        const F s_off = lanes_after<F, T>(s_run, sub);
-        const F b_off = lanes_before<F, T>(b_run, sub);
-        const F x_off = lanes_before<F, T>(x_run, sub);
-#pragma unroll
-        for (int q = 0; q < MT / W; ++q) {
-            F d[W], u[W];
-            unpack<F>(*reinterpret_cast<const V *>(prm + Slot<M>::kRowD + q * W), d);
-            unpack<F>(*reinterpret_cast<const V *>(prm + Slot<M>::kRowU + q * W), u);
-#pragma unroll
-            for (int r = 0; r < W; ++r) {
-                const int k = q * W + r;
-                const F qk = qs[k] + q_off;
-                beta[k] = fma(u[r], qk, fma(d[r], w[k], bs[k] + b_off));
-                g.u[k] = fma(x[k], qk, g.u[k]);
-                g.b[k] = fma(ss[k] + s_off, w[k], g.b[k]);
-                g.d[k] = fma(x[k], w[k], g.d[k]);
-                g.v[k] = fma(xs[k] + x_off, w[k], g.v[k]);
-            }
-        }
+    for (int k = 0; k < MT; ++k) {
+        beta[k] = fma(p.d[k], w[k], beta[k] + b_run);
+        g.d[k] = fma(x[k], w[k], g.d[k]);
+        g.v[k] = fma(x_run, w[k], g.v[k]);
+        b_run = fma(p.b[k], w[k], b_run);
+        x_run = fma(p.u[k], x[k], x_run);
     }
     posterior_to_emission<F, MT>(beta, x, ob_prev, g);
 }
+
+constexpr int kNorm = 4;  // the forward vector is rescaled after every kNorm-th site of a segment
 
 // Observations of one K-site segment packed in 64-bit words (K = 8 or 16).
 template <int K> struct ObsWords {
@@ -312,70 +333,63 @@ template <int K> struct ObsWords {
 #pragma unroll
         for (int i = 0; i < K / 8; ++i) w[i] = __ldg(reinterpret_cast<const unsigned long long *>(row + site0) + i);
     }
-    __device__ __forceinline__ int at(int k) const {
+    // the 4 observations of sites [k0, k0 + 4), k0 a multiple of 4
+    __device__ __forceinline__ uint32_t block4(int k0) const {
         uint64_t word = w[0];
-        if constexpr (K == 16) word = (k & 8) ? w[1] : w[0];
-        return static_cast<int>(static_cast<int8_t>((word >> ((k & 7) * 8)) & 0xff));
+        if constexpr (K == 16) word = (k0 & 8) ? w[1] : w[0];
+        return static_cast<uint32_t>(word >> ((k0 & 4) * 8));
+    }
+    __device__ __forceinline__ int at(int k) const { return byte_of(block4(k & ~3), k & 3); }
+    static __device__ __forceinline__ int byte_of(uint32_t blk, int j) {
+        return static_cast<int>(static_cast<int8_t>((blk >> (8 * j)) & 0xffu));
     }
 };
 
-template <typename F, int MT, int T, int K> constexpr size_t smem_bytes(int n_slots) {
-    return sizeof(F) * (size_t(n_slots) * Slot<MT * T>::kStride + size_t(K) * MT * kThreads + size_t(K) * kThreads);
+template <typename F, int MT, int K> constexpr size_t smem_bytes() {
+    return sizeof(F) * (size_t(K) * MT * kThreads + size_t(K / kNorm) * kThreads);
 }
-// checkpoint scratch elements (of F) per CTA slot
-template <int MT, int K> constexpr int64_t ckpt_elems_per_cta(int64_t L) {
-    return ((L + K - 1) / K) * int64_t(MT) * kThreads;
+// checkpoint scratch bytes per resident warp
+template <typename F, int MT, int K> __host__ __device__ constexpr int64_t ckpt_bytes_per_warp(int64_t L) {
+    return ((L + K - 1) / K) * int64_t(MT) * 32 * int64_t(sizeof(F));
 }
 
 template <typename F, int MT, int T, int K, bool GRAD, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) psmc_loglik_kernel(const KernelArgs a) {
     constexpr int M = MT * T;
-    constexpr int PB = kThreads / T;  // pairs per CTA
+    constexpr int PW = 32 / T;  // pairs per warp
     using V = typename Vec<F>::type;
     constexpr int W = Vec<F>::W;
     constexpr int QN = MT / W;
-    static_assert(MT % 4 == 0 && K % 8 == 0, "layout assumptions");
+    static_assert(MT % 4 == 0 && K % 8 == 0 && K % kNorm == 0 && T <= 32, "layout assumptions");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    F *prm_s = reinterpret_cast<F *>(smem_raw);
-    V *seg_s = reinterpret_cast<V *>(prm_s + a.n_slots * Slot<M>::kStride);  // [K][QN][kThreads]
-    F *invc_s = reinterpret_cast<F *>(seg_s + K * QN * kThreads);            // [K][kThreads]
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    // per-warp ring of forward vectors [K][QN][32] and block scale factors [K / kNorm][32]
+    V *seg_s = reinterpret_cast<V *>(smem_raw) + warp * (K * QN * 32) + lane;
+    F *scale_s = reinterpret_cast<F *>(reinterpret_cast<V *>(smem_raw) + kWarps * (K * QN * 32)) + warp * (K / kNorm * 32) + lane;
 
-    const int tid = threadIdx.x;
-    const int sub = tid % T;
-    const int lp = tid / T;
+    const int sub = lane % T;
+    const int lp = lane / T;
     const int64_t n_pairs = a.B * a.S;
     const int64_t n_seg = (a.L + K - 1) / K;
-    const bool shared_params = a.pstride_s == 0;
+    const int64_t warp_slot = int64_t(blockIdx.x) * kWarps + warp;
     const F *params6 = static_cast<const F *>(a.params6);
     const F *pi_g = static_cast<const F *>(a.pi);
-    V *ck = GRAD ? reinterpret_cast<V *>(static_cast<F *>(a.ckpt) + int64_t(blockIdx.x) * n_seg * MT * kThreads) : nullptr;
+    V *ck = GRAD ? reinterpret_cast<V *>(static_cast<char *>(a.ckpt) + warp_slot * ckpt_bytes_per_warp<F, MT, K>(a.L)) + lane
+                 : nullptr;
 
+    // the work list is walked per CTA (not per warp) so that every loop bound below is provably
+    // uniform and the shuffles need no reconvergence guards
     for (int64_t grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
-        const int64_t p_first = grp * PB;
-        const int64_t p_last = min(p_first + PB, n_pairs) - 1;
-        const int64_t b_first = p_first / a.S;
-        __syncthreads();  // everyone is done with the previous group's slots
-        {
-            const int n_used = shared_params ? int(p_last / a.S - b_first) + 1 : int(p_last - p_first) + 1;
-            for (int i = tid; i < n_used * 7 * M; i += kThreads) {
-                const int slot = i / (7 * M), r = i % (7 * M);
-                F val = F(1);  // row 6 = emission of a missing observation
-                if (r < 6 * M) {
-                    const int64_t pb = shared_params ? (b_first + slot) : (p_first + slot) / a.S;
-                    const int64_t ps = shared_params ? 0 : (p_first + slot) % a.S;
-                    val = params6[pb * a.pstride_b + ps * a.pstride_s + r];
-                }
-                prm_s[slot * Slot<M>::kStride + r] = val;
-            }
-        }
-        __syncthreads();
-
-        const int64_t pair = min(p_first + lp, n_pairs - 1);
-        const bool writer = (p_first + lp) < n_pairs;
+        const int64_t pair_raw = (grp * kWarps + warp) * PW + lp;
+        const bool writer = pair_raw < n_pairs;
+        const int64_t pair = writer ? pair_raw : n_pairs - 1;  // idle lanes shadow the last pair
         const int64_t pb = pair / a.S, ps = pair % a.S;
-        const int slot = shared_params ? int(pb - b_first) : int(pair - p_first);
-        const F *prm = prm_s + slot * Slot<M>::kStride + sub * MT;
+        Params<F, MT> p;
+        p.load(params6 + pb * a.pstride_b + ps * a.pstride_s + sub * MT, M);
+        PartnerCoef<F, MT, T, GRAD> pc;
+        pc.init(p, sub);
         int64_t row = a.inds[ps];
         if (row < 0 || row >= a.n_rows) {
             if (sub == 0) atomicOr(a.err_flag, 1);
@@ -392,16 +406,18 @@ __global__ void __launch_bounds__(kThreads, MINB) psmc_loglik_kernel(const Kerne
         for (int64_t seg = 0; seg < n_seg; ++seg) {
             if (GRAD && seg > 0) {
 #pragma unroll
-                for (int q = 0; q < QN; ++q) ck[(seg * QN + q) * kThreads + tid] = pack(&x[q * W]);
+                for (int q = 0; q < QN; ++q) ck[(seg * QN + q) * 32] = pack(&x[q * W]);
             }
             ObsWords<K> ow;
             ow.load(obs, seg * K);
             const int len = int(min(int64_t(K), a.L - seg * K));
             F acc = F(0);
-#pragma unroll 2
-            for (int k = 0; k < len; ++k) {
-                const int ob = ow.at(k);
-                const F tot = forward_site<F, MT, T>(x, prm, ob < 0 ? 2 : ob, sub);
+            for (int kb = 0; kb < len; kb += kNorm) {
+                const uint32_t blk = ow.block4(kb);
+#pragma unroll
+                for (int j = 0; j < kNorm; ++j)
+                    if (kb + j < len) forward_site<F, MT, T, GRAD>(x, p, pc, ObsWords<K>::byte_of(blk, j), sub);
+                const F tot = pair_sum<F, MT, T>(x);
                 const F inv = fast_rcp<F>(tot);
 #pragma unroll
                 for (int j = 0; j < MT; ++j) x[j] *= inv;
@@ -428,10 +444,7 @@ __global__ void __launch_bounds__(kThreads, MINB) psmc_loglik_kernel(const Kerne
             {
                 // after the last site: beta = 1 / sum(x) so that beta . x == 1, and the posterior of
                 // the last site is x .* beta
-                F tot = F(0);
-#pragma unroll
-                for (int k = 0; k < MT; ++k) tot += x[k];
-                tot = fast_rcp<F>(lanes_total<F, T>(tot));
+                const F tot = fast_rcp<F>(pair_sum<F, MT, T>(x));
 #pragma unroll
                 for (int k = 0; k < MT; ++k) beta[k] = tot;
                 posterior_to_emission<F, MT>(beta, x, int(obs[a.L - 1]), g);
@@ -449,16 +462,20 @@ __global__ void __launch_bounds__(kThreads, MINB) psmc_loglik_kernel(const Kerne
                     for (int k = 0; k < MT; ++k) xs[k] = pi_p[k];
                 } else {
 #pragma unroll
-                    for (int q = 0; q < QN; ++q) unpack<F>(ck[(seg * QN + q) * kThreads + tid], &xs[q * W]);
+                    for (int q = 0; q < QN; ++q) unpack<F>(ck[(seg * QN + q) * 32], &xs[q * W]);
                 }
-#pragma unroll 2
-                for (int k = 0; k < len; ++k) {
+                for (int kb = 0; kb < len; kb += kNorm) {
+                    const uint32_t blk = ow.block4(kb);
 #pragma unroll
-                    for (int q = 0; q < QN; ++q) seg_s[(k * QN + q) * kThreads + tid] = pack(&xs[q * W]);
-                    const int ob = ow.at(k);
-                    const F tot = forward_site<F, MT, T>(xs, prm, ob < 0 ? 2 : ob, sub);
-                    const F inv = fast_rcp<F>(tot);
-                    invc_s[k * kThreads + tid] = inv;
+                    for (int j = 0; j < kNorm; ++j) {
+                        if (kb + j < len) {
+#pragma unroll
+                            for (int q = 0; q < QN; ++q) seg_s[((kb + j) * QN + q) * 32] = pack(&xs[q * W]);
+                            forward_site<F, MT, T, GRAD>(xs, p, pc, ObsWords<K>::byte_of(blk, j), sub);
+                        }
+                    }
+                    const F inv = fast_rcp<F>(pair_sum<F, MT, T>(xs));
+                    scale_s[(kb / kNorm) * 32] = inv;
 #pragma unroll
                     for (int j = 0; j < MT; ++j) xs[j] *= inv;
                 }
@@ -472,14 +489,24 @@ __global__ void __launch_bounds__(kThreads, MINB) psmc_loglik_kernel(const Kerne
 #pragma unroll
                     for (int k = 0; k < MT; ++k) beta[k] *= dot;
                 }
-#pragma unroll 2
-                for (int k = len - 1; k >= 0; --k) {
-                    F xin[MT];
+                for (int kb = ((len - 1) / kNorm) * kNorm; kb >= 0; kb -= kNorm) {
+                    const uint32_t blk = ow.block4(kb);
+                    const int ob_before = kb > 0 ? ow.at(kb - 1) : (seg > 0 ? ow_prev.at(K - 1) : -1);
+                    // the forward pass multiplied its vector by `scale` after the last site of this
+                    // block; carrying the same factor on beta keeps beta . alpha == 1
+                    const F scale = scale_s[(kb / kNorm) * 32];
 #pragma unroll
-                    for (int q = 0; q < QN; ++q) unpack<F>(seg_s[(k * QN + q) * kThreads + tid], &xin[q * W]);
-                    const F inv_c = invc_s[k * kThreads + tid];
-                    const int ob_prev = k > 0 ? ow.at(k - 1) : (seg > 0 ? ow_prev.at(K - 1) : -1);
-                    backward_site<F, MT, T>(beta, xin, inv_c, ow.at(k), ob_prev, prm, sub, g);
+                    for (int k = 0; k < MT; ++k) beta[k] *= scale;
+#pragma unroll
+                    for (int j = kNorm - 1; j >= 0; --j) {
+                        if (kb + j < len) {
+                            F xin[MT];
+#pragma unroll
+                            for (int q = 0; q < QN; ++q) unpack<F>(seg_s[((kb + j) * QN + q) * 32], &xin[q * W]);
+                            const int ob_prev = j > 0 ? ObsWords<K>::byte_of(blk, j - 1) : ob_before;
+                            backward_site<F, MT, T>(beta, xin, ObsWords<K>::byte_of(blk, j), ob_prev, p, pc, sub, g);
+                        }
+                    }
                 }
                 ow = ow_prev;
             }
@@ -487,10 +514,10 @@ __global__ void __launch_bounds__(kThreads, MINB) psmc_loglik_kernel(const Kerne
                 F *out = static_cast<F *>(a.dlog) + pair * 7 * M + sub * MT;
 #pragma unroll
                 for (int k = 0; k < MT; ++k) {
-                    out[0 * M + k] = g.b[k] * prm[Slot<M>::kRowB + k];
-                    out[1 * M + k] = g.d[k] * prm[Slot<M>::kRowD + k];
-                    out[2 * M + k] = g.u[k] * prm[Slot<M>::kRowU + k];
-                    out[3 * M + k] = g.v[k] * prm[Slot<M>::kRowV + k];
+                    out[0 * M + k] = g.b[k] * p.b[k];
+                    out[1 * M + k] = g.d[k] * p.d[k];
+                    out[2 * M + k] = g.u[k] * p.u[k];
+                    out[3 * M + k] = g.v[k] * p.v[k];
                     out[4 * M + k] = g.e0[k];
                     out[5 * M + k] = g.e1[k];
                     out[6 * M + k] = beta[k] * pi_p[k];
