@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -63,7 +64,7 @@ struct DeviceBuffer {
 };
 
 struct Variant {
-    int M, T, K;
+    int M, T, K, NT;
     bool dbl, grad;
     const void *func;
     size_t smem;                                  // dynamic shared memory per CTA
@@ -85,21 +86,22 @@ struct phb_kernel {
     int force_T = 0;
     int num_sms = 0;
     int64_t launches = 0;
-    DeviceBuffer params, inds, ll, dlog, ckpt;
+    DeviceBuffer params, inds, ll, dlog, ckpt, gacc;
     size_t elem() const { return dbl ? sizeof(double) : sizeof(float); }
 };
 
 namespace {
 
-template <typename F, int MT, int T, int K, bool GRAD, int MINB> Variant make_variant() {
+template <typename F, int MT, int T, int K, bool GRAD, int NT, int MINB> Variant make_variant() {
     Variant v;
     v.M = MT * T;
     v.T = T;
     v.K = K;
+    v.NT = NT;
     v.dbl = sizeof(F) == 8;
     v.grad = GRAD;
-    v.func = reinterpret_cast<const void *>(&phb::psmc_loglik_kernel<F, MT, T, K, GRAD, MINB>);
-    v.smem = phb::smem_bytes<F, MT, K>();
+    v.func = reinterpret_cast<const void *>(&phb::psmc_loglik_kernel<F, MT, T, K, GRAD, NT, MINB>);
+    v.smem = phb::smem_bytes<F, MT, K, NT>();
     v.ckpt_bytes_per_warp = [](int64_t L) { return phb::ckpt_bytes_per_warp<F, MT, K>(L); };
     return v;
 }
@@ -111,47 +113,48 @@ template <typename F, int MT, int T, int K, bool GRAD, int MINB> Variant make_va
 const std::vector<Variant> &variants() {
     static const std::vector<Variant> table = [] {
         std::vector<Variant> t;
-#define PHB_GRAD(F, MT, T, K, MINB) t.push_back(make_variant<F, MT, T, K, true, MINB>());
-#define PHB_FWD(F, MT, T, K, MINB) t.push_back(make_variant<F, MT, T, K, false, MINB>());
+#define PHB_GRAD(F, MT, T, K, NT, MINB) t.push_back(make_variant<F, MT, T, K, true, NT, MINB>());
+#define PHB_FWD(F, MT, T, K, NT, MINB) t.push_back(make_variant<F, MT, T, K, false, NT, MINB>());
         // ---- float, loglik + grad
-        PHB_GRAD(float, 4, 1, 16, 4)   // M = 4
-        PHB_GRAD(float, 8, 1, 16, 3)   // M = 8
-        PHB_GRAD(float, 4, 2, 16, 4)
-        PHB_GRAD(float, 8, 2, 16, 3)   // M = 16
-        PHB_GRAD(float, 4, 4, 16, 4)
-        PHB_GRAD(float, 8, 4, 16, 3)   // M = 32
-        PHB_GRAD(float, 4, 8, 16, 4)
-        PHB_GRAD(float, 8, 8, 16, 3)   // M = 64
-        PHB_GRAD(float, 4, 16, 16, 4)
+        PHB_GRAD(float, 4, 1, 16, 128, 4)   // M = 4
+        PHB_GRAD(float, 8, 1, 16, 128, 3)   // M = 8
+        PHB_GRAD(float, 4, 2, 16, 128, 4)
+        PHB_GRAD(float, 8, 2, 16, 128, 3)   // M = 16 (first entry = default; PHB_NT=256 selects the next)
+        PHB_GRAD(float, 8, 2, 16, 256, 1)
+        PHB_GRAD(float, 4, 4, 16, 128, 4)
+        PHB_GRAD(float, 8, 4, 16, 128, 3)   // M = 32
+        PHB_GRAD(float, 4, 8, 16, 128, 4)
+        PHB_GRAD(float, 8, 8, 16, 128, 3)   // M = 64
+        PHB_GRAD(float, 4, 16, 16, 128, 4)
         // ---- float, forward only
-        PHB_FWD(float, 4, 1, 16, 4)    // M = 4
-        PHB_FWD(float, 8, 1, 16, 4)    // M = 8
-        PHB_FWD(float, 4, 2, 16, 4)
-        PHB_FWD(float, 16, 1, 8, 3)    // M = 16
-        PHB_FWD(float, 8, 2, 16, 4)
-        PHB_FWD(float, 4, 4, 16, 4)
-        PHB_FWD(float, 16, 2, 8, 3)    // M = 32
-        PHB_FWD(float, 8, 4, 16, 4)
-        PHB_FWD(float, 4, 8, 16, 4)
-        PHB_FWD(float, 16, 4, 8, 3)    // M = 64
-        PHB_FWD(float, 8, 8, 16, 4)
-        PHB_FWD(float, 4, 16, 16, 4)
+        PHB_FWD(float, 4, 1, 16, 128, 4)    // M = 4
+        PHB_FWD(float, 8, 1, 16, 128, 4)    // M = 8
+        PHB_FWD(float, 4, 2, 16, 128, 4)
+        PHB_FWD(float, 16, 1, 8, 128, 3)    // M = 16
+        PHB_FWD(float, 8, 2, 16, 128, 4)
+        PHB_FWD(float, 4, 4, 16, 128, 4)
+        PHB_FWD(float, 16, 2, 8, 128, 3)    // M = 32
+        PHB_FWD(float, 8, 4, 16, 128, 4)
+        PHB_FWD(float, 4, 8, 16, 128, 4)
+        PHB_FWD(float, 16, 4, 8, 128, 3)    // M = 64
+        PHB_FWD(float, 8, 8, 16, 128, 4)
+        PHB_FWD(float, 4, 16, 16, 128, 4)
         // ---- double, loglik + grad
-        PHB_GRAD(double, 4, 1, 8, 2)   // M = 4
-        PHB_GRAD(double, 4, 2, 8, 2)   // M = 8
-        PHB_GRAD(double, 4, 4, 8, 2)   // M = 16
-        PHB_GRAD(double, 4, 8, 8, 2)   // M = 32
-        PHB_GRAD(double, 4, 16, 8, 2)  // M = 64
+        PHB_GRAD(double, 4, 1, 8, 128, 2)   // M = 4
+        PHB_GRAD(double, 4, 2, 8, 128, 2)   // M = 8
+        PHB_GRAD(double, 4, 4, 8, 128, 2)   // M = 16
+        PHB_GRAD(double, 4, 8, 8, 128, 2)   // M = 32
+        PHB_GRAD(double, 4, 16, 8, 128, 2)  // M = 64
         // ---- double, forward only
-        PHB_FWD(double, 4, 1, 8, 3)    // M = 4
-        PHB_FWD(double, 8, 1, 8, 3)    // M = 8
-        PHB_FWD(double, 4, 2, 8, 3)
-        PHB_FWD(double, 8, 2, 8, 3)    // M = 16
-        PHB_FWD(double, 4, 4, 8, 3)
-        PHB_FWD(double, 8, 4, 8, 3)    // M = 32
-        PHB_FWD(double, 4, 8, 8, 3)
-        PHB_FWD(double, 8, 8, 8, 3)    // M = 64
-        PHB_FWD(double, 4, 16, 8, 3)
+        PHB_FWD(double, 4, 1, 8, 128, 3)    // M = 4
+        PHB_FWD(double, 8, 1, 8, 128, 3)    // M = 8
+        PHB_FWD(double, 4, 2, 8, 128, 3)
+        PHB_FWD(double, 8, 2, 8, 128, 3)    // M = 16
+        PHB_FWD(double, 4, 4, 8, 128, 3)
+        PHB_FWD(double, 8, 4, 8, 128, 3)    // M = 32
+        PHB_FWD(double, 4, 8, 8, 128, 3)
+        PHB_FWD(double, 8, 8, 8, 128, 3)    // M = 64
+        PHB_FWD(double, 4, 16, 8, 128, 3)
 #undef PHB_GRAD
 #undef PHB_FWD
         return t;
@@ -161,9 +164,19 @@ const std::vector<Variant> &variants() {
 
 const Variant *pick_variant(const phb_kernel *k, bool grad, int64_t n_pairs) {
     const Variant *last = nullptr, *forced = nullptr, *first_fill = nullptr;
-    const int64_t fill = int64_t(k->num_sms) * 2 * phb::kThreads;
+    const int64_t fill = int64_t(k->num_sms) * 256;
+    // tuning knob: PHB_NT=<threads per CTA> picks among variants that differ only in CTA size
+    const char *nt_env = getenv("PHB_NT");
+    const int want_nt = nt_env ? atoi(nt_env) : 0;
     for (const Variant &v : variants()) {
         if (v.M != k->M || v.dbl != (k->dbl != 0) || v.grad != grad) continue;
+        if (last && last->T == v.T && v.NT != want_nt) continue;  // same layout, other CTA size
+        if (last && last->T == v.T && v.NT == want_nt) {
+            if (forced == last) forced = &v;
+            if (first_fill == last) first_fill = &v;
+            last = &v;
+            continue;
+        }
         if (v.T == k->force_T) forced = &v;
         last = &v;
         if (!first_fill && n_pairs * v.T >= fill) first_fill = &v;
@@ -183,24 +196,28 @@ int launch(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream) {
     if (n_pairs == 0) return PHB_OK;
     const Variant *v = pick_variant(k, grad, n_pairs);
     if (!v) return fail(PHB_E_INVALID, "no kernel variant for M=%d, threads_per_pair=%d", k->M, k->force_T);
-    const int pairs_per_cta = phb::kThreads / v->T;
+    const int pairs_per_cta = v->NT / v->T;
     a.n_groups = (n_pairs + pairs_per_cta - 1) / pairs_per_cta;
     const size_t smem = v->smem;
     PHB_CUDA(cudaFuncSetAttribute(v->func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int occ = 0;
-    PHB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v->func, phb::kThreads, smem));
+    PHB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v->func, v->NT, smem));
     if (occ < 1) return fail(PHB_E_CUDA, "kernel does not fit on an SM (smem %zu bytes)", smem);
     const int64_t grid = std::min<int64_t>(a.n_groups, int64_t(occ) * k->num_sms);
     if (grad) {
-        const size_t need = size_t(grid) * phb::kWarps * size_t(v->ckpt_bytes_per_warp(a.L));
+        const size_t need = size_t(grid) * (v->NT / 32) * size_t(v->ckpt_bytes_per_warp(a.L));
         int rc = k->ckpt.reserve(need);
         if (rc != PHB_OK) return rc;
         a.ckpt = k->ckpt.ptr;
+        const int mt = v->M / v->T;
+        rc = k->gacc.reserve(size_t(grid) * v->NT * 6 * mt * sizeof(double));
+        if (rc != PHB_OK) return rc;
+        a.gacc = static_cast<double *>(k->gacc.ptr);
     }
     a.err_flag = k->d_err;
     void *kargs[] = {&a};
     PHB_CUDA(cudaEventRecord(k->ev0, stream));
-    PHB_CUDA(cudaLaunchKernel(v->func, dim3(unsigned(grid)), dim3(phb::kThreads), kargs, smem, stream));
+    PHB_CUDA(cudaLaunchKernel(v->func, dim3(unsigned(grid)), dim3(v->NT), kargs, smem, stream));
     PHB_CUDA(cudaEventRecord(k->ev1, stream));
     k->timed = true;
     k->launches += 1;
@@ -304,6 +321,7 @@ void phb_destroy(phb_kernel *k) {
     k->ll.release();
     k->dlog.release();
     k->ckpt.release();
+    k->gacc.release();
     if (k->d_data) cudaFree(k->d_data);
     if (k->d_err) cudaFree(k->d_err);
     if (k->ev0) cudaEventDestroy(k->ev0);

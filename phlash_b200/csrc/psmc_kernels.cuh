@@ -32,8 +32,8 @@
 
 namespace phb {
 
-constexpr int kThreads = 128;  // threads per CTA
-constexpr int kWarps = kThreads / 32;
+// Threads per CTA are a template parameter (NT) of the kernel: the warps of a CTA never
+// synchronise, so NT only sets the register budget (65536 / NT per thread at one CTA per SM).
 
 struct KernelArgs {
     const int8_t *data;  // [N, pitch]
@@ -50,6 +50,7 @@ struct KernelArgs {
     void *dlog;          // [B, S, 7, M] or nullptr
     void *alpha_out;     // [B, S, M] filtered distribution after the last site, or nullptr
     void *ckpt;          // checkpoint scratch, see ckpt_bytes_per_warp()
+    double *gacc;        // fp64 gradient accumulators: [6 * MT][gridDim.x * NT]
     int64_t n_groups;    // ceil(B*S / pairs-per-CTA)
     int *err_flag;       // bit 0: index out of range, bit 1: non-finite result
 };
@@ -235,12 +236,33 @@ template <typename F, int MT, int T> __device__ __forceinline__ F pair_sum(const
 }
 
 // Gradient accumulators of one lane (d ll / d theta, not yet multiplied by theta, for b, d, u, v;
-// already d / d log for the two emission rows).
+// already d / d log for the two emission rows).  They are fp32 registers (for F = float) that
+// only ever hold the sum over a window of kFlushSites sites; every window is added into a
+// per-thread fp64 slot in global memory (L2 resident).  Without this, increments smaller than
+// half an ulp of a 50 000-site running sum are lost and the gradient is off by up to 5e-4.
+constexpr int kFlushSites = 1024;
+
 template <typename F, int MT> struct Grad {
     F b[MT], d[MT], u[MT], v[MT], e0[MT], e1[MT];
     __device__ __forceinline__ void clear() {
 #pragma unroll
         for (int k = 0; k < MT; ++k) b[k] = d[k] = u[k] = v[k] = e0[k] = e1[k] = F(0);
+    }
+    // acc[i * stride] += window sums, then clear the registers
+    __device__ __forceinline__ void flush(double *acc, int64_t stride) {
+#define PHB_FLUSH_ROW(row, r)                                         \
+    _Pragma("unroll") for (int k = 0; k < MT; ++k) {                  \
+        /* fire-and-forget reduction: no loaded value to keep live */ \
+        atomicAdd(acc + int64_t((r) * MT + k) * stride, double(row[k])); \
+        row[k] = F(0);                                                \
+    }
+        PHB_FLUSH_ROW(b, 0)
+        PHB_FLUSH_ROW(d, 1)
+        PHB_FLUSH_ROW(u, 2)
+        PHB_FLUSH_ROW(v, 3)
+        PHB_FLUSH_ROW(e0, 4)
+        PHB_FLUSH_ROW(e1, 5)
+#undef PHB_FLUSH_ROW
     }
 };
 
@@ -345,16 +367,28 @@ template <int K> struct ObsWords {
     }
 };
 
-template <typename F, int MT, int K> constexpr size_t smem_bytes() {
-    return sizeof(F) * (size_t(K) * MT * kThreads + size_t(K / kNorm) * kThreads);
+template <typename F, int MT, int K, int NT> constexpr size_t smem_bytes() {
+    return sizeof(F) * (size_t(K) * MT * NT + size_t(K / kNorm) * NT);
 }
 // checkpoint scratch bytes per resident warp
 template <typename F, int MT, int K> __host__ __device__ constexpr int64_t ckpt_bytes_per_warp(int64_t L) {
     return ((L + K - 1) / K) * int64_t(MT) * 32 * int64_t(sizeof(F));
 }
 
-template <typename F, int MT, int T, int K, bool GRAD, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) psmc_loglik_kernel(const KernelArgs a) {
+// Register budget: the register file is 16 K registers per SM sub-partition, so what matters is
+// the number of warps per sub-partition w = ceil(NT * MINB / 128): 255 registers at w <= 2, 168 at
+// w = 3, 128 at w = 4 (allocation granularity: 8 registers per thread).
+constexpr int max_regs(int nt, int minb) {
+    const int w = (nt * minb + 127) / 128;
+    const int r = (16384 / w) / 32 / 8 * 8;
+    return r > 255 ? 255 : r;
+}
+
+template <typename F, int MT, int T, int K, bool GRAD, int NT, int MINB>
+__global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelArgs a) {
+    constexpr int kThreads = NT;
+    constexpr int kWarps = NT / 32;
+    static_assert(NT % 32 == 0, "whole warps");
     constexpr int M = MT * T;
     constexpr int PW = 32 / T;  // pairs per warp
     using V = typename Vec<F>::type;
@@ -378,6 +412,12 @@ __global__ void __launch_bounds__(kThreads, MINB) psmc_loglik_kernel(const Kerne
     const F *pi_g = static_cast<const F *>(a.pi);
     V *ck = GRAD ? reinterpret_cast<V *>(static_cast<char *>(a.ckpt) + warp_slot * ckpt_bytes_per_warp<F, MT, K>(a.L)) + lane
                  : nullptr;
+    constexpr int kFlushSegs = kFlushSites / K;
+    static_assert((kFlushSegs & (kFlushSegs - 1)) == 0, "flush cadence must be a power of two");
+    // fp64 gradient slots of this thread: a.gacc[i * gacc_stride + gacc_index]; recomputed where
+    // needed instead of being carried in registers through the hot loops
+#define PHB_GACC_STRIDE (int64_t(gridDim.x) * kThreads)
+#define PHB_GACC_BASE (a.gacc + int64_t(blockIdx.x) * kThreads + threadIdx.x)
 
     // the work list is walked per CTA (not per warp) so that every loop bound below is provably
     // uniform and the shuffles need no reconvergence guards
@@ -449,11 +489,14 @@ __global__ void __launch_bounds__(kThreads, MINB) psmc_loglik_kernel(const Kerne
                 for (int k = 0; k < MT; ++k) beta[k] = tot;
                 posterior_to_emission<F, MT>(beta, x, int(obs[a.L - 1]), g);
             }
-            ObsWords<K> ow;
-            ow.load(obs, (n_seg - 1) * K);
+#pragma unroll 1
+            for (int i = 0; i < 6 * MT; ++i) PHB_GACC_BASE[int64_t(i) * PHB_GACC_STRIDE] = 0.0;
             for (int64_t seg = n_seg - 1; seg >= 0; --seg) {
-                ObsWords<K> ow_prev = ow;
-                if (seg > 0) ow_prev.load(obs, (seg - 1) * K);
+                ObsWords<K> ow;
+                ow.load(obs, seg * K);
+                // observation just before this segment (its posterior is accumulated by the
+                // adjoint step of the segment's first site)
+                const int ob_before_seg = seg > 0 ? int(obs[seg * K - 1]) : -1;
                 const int len = int(min(int64_t(K), a.L - seg * K));
                 // re-run the forward steps of this segment, keeping every input vector
                 F xs[MT];
@@ -491,7 +534,7 @@ __global__ void __launch_bounds__(kThreads, MINB) psmc_loglik_kernel(const Kerne
                 }
                 for (int kb = ((len - 1) / kNorm) * kNorm; kb >= 0; kb -= kNorm) {
                     const uint32_t blk = ow.block4(kb);
-                    const int ob_before = kb > 0 ? ow.at(kb - 1) : (seg > 0 ? ow_prev.at(K - 1) : -1);
+                    const int ob_before = kb > 0 ? ow.at(kb - 1) : ob_before_seg;
                     // the forward pass multiplied its vector by `scale` after the last site of this
                     // block; carrying the same factor on beta keeps beta . alpha == 1
                     const F scale = scale_s[(kb / kNorm) * 32];
@@ -508,23 +551,28 @@ __global__ void __launch_bounds__(kThreads, MINB) psmc_loglik_kernel(const Kerne
                         }
                     }
                 }
-                ow = ow_prev;
+                if ((seg & (kFlushSegs - 1)) == 0) g.flush(PHB_GACC_BASE, PHB_GACC_STRIDE);
             }
             if (writer) {
                 F *out = static_cast<F *>(a.dlog) + pair * 7 * M + sub * MT;
+                const double *gacc = PHB_GACC_BASE;
+                const int64_t gacc_stride = PHB_GACC_STRIDE;
 #pragma unroll
                 for (int k = 0; k < MT; ++k) {
-                    out[0 * M + k] = g.b[k] * p.b[k];
-                    out[1 * M + k] = g.d[k] * p.d[k];
-                    out[2 * M + k] = g.u[k] * p.u[k];
-                    out[3 * M + k] = g.v[k] * p.v[k];
-                    out[4 * M + k] = g.e0[k];
-                    out[5 * M + k] = g.e1[k];
+                    out[0 * M + k] = F(gacc[int64_t(0 * MT + k) * gacc_stride] * double(p.b[k]));
+                    out[1 * M + k] = F(gacc[int64_t(1 * MT + k) * gacc_stride] * double(p.d[k]));
+                    out[2 * M + k] = F(gacc[int64_t(2 * MT + k) * gacc_stride] * double(p.u[k]));
+                    out[3 * M + k] = F(gacc[int64_t(3 * MT + k) * gacc_stride] * double(p.v[k]));
+                    out[4 * M + k] = F(gacc[int64_t(4 * MT + k) * gacc_stride]);
+                    out[5 * M + k] = F(gacc[int64_t(5 * MT + k) * gacc_stride]);
                     out[6 * M + k] = beta[k] * pi_p[k];
                 }
             }
         }
     }
 }
+
+#undef PHB_GACC_STRIDE
+#undef PHB_GACC_BASE
 
 }  // namespace phb
