@@ -88,8 +88,11 @@ int phb_loglik_shared_host(phb_kernel *k, const void *params6, const void *pi, i
                            const int64_t *inds, int64_t B, int64_t S, int want_grad, double *ll,
                            void *dlog);
 
-/* DEVICE-buffer evaluation, asynchronous on `stream` (a cudaStream_t, NULL = the kernel
- * object's own stream): the entry an XLA FFI custom call binds (replaces the
+/* The kernel object's own (non-blocking) stream, as a cudaStream_t.  The host entries run on it. */
+void *phb_stream(const phb_kernel *k);
+
+/* DEVICE-buffer evaluation, asynchronous on `stream` (a cudaStream_t used as given: NULL is the
+ * CUDA default stream, as everywhere in CUDA): the entry an XLA FFI custom call binds (replaces the
  * jax.pure_callback round trip, gpu.py:441-465).  All pointers are device pointers valid on
  * the kernel object's device.  params_stride_s == 0 selects the shared-parameter fast path:
  *   params6 + b * params_stride_b + s * params_stride_s  -> [6, M] block of pair (b, s)
@@ -101,7 +104,8 @@ int phb_loglik_device(phb_kernel *k, const void *params6, int64_t params_stride_
                       int64_t pi_stride_s, const int64_t *inds, int64_t B, int64_t S,
                       int want_grad, double *ll, void *dlog, void *stream);
 
-/* Wait for the kernel object's own stream and report deferred device-side errors. */
+/* Wait for the kernel object's own stream AND for the stream of the most recent
+ * phb_loglik_device call, then report deferred device-side errors. */
 int phb_sync(phb_kernel *k);
 
 /* Device pointer to the resident observation matrix and its row pitch in bytes (read-only;

@@ -380,13 +380,16 @@ int phb_loglik_device(phb_kernel *k, const void *params6, int64_t params_stride_
     a.ll = ll;
     a.dlog = want_grad ? dlog : nullptr;
     a.alpha_out = nullptr;
-    return launch(k, a, want_grad != 0, stream ? static_cast<cudaStream_t>(stream) : k->stream);
+    return launch(k, a, want_grad != 0, static_cast<cudaStream_t>(stream));
 }
+
+void *phb_stream(const phb_kernel *k) { return k ? static_cast<void *>(k->stream) : nullptr; }
 
 int phb_sync(phb_kernel *k) {
     if (int rc = check_handle(k)) return rc;
     PHB_CUDA(cudaSetDevice(k->device));
     PHB_CUDA(cudaStreamSynchronize(k->stream));
+    if (k->timed) PHB_CUDA(cudaEventSynchronize(k->ev1));  // last launch, whatever stream it used
     int flag = 0;
     PHB_CUDA(cudaMemcpy(&flag, k->d_err, sizeof flag, cudaMemcpyDeviceToHost));
     if (flag) PHB_CUDA(cudaMemset(k->d_err, 0, sizeof(int)));

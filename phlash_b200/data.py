@@ -1,0 +1,49 @@
+"""Host-side data layer on the hot path: cutting binned contigs into overlapping chunks
+(reference: src/phlash/data.py:22-24, 37-61, 102-112, 506-558).  The reference does this once,
+in NumPy on the host; so does this mirror.  File readers (psmcfa / VCF / tree sequences) are out
+of scope."""
+
+from __future__ import annotations
+
+from typing import NamedTuple, Optional, Sequence
+
+import numpy as np
+
+
+class ChunkedContig(NamedTuple):
+    chunks: np.ndarray  # int8 [N, overlap + chunk_size]
+    afs: Optional[np.ndarray]
+
+
+def _chunk_het_matrix(het_matrix: np.ndarray, overlap: int, chunk_size: int) -> np.ndarray:
+    """Windows of ``overlap + chunk_size`` bins starting every ``chunk_size`` bins, rows padded
+    with -1 (reference: data.py:37-61; same quirks: ``ceil(L / W)`` windows per row, so the tail of
+    a long row is not covered, and window 0's first ``overlap`` bins only ever serve as warm-up)."""
+    data = np.ascontiguousarray(np.clip(het_matrix, -1, 1).astype(np.int8))
+    assert data.ndim == 2
+    n, length = data.shape
+    width = chunk_size + overlap
+    n_chunks = -(-length // width)
+    reach = (n_chunks - 1) * chunk_size + width  # last bin (exclusive) any window touches
+    padded = np.full((n, max(reach, length)), -1, dtype=np.int8)
+    padded[:, :length] = data
+    windows = np.lib.stride_tricks.sliding_window_view(padded, width, axis=1)[:, :: chunk_size][:, :n_chunks]
+    return np.ascontiguousarray(windows).reshape(n * n_chunks, width)
+
+
+def default_chunk_size(lengths_in_bp: Sequence[int], window_size: int) -> int:
+    """~1/5th of the shortest contig, in bins (reference: data.py:520-521)."""
+    return int(min(0.2 * length / window_size for length in lengths_in_bp if length))
+
+
+def init_mcmc_data(het_matrices: Sequence[np.ndarray], overlap: int, chunk_size: int) -> np.ndarray:
+    """Chunk every contig with the same geometry and stack the chunks
+    (reference: data.py:506-558 without the process pool and the AFS bookkeeping)."""
+    chunks = [_chunk_het_matrix(h, overlap, chunk_size) for h in het_matrices]
+    assert len({c.shape[-1] for c in chunks}) == 1
+    return np.concatenate(chunks, 0)
+
+
+def split_warmup(chunks: np.ndarray, overlap: int):
+    """warmup_chunks, data_chunks = np.split(chunks, [overlap], axis=1) (reference: mcmc.py:203)."""
+    return chunks[:, :overlap], np.ascontiguousarray(chunks[:, overlap:])

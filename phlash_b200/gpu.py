@@ -87,8 +87,9 @@ class _PSMCKernelBase:
     def launch_count(self) -> int:
         return int(self._lib.phb_launch_count(self._handle))
 
-    def evaluate(self, pa: np.ndarray, inds: np.ndarray, grad: bool):
-        """pa [B, S, 7, M] (any float dtype), inds [S] -> ll [B, S] (, dlog [B, S, 7, M])."""
+    def evaluate(self, pa: np.ndarray, inds: np.ndarray, grad: bool, ll_out=None, dlog_out=None):
+        """pa [B, S, 7, M] (any float dtype), inds [S] -> ll [B, S] (, dlog [B, S, 7, M]).
+        ``ll_out`` / ``dlog_out``: optional preallocated (e.g. pinned) result arrays."""
         M = self._M
         B, S = pa.shape[:2]
         assert pa.shape == (B, S, 7, M)
@@ -97,8 +98,12 @@ class _PSMCKernelBase:
         assert np.isfinite(pa).all(), "not all parameters finite"
         pa = np.ascontiguousarray(pa, dtype=self.float_type)
         inds = np.ascontiguousarray(inds, dtype=np.int64)
-        ll = np.zeros([B, S], dtype=np.float64)
-        dlog = np.zeros([B, S, 7, M], dtype=self.float_type) if grad else None
+        ll = np.zeros([B, S], dtype=np.float64) if ll_out is None else ll_out
+        dlog = None
+        if grad:
+            dlog = np.zeros([B, S, 7, M], dtype=self.float_type) if dlog_out is None else dlog_out
+            assert dlog.shape == (B, S, 7, M) and dlog.dtype == self.float_type and dlog.flags.c_contiguous
+        assert ll.shape == (B, S) and ll.dtype == np.float64 and ll.flags.c_contiguous
         _check(
             self._lib.phb_loglik_host(
                 self._handle, _ptr(pa), _ptr(inds), B, S, int(grad), _ptr(ll), _ptr(dlog) if grad else None
