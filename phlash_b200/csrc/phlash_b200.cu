@@ -101,7 +101,7 @@ template <typename F, int MT, int T, int K, bool GRAD, int NT, int MINB> Variant
     v.dbl = sizeof(F) == 8;
     v.grad = GRAD;
     v.func = reinterpret_cast<const void *>(&phb::psmc_loglik_kernel<F, MT, T, K, GRAD, NT, MINB>);
-    v.smem = phb::smem_bytes<F, MT, K, NT>();
+    v.smem = phb::smem_bytes<F, MT, K, NT, GRAD>();
     v.ckpt_bytes_per_warp = [](int64_t L) { return phb::ckpt_bytes_per_warp<F, MT, K>(L); };
     return v;
 }

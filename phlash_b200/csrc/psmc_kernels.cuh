@@ -124,9 +124,22 @@ template <typename F> __device__ __forceinline__ F log2_of(F x);
 template <> __device__ __forceinline__ float log2_of<float>(float x) { return log2f(x); }
 template <> __device__ __forceinline__ double log2_of<double>(double x) { return log2(x); }
 
-// This lane's slice of the six parameter rows, register resident.
+// Branch-free selection by bit arithmetic (LOP3 / SEL on the integer pipe).  The obvious ternary
+// on per-lane data is compiled into a divergent branch, which serialises the warp: the lanes of a
+// warp hold different chunks.
+__device__ __forceinline__ float bit_select(uint32_t mask, float a, float b) {
+    return __uint_as_float((__float_as_uint(a) & mask) | (__float_as_uint(b) & ~mask));
+}
+__device__ __forceinline__ double bit_select(uint32_t mask, double a, double b) {
+    const uint64_t m = (uint64_t(mask) << 32) | mask;
+    return __longlong_as_double((__double_as_longlong(a) & m) | (__double_as_longlong(b) & ~m));
+}
+
+// This lane's slice of the four transition rows, register resident.  The two emission rows live
+// in a per-lane shared-memory table (see EmisTable): selecting between registers costs two
+// selects per state and site, the table costs one 128-bit shared load per four states.
 template <typename F, int MT> struct Params {
-    F b[MT], d[MT], u[MT], v[MT], e0[MT], e1[MT];
+    F b[MT], d[MT], u[MT], v[MT];
     __device__ __forceinline__ void load(const F *__restrict__ src, int M) {
 #pragma unroll
         for (int k = 0; k < MT; ++k) {
@@ -134,8 +147,40 @@ template <typename F, int MT> struct Params {
             d[k] = src[1 * M + k];
             u[k] = src[2 * M + k];
             v[k] = src[3 * M + k];
-            e0[k] = src[4 * M + k];
-            e1[k] = src[5 * M + k];
+        }
+    }
+};
+
+// Per-lane emission table in shared memory: rows emis0, emis1 of this lane's MT states, laid out
+// [row][MT / W][NT] in 128-bit words so that a warp's access is conflict free.  `base` already
+// points at this thread's column.
+template <typename F, int MT, int NT> struct EmisTable {
+    using V = typename Vec<F>::type;
+    static constexpr int W = Vec<F>::W;
+    static constexpr int QN = MT / W;
+    V *base;
+    const V *ones;  // one 128-bit word of 1.0 shared by the CTA
+    __device__ __forceinline__ void fill(const F *__restrict__ src, int M) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+#pragma unroll
+            for (int q = 0; q < QN; ++q) {
+                F tmp[W];
+#pragma unroll
+                for (int i = 0; i < W; ++i) tmp[i] = src[(4 + r) * M + q * W + i];
+                base[(r * QN + q) * NT] = pack(tmp);
+            }
+        }
+    }
+    // emission probabilities of observation `ob` for this lane's states.  A missing observation
+    // emits 1 in every state: one word of ones shared by the whole CTA sits behind the table, and
+    // the choice is made on the ADDRESS (one select per 128-bit load, not one per state).
+    __device__ __forceinline__ void get(int ob, const V *ones, F (&e)[MT]) const {
+        const int row = ob == 1 ? 1 : 0;
+#pragma unroll
+        for (int q = 0; q < QN; ++q) {
+            const V *src = ob < 0 ? ones : base + (row * QN + q) * NT;
+            unpack<F>(*src, &e[q * W]);
         }
     }
 };
@@ -166,32 +211,14 @@ template <typename F, int MT> struct PartnerCoef<F, MT, 2, true> {
     }
 };
 
-// Branch-free choice of the emission probability.  Written as bit arithmetic (two LOP3 on the
-// otherwise idle integer pipe) because the obvious ternary is compiled into one divergent branch
-// per state, which serialises the warp: the lanes of a warp hold different chunks.
-struct ObsMask {
-    uint32_t is0, is1;  // all-ones when the observation is 0 / is 1; both zero when it is missing
-    __device__ __forceinline__ explicit ObsMask(int ob) : is0(ob == 0 ? 0xffffffffu : 0u), is1(ob == 1 ? 0xffffffffu : 0u) {}
-};
-__device__ __forceinline__ float bit_select(uint32_t mask, float a, float b) {
-    return __uint_as_float((__float_as_uint(a) & mask) | (__float_as_uint(b) & ~mask));
-}
-__device__ __forceinline__ double bit_select(uint32_t mask, double a, double b) {
-    const uint64_t m = (uint64_t(mask) << 32) | mask;
-    return __longlong_as_double((__double_as_longlong(a) & m) | (__double_as_longlong(b) & ~m));
-}
-// emission probability of the observation behind `m` in state k (missing -> 1)
-template <typename F, int MT> __device__ __forceinline__ F emis(const Params<F, MT> &p, int k, const ObsMask &m) {
-    return bit_select(m.is0, p.e0[k], bit_select(m.is1, p.e1[k], F(1)));
-}
-
 // One forward step for this lane's MT states: x <- (x A) .* emis(ob).  No rescaling here: the
 // callers renormalise every kNorm sites (lazy scaling), which is exact for the log-likelihood and
 // the gradient as long as the bookkeeping uses the same factors.
-template <typename F, int MT, int T, bool GRAD>
+template <typename F, int MT, int T, bool GRAD, int NT>
 __device__ __forceinline__ void forward_site(F (&x)[MT], const Params<F, MT> &p, const PartnerCoef<F, MT, T, GRAD> &pc,
-                                             int ob, int sub) {
-    const ObsMask om(ob);
+                                             const EmisTable<F, MT, NT> &et, int ob, int sub) {
+    F e[MT];
+    et.get(ob, et.ones, e);
     F pre_run = F(0), suf_run = F(0);
     if constexpr (T == 2) {
         F t[2] = {F(0), F(0)};
@@ -223,7 +250,7 @@ __device__ __forceinline__ void forward_site(F (&x)[MT], const Params<F, MT> &p,
         o = fma(p.v[k], pre_run, o);
         o = fma(p.b[k], suf[k], o);
         pre_run = fma(p.u[k], xk, pre_run);
-        x[k] = o * emis(p, k, om);
+        x[k] = o * e[k];
     }
 }
 
@@ -289,14 +316,14 @@ __device__ __forceinline__ void posterior_to_emission(const F (&beta)[MT], const
 // With w = emis(ob) .* beta:  beta'_i = sum_{j<i} b_j w_j + d_i w_i + u_i sum_{j>i} v_j w_j
 //   d ll/d b_j += (sum_{i>j} x_i) w_j      d ll/d d_j += x_j w_j
 //   d ll/d u_i += x_i sum_{j>i} v_j w_j    d ll/d v_j += (sum_{i<j} u_i x_i) w_j
-template <typename F, int MT, int T>
+template <typename F, int MT, int T, int NT>
 __device__ __forceinline__ void backward_site(F (&beta)[MT], const F (&x)[MT], int ob, int ob_prev,
-                                              const Params<F, MT> &p, const PartnerCoef<F, MT, T, true> &pc, int sub,
-                                              Grad<F, MT> &g) {
-    const ObsMask om(ob);
+                                              const Params<F, MT> &p, const PartnerCoef<F, MT, T, true> &pc,
+                                              const EmisTable<F, MT, NT> &et, int sub, Grad<F, MT> &g) {
     F w[MT];
+    et.get(ob, et.ones, w);
 #pragma unroll
-    for (int k = 0; k < MT; ++k) w[k] = emis(p, k, om) * beta[k];
+    for (int k = 0; k < MT; ++k) w[k] *= beta[k];
     F q_run = F(0), s_run = F(0), b_run = F(0), x_run = F(0);
     if constexpr (T == 2) {
         F tw[2] = {F(0), F(0)}, tx[2] = {F(0), F(0)};
@@ -367,8 +394,9 @@ template <int K> struct ObsWords {
     }
 };
 
-template <typename F, int MT, int K, int NT> constexpr size_t smem_bytes() {
-    return sizeof(F) * (size_t(K) * MT * NT + size_t(K / kNorm) * NT);
+// emission table always; the ring of forward vectors and block scales only for the gradient kernel
+template <typename F, int MT, int K, int NT, bool GRAD> constexpr size_t smem_bytes() {
+    return 16 + sizeof(F) * (size_t(2) * MT * NT + (GRAD ? size_t(K) * MT * NT + size_t(K / kNorm) * NT : 0));
 }
 // checkpoint scratch bytes per resident warp
 template <typename F, int MT, int K> __host__ __device__ constexpr int64_t ckpt_bytes_per_warp(int64_t L) {
@@ -399,9 +427,20 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    // per-warp ring of forward vectors [K][QN][32] and block scale factors [K / kNorm][32]
-    V *seg_s = reinterpret_cast<V *>(smem_raw) + warp * (K * QN * 32) + lane;
-    F *scale_s = reinterpret_cast<F *>(reinterpret_cast<V *>(smem_raw) + kWarps * (K * QN * 32)) + warp * (K / kNorm * 32) + lane;
+    // emission table [2][QN][NT]; then (gradient kernel) the per-warp ring of forward vectors
+    // [K][QN][32] and block scale factors [K / kNorm][32]
+    EmisTable<F, MT, NT> et;
+    et.ones = reinterpret_cast<const V *>(smem_raw);
+    et.base = reinterpret_cast<V *>(smem_raw) + 1 + threadIdx.x;
+    V *seg_s = reinterpret_cast<V *>(smem_raw) + 1 + 2 * QN * NT + warp * (K * QN * 32) + lane;
+    F *scale_s = reinterpret_cast<F *>(reinterpret_cast<V *>(smem_raw) + 1 + 2 * QN * NT + kWarps * (K * QN * 32)) + warp * (K / kNorm * 32) + lane;
+    if (threadIdx.x == 0) {
+        F one[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i) one[i] = F(1);
+        *reinterpret_cast<V *>(smem_raw) = pack(one);
+    }
+    __syncthreads();  // the only block-level barrier: publishes the word of ones
 
     const int sub = lane % T;
     const int lp = lane / T;
@@ -428,6 +467,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
         const int64_t pb = pair / a.S, ps = pair % a.S;
         Params<F, MT> p;
         p.load(params6 + pb * a.pstride_b + ps * a.pstride_s + sub * MT, M);
+        et.fill(params6 + pb * a.pstride_b + ps * a.pstride_s + sub * MT, M);
         PartnerCoef<F, MT, T, GRAD> pc;
         pc.init(p, sub);
         int64_t row = a.inds[ps];
@@ -456,7 +496,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                 const uint32_t blk = ow.block4(kb);
 #pragma unroll
                 for (int j = 0; j < kNorm; ++j)
-                    if (kb + j < len) forward_site<F, MT, T, GRAD>(x, p, pc, ObsWords<K>::byte_of(blk, j), sub);
+                    if (kb + j < len) forward_site<F, MT, T, GRAD, NT>(x, p, pc, et, ObsWords<K>::byte_of(blk, j), sub);
                 const F tot = pair_sum<F, MT, T>(x);
                 const F inv = fast_rcp<F>(tot);
 #pragma unroll
@@ -514,7 +554,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                         if (kb + j < len) {
 #pragma unroll
                             for (int q = 0; q < QN; ++q) seg_s[((kb + j) * QN + q) * 32] = pack(&xs[q * W]);
-                            forward_site<F, MT, T, GRAD>(xs, p, pc, ObsWords<K>::byte_of(blk, j), sub);
+                            forward_site<F, MT, T, GRAD, NT>(xs, p, pc, et, ObsWords<K>::byte_of(blk, j), sub);
                         }
                     }
                     const F inv = fast_rcp<F>(pair_sum<F, MT, T>(xs));
@@ -547,7 +587,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
 #pragma unroll
                             for (int q = 0; q < QN; ++q) unpack<F>(seg_s[((kb + j) * QN + q) * 32], &xin[q * W]);
                             const int ob_prev = j > 0 ? ObsWords<K>::byte_of(blk, j - 1) : ob_before;
-                            backward_site<F, MT, T>(beta, xin, ObsWords<K>::byte_of(blk, j), ob_prev, p, pc, sub, g);
+                            backward_site<F, MT, T, NT>(beta, xin, ObsWords<K>::byte_of(blk, j), ob_prev, p, pc, et, sub, g);
                         }
                     }
                 }
