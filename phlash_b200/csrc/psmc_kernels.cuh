@@ -352,28 +352,34 @@ __device__ __forceinline__ void backward_site(F (&beta)[MT], const F (&x)[MT], i
         b_run = lanes_before<F, T>(tb, sub);
         x_run = lanes_before<F, T>(tx, sub);
     }
-    // descending sweep: tails  Q_k = sum_{j>k} v_j w_j  and  S_k = sum_{j>k} x_j
-#pragma unroll
-    for (int k = MT - 1; k >= 0; --k) {
-        beta[k] = p.u[k] * q_run;
-        g.u[k] = fma(x[k], q_run, g.u[k]);
-        g.b[k] = fma(s_run, w[k], g.b[k]);
-        q_run = fma(p.v[k], w[k], q_run);
-        s_run += x[k];
-    }
     // ascending sweep: heads  Pb_k = sum_{j<k} b_j w_j  and  Px_k = sum_{j<k} u_j x_j
+    // (beta is dead once w has been formed, so it collects the new vector)
 #pragma unroll
     for (int k = 0; k < MT; ++k) {
-        beta[k] = fma(p.d[k], w[k], beta[k] + b_run);
+        beta[k] = fma(p.d[k], w[k], b_run);
         g.d[k] = fma(x[k], w[k], g.d[k]);
         g.v[k] = fma(x_run, w[k], g.v[k]);
         b_run = fma(p.b[k], w[k], b_run);
         x_run = fma(p.u[k], x[k], x_run);
     }
+    // descending sweep: tails  Q_k = sum_{j>k} v_j w_j  and  S_k = sum_{j>k} x_j
+#pragma unroll
+    for (int k = MT - 1; k >= 0; --k) {
+        beta[k] = fma(p.u[k], q_run, beta[k]);
+        g.u[k] = fma(x[k], q_run, g.u[k]);
+        g.b[k] = fma(s_run, w[k], g.b[k]);
+        q_run = fma(p.v[k], w[k], q_run);
+        s_run += x[k];
+    }
     posterior_to_emission<F, MT>(beta, x, ob_prev, g);
 }
 
 constexpr int kNorm = 4;  // the forward vector is rescaled after every kNorm-th site of a segment
+
+// With ~227 KB of shared memory per SM in use there is practically no L1, so every segment's
+// observation / checkpoint load would see L2 or DRAM latency; a hint one segment ahead costs no
+// registers.
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Observations of one K-site segment packed in 64-bit words (K = 8 or 16).
 template <int K> struct ObsWords {
@@ -483,13 +489,15 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
 #pragma unroll
         for (int k = 0; k < MT; ++k) x[k] = pi_p[k];
         double ll = 0.0;
+        ObsWords<K> ow_next;
+        ow_next.load(obs, 0);
         for (int64_t seg = 0; seg < n_seg; ++seg) {
             if (GRAD && seg > 0) {
 #pragma unroll
                 for (int q = 0; q < QN; ++q) ck[(seg * QN + q) * 32] = pack(&x[q * W]);
             }
-            ObsWords<K> ow;
-            ow.load(obs, seg * K);
+            const ObsWords<K> ow = ow_next;
+            if (seg + 1 < n_seg) ow_next.load(obs, (seg + 1) * K);  // one segment ahead
             const int len = int(min(int64_t(K), a.L - seg * K));
             F acc = F(0);
             for (int kb = 0; kb < len; kb += kNorm) {
@@ -534,6 +542,10 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
             for (int64_t seg = n_seg - 1; seg >= 0; --seg) {
                 ObsWords<K> ow;
                 ow.load(obs, seg * K);
+                if (seg > 0) {
+                    prefetch_l2(obs + (seg - 1) * K);
+                    if (seg > 1) prefetch_l2(&ck[(seg - 1) * QN * 32]);
+                }
                 // observation just before this segment (its posterior is accumulated by the
                 // adjoint step of the segment's first site)
                 const int ob_before_seg = seg > 0 ? int(obs[seg * K - 1]) : -1;
