@@ -104,6 +104,21 @@ int phb_loglik_device(phb_kernel *k, const void *params6, int64_t params_stride_
                       int64_t pi_stride_s, const int64_t *inds, int64_t B, int64_t S,
                       int want_grad, double *ll, void *dlog, void *stream);
 
+/* FUSED WARM-UP evaluation (replaces the native-JAX warm-up scan and the per-chunk pi plumbing of
+ * model.py:50-57).  The kernel object must have been created on FULL chunks [N, overlap + L]
+ * (mcmc.py:203 before the split).  For every pair (b, s):
+ *     ll[b, s]   = log p(chunk bins | pi_s)      with pi_s = the filtered distribution after the
+ *                  first `overlap` bins started from params7[b, 6, :] (the stationary pi),
+ *     dlog[b, s] = its gradient w.r.t. log of the PARTICLE's 7 rows (through the warm-up as well).
+ * Both are additive over s, so sum_s is d l2 / d log(theta_b) of model.py:57.
+ * Computed as LL(all bins) - LL(first `overlap` bins) by two launches of the same kernel.
+ * params7 is [B, 7, M] (device pointer for _device, host pointer for _host). */
+int phb_loglik_warmup_device(phb_kernel *k, const void *params7, const int64_t *inds, int64_t B,
+                             int64_t S, int64_t overlap, int want_grad, double *ll, void *dlog,
+                             void *stream);
+int phb_loglik_warmup_host(phb_kernel *k, const void *params7, const int64_t *inds, int64_t B,
+                           int64_t S, int64_t overlap, int want_grad, double *ll, void *dlog);
+
 /* Wait for the kernel object's own stream AND for the stream of the most recent
  * phb_loglik_device call, then report deferred device-side errors. */
 int phb_sync(phb_kernel *k);

@@ -354,20 +354,22 @@ int phb_set_threads_per_pair(phb_kernel *k, int threads_per_pair) {
     return PHB_OK;
 }
 
-int phb_loglik_device(phb_kernel *k, const void *params6, int64_t params_stride_b, int64_t params_stride_s,
-                      const void *pi, int64_t pi_stride_b, int64_t pi_stride_s, const int64_t *inds,
-                      int64_t B, int64_t S, int want_grad, double *ll, void *dlog, void *stream) {
+static int device_eval(phb_kernel *k, const void *params6, int64_t params_stride_b, int64_t params_stride_s,
+                       const void *pi, int64_t pi_stride_b, int64_t pi_stride_s, const int64_t *inds, int64_t B,
+                       int64_t S, int want_grad, double *ll, void *dlog, cudaStream_t stream, int64_t n_sites,
+                       int out_mode) {
     if (int rc = check_handle(k)) return rc;
     if (B < 0 || S < 0) return fail(PHB_E_INVALID, "negative batch shape");
     if (B == 0 || S == 0) return PHB_OK;
     if (!params6 || !pi || !inds || !ll) return fail(PHB_E_INVALID, "NULL device pointer");
     if (want_grad && !dlog) return fail(PHB_E_INVALID, "want_grad is set but dlog is NULL");
+    if (n_sites <= 0 || n_sites > k->L) return fail(PHB_E_INVALID, "number of sites %lld not in [1, %lld]", (long long)n_sites, (long long)k->L);
     PHB_CUDA(cudaSetDevice(k->device));
     phb::KernelArgs a{};
     a.data = k->d_data;
     a.pitch = k->pitch;
     a.n_rows = k->N;
-    a.L = k->L;
+    a.L = n_sites;
     a.inds = inds;
     a.B = B;
     a.S = S;
@@ -380,7 +382,32 @@ int phb_loglik_device(phb_kernel *k, const void *params6, int64_t params_stride_
     a.ll = ll;
     a.dlog = want_grad ? dlog : nullptr;
     a.alpha_out = nullptr;
-    return launch(k, a, want_grad != 0, static_cast<cudaStream_t>(stream));
+    a.out_mode = out_mode;
+    return launch(k, a, want_grad != 0, stream);
+}
+
+int phb_loglik_device(phb_kernel *k, const void *params6, int64_t params_stride_b, int64_t params_stride_s,
+                      const void *pi, int64_t pi_stride_b, int64_t pi_stride_s, const int64_t *inds,
+                      int64_t B, int64_t S, int want_grad, double *ll, void *dlog, void *stream) {
+    if (int rc = check_handle(k)) return rc;
+    return device_eval(k, params6, params_stride_b, params_stride_s, pi, pi_stride_b, pi_stride_s, inds, B, S,
+                       want_grad, ll, dlog, static_cast<cudaStream_t>(stream), k->L, 0);
+}
+
+int phb_loglik_warmup_device(phb_kernel *k, const void *params7, const int64_t *inds, int64_t B, int64_t S,
+                             int64_t overlap, int want_grad, double *ll, void *dlog, void *stream) {
+    if (int rc = check_handle(k)) return rc;
+    if (overlap < 0 || overlap >= k->L)
+        return fail(PHB_E_INVALID, "overlap %lld not in [0, row length %lld)", (long long)overlap, (long long)k->L);
+    const int M = k->M;
+    const char *base = static_cast<const char *>(params7);
+    const void *pi = base + size_t(6) * M * k->elem();
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // LL over warm-up + chunk, started from the particle's stationary pi ...
+    int rc = device_eval(k, params7, 7 * M, 0, pi, 7 * M, 0, inds, B, S, want_grad, ll, dlog, st, k->L, 0);
+    if (rc != PHB_OK || overlap == 0) return rc;
+    // ... minus LL over the warm-up bins alone (same stream: ordered after the first launch)
+    return device_eval(k, params7, 7 * M, 0, pi, 7 * M, 0, inds, B, S, want_grad, ll, dlog, st, overlap, 1);
 }
 
 void *phb_stream(const phb_kernel *k) { return k ? static_cast<void *>(k->stream) : nullptr; }
@@ -479,6 +506,39 @@ int phb_loglik_shared_host(phb_kernel *k, const void *params6, const void *pi, i
     const size_t pi_elems = pi_per_pair ? size_t(B) * S * M : size_t(B) * M;
     return host_eval(k, params6, size_t(B) * 6 * M, 6 * M, 0, 0, pi_per_pair ? S * M : M, pi_per_pair ? M : 0, pi,
                      pi_elems, inds, B, S, want_grad, ll, dlog);
+}
+
+int phb_loglik_warmup_host(phb_kernel *k, const void *params7, const int64_t *inds, int64_t B, int64_t S,
+                           int64_t overlap, int want_grad, double *ll, void *dlog) {
+    if (int rc = check_handle(k)) return rc;
+    if (B < 0 || S < 0) return fail(PHB_E_INVALID, "negative batch shape");
+    if (B == 0 || S == 0) return PHB_OK;
+    if (!params7 || !inds || !ll) return fail(PHB_E_INVALID, "NULL pointer");
+    if (want_grad && !dlog) return fail(PHB_E_INVALID, "want_grad is set but dlog is NULL");
+    const int M = k->M;
+    const size_t es = k->elem();
+    const size_t n_par = size_t(B) * 7 * M;
+    for (int64_t s = 0; s < S; ++s)
+        if (inds[s] < 0 || inds[s] >= k->N)
+            return fail(PHB_E_INVALID, "0 <= inds[%lld]=%lld < N=%lld violated", (long long)s, (long long)inds[s], (long long)k->N);
+    const bool fin = k->dbl ? all_finite(static_cast<const double *>(params7), n_par)
+                            : all_finite(static_cast<const float *>(params7), n_par);
+    if (!fin) return fail(PHB_E_INVALID, "not all parameters finite");
+    PHB_CUDA(cudaSetDevice(k->device));
+    int rc;
+    if ((rc = k->params.reserve(n_par * es)) != PHB_OK) return rc;
+    if ((rc = k->inds.reserve(size_t(S) * sizeof(int64_t))) != PHB_OK) return rc;
+    if ((rc = k->ll.reserve(size_t(B) * S * sizeof(double))) != PHB_OK) return rc;
+    if (want_grad && (rc = k->dlog.reserve(size_t(B) * S * 7 * M * es)) != PHB_OK) return rc;
+    PHB_CUDA(cudaMemcpyAsync(k->params.ptr, params7, n_par * es, cudaMemcpyHostToDevice, k->stream));
+    PHB_CUDA(cudaMemcpyAsync(k->inds.ptr, inds, size_t(S) * sizeof(int64_t), cudaMemcpyHostToDevice, k->stream));
+    rc = phb_loglik_warmup_device(k, k->params.ptr, static_cast<const int64_t *>(k->inds.ptr), B, S, overlap, want_grad,
+                                  static_cast<double *>(k->ll.ptr), want_grad ? k->dlog.ptr : nullptr, k->stream);
+    if (rc != PHB_OK) return rc;
+    PHB_CUDA(cudaMemcpyAsync(ll, k->ll.ptr, size_t(B) * S * sizeof(double), cudaMemcpyDeviceToHost, k->stream));
+    if (want_grad)
+        PHB_CUDA(cudaMemcpyAsync(dlog, k->dlog.ptr, size_t(B) * S * 7 * M * es, cudaMemcpyDeviceToHost, k->stream));
+    return phb_sync(k);
 }
 
 }  // extern "C"

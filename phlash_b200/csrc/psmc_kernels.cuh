@@ -53,6 +53,8 @@ struct KernelArgs {
     double *gacc;        // fp64 gradient accumulators: [6 * MT][gridDim.x * NT]
     int64_t n_groups;    // ceil(B*S / pairs-per-CTA)
     int *err_flag;       // bit 0: index out of range, bit 1: non-finite result
+    int out_mode;        // 0: ll / dlog are written;  1: the results are SUBTRACTED from what is there
+                         // (second launch of the fused warm-up evaluation, see phb_loglik_warmup_*)
 };
 
 template <typename F> struct Vec;
@@ -517,7 +519,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
         if (!(ll == ll) || ll > 1e300 || ll < -1e300) {
             if (sub == 0) atomicOr(a.err_flag, 2);
         }
-        if (writer && sub == 0) a.ll[pair] = ll;
+        if (writer && sub == 0) a.ll[pair] = a.out_mode ? a.ll[pair] - ll : ll;
         if (writer && a.alpha_out != nullptr) {
             F *ao = static_cast<F *>(a.alpha_out) + pair * M + sub * MT;
 #pragma unroll
@@ -611,13 +613,16 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                 const int64_t gacc_stride = PHB_GACC_STRIDE;
 #pragma unroll
                 for (int k = 0; k < MT; ++k) {
-                    out[0 * M + k] = F(gacc[int64_t(0 * MT + k) * gacc_stride] * double(p.b[k]));
-                    out[1 * M + k] = F(gacc[int64_t(1 * MT + k) * gacc_stride] * double(p.d[k]));
-                    out[2 * M + k] = F(gacc[int64_t(2 * MT + k) * gacc_stride] * double(p.u[k]));
-                    out[3 * M + k] = F(gacc[int64_t(3 * MT + k) * gacc_stride] * double(p.v[k]));
-                    out[4 * M + k] = F(gacc[int64_t(4 * MT + k) * gacc_stride]);
-                    out[5 * M + k] = F(gacc[int64_t(5 * MT + k) * gacc_stride]);
-                    out[6 * M + k] = beta[k] * pi_p[k];
+                    F val[7];
+                    val[0] = F(gacc[int64_t(0 * MT + k) * gacc_stride] * double(p.b[k]));
+                    val[1] = F(gacc[int64_t(1 * MT + k) * gacc_stride] * double(p.d[k]));
+                    val[2] = F(gacc[int64_t(2 * MT + k) * gacc_stride] * double(p.u[k]));
+                    val[3] = F(gacc[int64_t(3 * MT + k) * gacc_stride] * double(p.v[k]));
+                    val[4] = F(gacc[int64_t(4 * MT + k) * gacc_stride]);
+                    val[5] = F(gacc[int64_t(5 * MT + k) * gacc_stride]);
+                    val[6] = beta[k] * pi_p[k];
+#pragma unroll
+                    for (int r = 0; r < 7; ++r) out[r * M + k] = a.out_mode ? out[r * M + k] - val[r] : val[r];
                 }
             }
         }

@@ -133,6 +133,53 @@ class _PSMCKernelBase:
         )
         return (ll, dlog) if grad else ll
 
+    def evaluate_warmup(self, params7: np.ndarray, inds: np.ndarray, overlap: int, grad: bool):
+        """Fused warm-up evaluation (model.py:50-57) on a kernel built from FULL chunks
+        [N, overlap + L]: params7 [B, 7, M] (pi row = the particle's stationary pi).  Returns
+        ll [B, S] = log p(chunk | warm-up) and, if grad, dlog [B, S, 7, M] w.r.t. the particle's
+        own rows; both additive over the chunk axis."""
+        M = self._M
+        B, S = params7.shape[0], inds.shape[0]
+        assert params7.shape == (B, 7, M)
+        assert 0 <= overlap < self._L
+        assert np.all(0 <= inds) & np.all(inds < self._N)
+        assert np.isfinite(params7).all(), "not all parameters finite"
+        params7 = np.ascontiguousarray(params7, dtype=self.float_type)
+        inds = np.ascontiguousarray(inds, dtype=np.int64)
+        ll = np.zeros([B, S], dtype=np.float64)
+        dlog = np.zeros([B, S, 7, M], dtype=self.float_type) if grad else None
+        _check(
+            self._lib.phb_loglik_warmup_host(
+                self._handle, _ptr(params7), _ptr(inds), B, S, int(overlap), int(grad), _ptr(ll),
+                _ptr(dlog) if grad else None,
+            )
+        )
+        return (ll, dlog) if grad else ll
+
+    def evaluate_warmup_device(self, params7, inds, overlap: int, grad: bool, ll=None, dlog=None, stream=None):
+        """Device-buffer form of evaluate_warmup (torch CUDA tensors; asynchronous)."""
+        import torch
+
+        M = self._M
+        B, S = int(params7.shape[0]), int(inds.shape[0])
+        tdtype = torch.float64 if self.double_precision else torch.float32
+        assert params7.is_cuda and inds.is_cuda and params7.device.index == self.device
+        assert params7.shape == (B, 7, M) and params7.dtype == tdtype and params7.is_contiguous()
+        assert inds.dtype == torch.int64 and inds.is_contiguous()
+        if ll is None:
+            ll = torch.empty((B, S), dtype=torch.float64, device=params7.device)
+        if grad and dlog is None:
+            dlog = torch.empty((B, S, 7, M), dtype=tdtype, device=params7.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(params7.device).cuda_stream
+        _check(
+            self._lib.phb_loglik_warmup_device(
+                self._handle, params7.data_ptr(), inds.data_ptr(), B, S, int(overlap), int(grad), ll.data_ptr(),
+                dlog.data_ptr() if grad else None, ctypes.c_void_p(stream),
+            )
+        )
+        return ll, (dlog if grad else None)
+
     # ---- device-resident entry (torch tensors are only used as device buffers here)
     def evaluate_device(self, params6, pi, inds, grad: bool, ll=None, dlog=None, stream=None):
         """Asynchronous evaluation on device buffers (torch CUDA tensors on this kernel's device).
