@@ -119,6 +119,21 @@ int phb_loglik_warmup_device(phb_kernel *k, const void *params7, const int64_t *
 int phb_loglik_warmup_host(phb_kernel *k, const void *params7, const int64_t *inds, int64_t B,
                            int64_t S, int64_t overlap, int want_grad, double *ll, void *dlog);
 
+/* HMM PARAMETER CONSTRUCTION on the device, float64 arithmetic (replaces MCMCParams.to_dm,
+ * params.py:94-131, and PSMCParams.from_dm, params.py:32-55, with transition.py:9-85 and
+ * size_history.py:123-193 behind it).  x is a device pointer to [B, P] doubles, P = 2 + n_epochs + 1:
+ * the flattened particle (t_tr[2], c_tr[n_epochs], rho_over_theta_tr; params.py:58-66).
+ * epoch_widths (host pointer, n_epochs ints summing to M) is the parsed PSMC pattern
+ * (util.py:8-37), theta the static mutation rate.  params7 receives [B, 7, M] FLOAT. */
+int phb_params_from_particles(phb_kernel *k, const double *x, int64_t B, const int32_t *epoch_widths,
+                              int n_epochs, double theta, void *params7, void *stream);
+
+/* Its vector-Jacobian product: cotangent [B, 7, M] FLOAT holds d l / d log(theta) (e.g. the
+ * per-particle sum of dlog over the minibatch); grad_x [B, P] doubles receives d l / d x - what
+ * JAX's reverse pass through jnp.log, from_dm and to_dm produces (gpu.py:361, model.py:50-51). */
+int phb_params_vjp(phb_kernel *k, const double *x, int64_t B, const int32_t *epoch_widths, int n_epochs,
+                   double theta, const void *cotangent, double *grad_x, void *stream);
+
 /* Wait for the kernel object's own stream AND for the stream of the most recent
  * phb_loglik_device call, then report deferred device-side errors. */
 int phb_sync(phb_kernel *k);

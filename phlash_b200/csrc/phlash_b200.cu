@@ -4,6 +4,7 @@
 // psmc_kernels.cuh.  No CPU fallback: every evaluation is a CUDA kernel launch or an error.
 #include "../../include/phlash_b200.h"
 #include "psmc_kernels.cuh"
+#include "psmc_params.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -539,6 +540,61 @@ int phb_loglik_warmup_host(phb_kernel *k, const void *params7, const int64_t *in
     if (want_grad)
         PHB_CUDA(cudaMemcpyAsync(dlog, k->dlog.ptr, size_t(B) * S * 7 * M * es, cudaMemcpyDeviceToHost, k->stream));
     return phb_sync(k);
+}
+
+static int fill_params_args(phb_kernel *k, const double *x, int64_t B, const int32_t *epoch_widths, int n_epochs,
+                            double theta, phb::ParamsArgs &a) {
+    if (int rc = check_handle(k)) return rc;
+    if (!x || !epoch_widths || B < 0) return fail(PHB_E_INVALID, "NULL pointer or negative batch");
+    if (n_epochs < 1 || n_epochs > phb::kMaxM) return fail(PHB_E_INVALID, "n_epochs=%d out of range", n_epochs);
+    int total = 0;
+    for (int e = 0; e < n_epochs; ++e) {
+        if (epoch_widths[e] <= 0) return fail(PHB_E_INVALID, "epochs must be positive");
+        total += epoch_widths[e];
+        a.widths[e] = epoch_widths[e];
+    }
+    if (total != k->M) return fail(PHB_E_INVALID, "pattern has %d states, kernel was built for M=%d", total, k->M);
+    if (!(theta > 0.0) || !std::isfinite(theta)) return fail(PHB_E_INVALID, "theta must be positive and finite");
+    a.x = x;
+    a.B = B;
+    a.n_epochs = n_epochs;
+    a.P = 2 + n_epochs + 1;
+    a.M = k->M;
+    a.theta = theta;
+    a.out_double = k->dbl;
+    return PHB_OK;
+}
+
+int phb_params_from_particles(phb_kernel *k, const double *x, int64_t B, const int32_t *epoch_widths, int n_epochs,
+                              double theta, void *params7, void *stream) {
+    phb::ParamsArgs a{};
+    if (int rc = fill_params_args(k, x, B, epoch_widths, n_epochs, theta, a)) return rc;
+    if (!params7) return fail(PHB_E_INVALID, "params7 is NULL");
+    if (B == 0) return PHB_OK;
+    PHB_CUDA(cudaSetDevice(k->device));
+    a.params7 = params7;
+    const int threads = 64;
+    phb::psmc_params_forward_kernel<<<unsigned((B + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    PHB_CUDA(cudaGetLastError());
+    k->launches += 1;
+    return PHB_OK;
+}
+
+int phb_params_vjp(phb_kernel *k, const double *x, int64_t B, const int32_t *epoch_widths, int n_epochs, double theta,
+                   const void *cotangent, double *grad_x, void *stream) {
+    phb::ParamsArgs a{};
+    if (int rc = fill_params_args(k, x, B, epoch_widths, n_epochs, theta, a)) return rc;
+    if (!cotangent || !grad_x) return fail(PHB_E_INVALID, "NULL pointer");
+    if (B == 0) return PHB_OK;
+    PHB_CUDA(cudaSetDevice(k->device));
+    a.cotangent = cotangent;
+    a.grad_x = grad_x;
+    const int threads = 64;
+    const int64_t n = B * a.P;
+    phb::psmc_params_vjp_kernel<<<unsigned((n + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    PHB_CUDA(cudaGetLastError());
+    k->launches += 1;
+    return PHB_OK;
 }
 
 }  // extern "C"

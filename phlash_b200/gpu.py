@@ -180,6 +180,53 @@ class _PSMCKernelBase:
         )
         return ll, (dlog if grad else None)
 
+    # ---- parameter construction on the device (params.py:32-55, 94-131; transition.py; size_history.py)
+    def params_from_particles(self, x, pattern: str, theta: float, stream=None):
+        """x: torch float64 CUDA tensor [B, P] of flattened particles (t_tr[2], c_tr, rho_over_theta_tr).
+        Returns the [B, 7, M] parameter blocks (kernel float type) as a torch tensor on the device."""
+        import torch
+
+        from phlash_b200.params import parse_pattern
+
+        widths = np.ascontiguousarray(parse_pattern(pattern), dtype=np.int32)
+        B, P = int(x.shape[0]), int(x.shape[1])
+        assert P == 2 + len(widths) + 1, "particle length does not match the pattern"
+        assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and x.device.index == self.device
+        tdtype = torch.float64 if self.double_precision else torch.float32
+        out = torch.empty((B, 7, self._M), dtype=tdtype, device=x.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+        _check(
+            self._lib.phb_params_from_particles(
+                self._handle, x.data_ptr(), B, _ptr(widths), len(widths), float(theta), out.data_ptr(),
+                ctypes.c_void_p(stream),
+            )
+        )
+        return out
+
+    def params_vjp(self, x, pattern: str, theta: float, cotangent, stream=None):
+        """cotangent [B, 7, M] = d l / d log(theta) (kernel float type).  Returns d l / d x [B, P]."""
+        import torch
+
+        from phlash_b200.params import parse_pattern
+
+        widths = np.ascontiguousarray(parse_pattern(pattern), dtype=np.int32)
+        B, P = int(x.shape[0]), int(x.shape[1])
+        tdtype = torch.float64 if self.double_precision else torch.float32
+        assert P == 2 + len(widths) + 1
+        assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous()
+        assert cotangent.shape == (B, 7, self._M) and cotangent.dtype == tdtype and cotangent.is_contiguous()
+        out = torch.empty((B, P), dtype=torch.float64, device=x.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+        _check(
+            self._lib.phb_params_vjp(
+                self._handle, x.data_ptr(), B, _ptr(widths), len(widths), float(theta), cotangent.data_ptr(),
+                out.data_ptr(), ctypes.c_void_p(stream),
+            )
+        )
+        return out
+
     # ---- device-resident entry (torch tensors are only used as device buffers here)
     def evaluate_device(self, params6, pi, inds, grad: bool, ll=None, dlog=None, stream=None):
         """Asynchronous evaluation on device buffers (torch CUDA tensors on this kernel's device).

@@ -35,3 +35,22 @@ class PSMCParams(NamedTuple):
     def to_block(self, dtype=None) -> np.ndarray:
         """Stack to [..., 7, M] (what the reference does with np.stack(pp, -2), gpu.py:189)."""
         return np.stack([np.asarray(a, dtype=dtype) for a in self], axis=-2)
+
+
+def parse_pattern(pattern: str):
+    """PSMC-style pattern string -> list of epoch widths (reference: src/phlash/util.py:8-37)."""
+    try:
+        epochs = []
+        for tok in pattern.split("+"):
+            if "*" in tok:
+                k, width = map(int, tok.split("*"))
+            else:
+                k, width = 1, int(tok)
+            epochs += [width] * k
+    except Exception:
+        raise ValueError("could not parse pattern")
+    if len(epochs) == 0:
+        raise ValueError("pattern must contain at least one epoch")
+    if any(e <= 0 for e in epochs):
+        raise ValueError("epochs must be positive")
+    return epochs
