@@ -101,3 +101,22 @@ def test_whole_chain_particle_to_gradient(golden):
         dn[p] -= h
         fd = (l2(up) - l2(dn)) / (2 * h)
         np.testing.assert_allclose(grad_x[1, p], fd, rtol=2e-5, atol=1e-6)
+
+
+def test_model_hmm_term(golden):
+    """phlash_b200.model.hmm_term_value_and_grad against the reference's log_density (golden F)
+    with the N / S weight of mcmc.py:244."""
+    import torch
+
+    from phlash_b200 import model
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    chunks, inds = golden["model_chunks"], golden["model_inds"]
+    kern = _PSMCKernelBase(16, chunks, double_precision=True)
+    dev = torch.device("cuda:0")
+    x = torch.tensor(golden["part_x"][:3], device=dev)
+    w = chunks.shape[0] / len(inds)
+    val, grad = model.hmm_term_value_and_grad(kern, x, PATTERN16, 1e-2, torch.tensor(inds, device=dev), 50, weight=w)
+    np.testing.assert_allclose(val.cpu().numpy(), w * golden["model_l2"], rtol=1e-10)
+    assert grad.shape == (3, 18) and torch.isfinite(grad).all()
+    assert model.default_minibatch_size(595, 1000) == 1 and model.default_minibatch_size(59500, 1000) == 5
