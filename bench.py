@@ -232,6 +232,7 @@ def main():
         e1.record()
         e1.synchronize()
         kernel_ms.append(kern.last_kernel_ms)
+    kernel_name = kern.last_kernel_name
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -286,7 +287,7 @@ def main():
                        "parallelism": f"dp{world}: chunks sharded, 1 all-reduce of [B,1+7M] per step" if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": hbm_achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
-                         "kernel": "psmc_loglik_kernel<float,8,2,16,grad>", "kernel_ms": k_ms,
+                         "kernel": kernel_name, "kernel_ms": k_ms,
                          "note": "1 algorithmic byte per site-transition; the binding pipe is FP32 FMA, see fp32"},
             "fp32": {"achieved_tflops": fp32_achieved, "peak_tflops": FFMA_PEAK_TFLOPS,
                      "frac": fp32_achieved / FFMA_PEAK_TFLOPS, "flop_per_site_transition": FLOP_PER_ST,

@@ -147,6 +147,10 @@ const int8_t *phb_device_data(const phb_kernel *k, int64_t *pitch);
  * Blocks until that kernel has finished. */
 float phb_last_kernel_ms(phb_kernel *k);
 
+/* Name of the kernel variant of the most recent evaluation, e.g.
+ * "psmc_loglik_kernel<float,MT=16,T=1,K=8,grad,NT=128>" ("" before the first one). */
+const char *phb_last_kernel_name(const phb_kernel *k);
+
 /* Number of kernels this library has launched on this object since creation. */
 int64_t phb_launch_count(const phb_kernel *k);
 

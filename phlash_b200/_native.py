@@ -38,6 +38,7 @@ SIGNATURES = {
     "phb_sync": (_i, [_vp]),
     "phb_device_data": (_vp, [_vp, ctypes.POINTER(_i64)]),
     "phb_last_kernel_ms": (ctypes.c_float, [_vp]),
+    "phb_last_kernel_name": (ctypes.c_char_p, [_vp]),
     "phb_launch_count": (_i64, [_vp]),
 }
 

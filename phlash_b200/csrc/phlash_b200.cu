@@ -87,6 +87,7 @@ struct phb_kernel {
     int force_T = 0;
     int num_sms = 0;
     int64_t launches = 0;
+    char last_name[96] = "";
     DeviceBuffer params, inds, ll, dlog, ckpt, gacc;
     size_t elem() const { return dbl ? sizeof(double) : sizeof(float); }
 };
@@ -120,8 +121,8 @@ const std::vector<Variant> &variants() {
         PHB_GRAD(float, 4, 1, 16, 128, 4)   // M = 4
         PHB_GRAD(float, 8, 1, 16, 128, 3)   // M = 8
         PHB_GRAD(float, 4, 2, 16, 128, 4)
-        PHB_GRAD(float, 8, 2, 16, 128, 3)   // M = 16 (first entry = default; PHB_NT=256 selects the next)
-        PHB_GRAD(float, 8, 2, 16, 256, 1)
+        PHB_GRAD(float, 16, 1, 8, 128, 2)   // M = 16: thread per pair, 255 registers, 2 warps per sub-partition
+        PHB_GRAD(float, 8, 2, 16, 128, 3)
         PHB_GRAD(float, 4, 4, 16, 128, 4)
         PHB_GRAD(float, 8, 4, 16, 128, 3)   // M = 32
         PHB_GRAD(float, 4, 8, 16, 128, 4)
@@ -222,6 +223,8 @@ int launch(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream) {
     PHB_CUDA(cudaEventRecord(k->ev1, stream));
     k->timed = true;
     k->launches += 1;
+    snprintf(k->last_name, sizeof k->last_name, "psmc_loglik_kernel<%s,MT=%d,T=%d,K=%d,%s,NT=%d>", v->dbl ? "double" : "float",
+             v->M / v->T, v->T, v->K, v->grad ? "grad" : "fwd", v->NT);
     return PHB_OK;
 }
 
@@ -337,6 +340,7 @@ int64_t phb_num_rows(const phb_kernel *k) { return k ? k->N : 0; }
 int64_t phb_row_length(const phb_kernel *k) { return k ? k->L : 0; }
 int phb_device(const phb_kernel *k) { return k ? k->device : -1; }
 int64_t phb_launch_count(const phb_kernel *k) { return k ? k->launches : 0; }
+const char *phb_last_kernel_name(const phb_kernel *k) { return k ? k->last_name : ""; }
 
 const int8_t *phb_device_data(const phb_kernel *k, int64_t *pitch) {
     if (!k) return nullptr;

@@ -84,6 +84,10 @@ class _PSMCKernelBase:
         return float(self._lib.phb_last_kernel_ms(self._handle))
 
     @property
+    def last_kernel_name(self) -> str:
+        return self._lib.phb_last_kernel_name(self._handle).decode()
+
+    @property
     def launch_count(self) -> int:
         return int(self._lib.phb_launch_count(self._handle))
 
