@@ -271,40 +271,95 @@ template <typename F, int MT, int T> __device__ __forceinline__ F pair_sum(const
 // half an ulp of a 50 000-site running sum are lost and the gradient is off by up to 5e-4.
 constexpr int kFlushSites = 1024;
 
-template <typename F, int MT> struct Grad {
+// ESM = true: the two emission rows are accumulated in shared memory instead (thread-per-pair
+// variant: 3 instructions per state become one 128-bit load + 4 FMA + one 128-bit store per 4
+// states, and 2*MT registers are freed).
+template <typename F, int MT, bool ESM> struct Grad;
+
+template <typename F, int MT> struct Grad<F, MT, false> {
     F b[MT], d[MT], u[MT], v[MT], e0[MT], e1[MT];
     __device__ __forceinline__ void clear() {
 #pragma unroll
         for (int k = 0; k < MT; ++k) b[k] = d[k] = u[k] = v[k] = e0[k] = e1[k] = F(0);
     }
-    // acc[i * stride] += window sums, then clear the registers
-    __device__ __forceinline__ void flush(double *acc, int64_t stride) {
-#define PHB_FLUSH_ROW(row, r)                                         \
-    _Pragma("unroll") for (int k = 0; k < MT; ++k) {                  \
-        /* fire-and-forget reduction: no loaded value to keep live */ \
-        atomicAdd(acc + int64_t((r) * MT + k) * stride, double(row[k])); \
-        row[k] = F(0);                                                \
-    }
-        PHB_FLUSH_ROW(b, 0)
-        PHB_FLUSH_ROW(d, 1)
-        PHB_FLUSH_ROW(u, 2)
-        PHB_FLUSH_ROW(v, 3)
-        PHB_FLUSH_ROW(e0, 4)
-        PHB_FLUSH_ROW(e1, 5)
-#undef PHB_FLUSH_ROW
+};
+template <typename F, int MT> struct Grad<F, MT, true> {
+    F b[MT], d[MT], u[MT], v[MT];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int k = 0; k < MT; ++k) b[k] = d[k] = u[k] = v[k] = F(0);
     }
 };
 
-// g.e{0,1} += x .* beta for the row selected by ob (nothing for a missing observation).
+// acc[i * stride] += window sum, then clear: fire-and-forget reduction, no loaded value kept live
 template <typename F, int MT>
-__device__ __forceinline__ void posterior_to_emission(const F (&beta)[MT], const F (&x)[MT], int ob, Grad<F, MT> &g) {
-    const F is0 = ob == 0 ? F(1) : F(0);
-    const F is1 = ob == 1 ? F(1) : F(0);
+__device__ __forceinline__ void flush_row(F (&row)[MT], int r, double *acc, int64_t stride) {
 #pragma unroll
     for (int k = 0; k < MT; ++k) {
-        const F gam = x[k] * beta[k];
-        g.e0[k] = fma(gam, is0, g.e0[k]);
-        g.e1[k] = fma(gam, is1, g.e1[k]);
+        atomicAdd(acc + int64_t(r * MT + k) * stride, double(row[k]));
+        row[k] = F(0);
+    }
+}
+
+// Shared-memory accumulators for the emission rows: [3][MT / W][NT] 128-bit words per CTA (row 2
+// swallows the contributions of missing observations so that no branch is needed).
+template <typename F, int MT, int NT> struct EmisAcc {
+    using V = typename Vec<F>::type;
+    static constexpr int W = Vec<F>::W;
+    static constexpr int QN = MT / W;
+    V *base;  // this thread's column
+    __device__ __forceinline__ void clear() {
+        F z[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i) z[i] = F(0);
+#pragma unroll
+        for (int i = 0; i < 3 * QN; ++i) base[i * NT] = pack(z);
+    }
+    // row(ob) += x .* beta
+    __device__ __forceinline__ void add(int ob, const F (&beta)[MT], const F (&x)[MT]) {
+        const int row = ob < 0 ? 2 : ob;
+#pragma unroll
+        for (int q = 0; q < QN; ++q) {
+            F a[W];
+            unpack<F>(base[(row * QN + q) * NT], a);
+#pragma unroll
+            for (int i = 0; i < W; ++i) a[i] = fma(x[q * W + i], beta[q * W + i], a[i]);
+            base[(row * QN + q) * NT] = pack(a);
+        }
+    }
+    __device__ __forceinline__ void flush(double *acc, int64_t stride) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+#pragma unroll
+            for (int q = 0; q < QN; ++q) {
+                F a[W], z[W];
+                unpack<F>(base[(r * QN + q) * NT], a);
+#pragma unroll
+                for (int i = 0; i < W; ++i) {
+                    atomicAdd(acc + int64_t((4 + r) * MT + q * W + i) * stride, double(a[i]));
+                    z[i] = F(0);
+                }
+                base[(r * QN + q) * NT] = pack(z);
+            }
+        }
+    }
+};
+
+// add the posterior x .* beta of a site to the emission row of its observation
+template <typename F, int MT, int NT, bool ESM>
+__device__ __forceinline__ void posterior_to_emission(const F (&beta)[MT], const F (&x)[MT], int ob, Grad<F, MT, ESM> &g,
+                                                      EmisAcc<F, MT, NT> &ea) {
+    if constexpr (ESM) {
+        ea.add(ob, beta, x);
+    } else {
+        const F is0 = ob == 0 ? F(1) : F(0);
+        const F is1 = ob == 1 ? F(1) : F(0);
+#pragma unroll
+        for (int k = 0; k < MT; ++k) {
+            const F gam = x[k] * beta[k];
+            g.e0[k] = fma(gam, is0, g.e0[k]);
+            g.e1[k] = fma(gam, is1, g.e1[k]);
+        }
     }
 }
 
@@ -318,10 +373,11 @@ __device__ __forceinline__ void posterior_to_emission(const F (&beta)[MT], const
 // With w = emis(ob) .* beta:  beta'_i = sum_{j<i} b_j w_j + d_i w_i + u_i sum_{j>i} v_j w_j
 //   d ll/d b_j += (sum_{i>j} x_i) w_j      d ll/d d_j += x_j w_j
 //   d ll/d u_i += x_i sum_{j>i} v_j w_j    d ll/d v_j += (sum_{i<j} u_i x_i) w_j
-template <typename F, int MT, int T, int NT>
+template <typename F, int MT, int T, int NT, bool ESM>
 __device__ __forceinline__ void backward_site(F (&beta)[MT], const F (&x)[MT], int ob, int ob_prev,
                                               const Params<F, MT> &p, const PartnerCoef<F, MT, T, true> &pc,
-                                              const EmisTable<F, MT, NT> &et, int sub, Grad<F, MT> &g) {
+                                              const EmisTable<F, MT, NT> &et, int sub, Grad<F, MT, ESM> &g,
+                                              EmisAcc<F, MT, NT> &ea) {
     F w[MT];
     et.get(ob, et.ones, w);
 #pragma unroll
@@ -373,7 +429,7 @@ __device__ __forceinline__ void backward_site(F (&beta)[MT], const F (&x)[MT], i
         q_run = fma(p.v[k], w[k], q_run);
         s_run += x[k];
     }
-    posterior_to_emission<F, MT>(beta, x, ob_prev, g);
+    posterior_to_emission<F, MT, NT, ESM>(beta, x, ob_prev, g, ea);
 }
 
 constexpr int kNorm = 4;  // the forward vector is rescaled after every kNorm-th site of a segment
@@ -403,8 +459,11 @@ template <int K> struct ObsWords {
 };
 
 // emission table always; the ring of forward vectors and block scales only for the gradient kernel
+// thread-per-pair layouts (MT >= 16) keep the emission-row accumulators in shared memory
+template <int MT> __host__ __device__ constexpr bool emis_acc_in_smem() { return MT >= 16; }
 template <typename F, int MT, int K, int NT, bool GRAD> constexpr size_t smem_bytes() {
-    return 16 + sizeof(F) * (size_t(2) * MT * NT + (GRAD ? size_t(K) * MT * NT + size_t(K / kNorm) * NT : 0));
+    return 16 + sizeof(F) * (size_t(2) * MT * NT +
+                             (GRAD ? size_t(K) * MT * NT + size_t(K / kNorm) * NT + (emis_acc_in_smem<MT>() ? size_t(3) * MT * NT : 0) : 0));
 }
 // checkpoint scratch bytes per resident warp
 template <typename F, int MT, int K> __host__ __device__ constexpr int64_t ckpt_bytes_per_warp(int64_t L) {
@@ -442,6 +501,9 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
     et.base = reinterpret_cast<V *>(smem_raw) + 1 + threadIdx.x;
     V *seg_s = reinterpret_cast<V *>(smem_raw) + 1 + 2 * QN * NT + warp * (K * QN * 32) + lane;
     F *scale_s = reinterpret_cast<F *>(reinterpret_cast<V *>(smem_raw) + 1 + 2 * QN * NT + kWarps * (K * QN * 32)) + warp * (K / kNorm * 32) + lane;
+    constexpr bool ESM = GRAD && emis_acc_in_smem<MT>();
+    EmisAcc<F, MT, NT> ea;
+    ea.base = reinterpret_cast<V *>(scale_s - lane - warp * (K / kNorm * 32) + (K / kNorm) * NT) + threadIdx.x;
     if (threadIdx.x == 0) {
         F one[W];
 #pragma unroll
@@ -528,8 +590,9 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
 
         if constexpr (GRAD) {
             // -------------------------------------------------------------- pass 2: adjoint
-            Grad<F, MT> g;
+            Grad<F, MT, ESM> g;
             g.clear();
+            if constexpr (ESM) ea.clear();
             F beta[MT];
             {
                 // after the last site: beta = 1 / sum(x) so that beta . x == 1, and the posterior of
@@ -537,7 +600,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                 const F tot = fast_rcp<F>(pair_sum<F, MT, T>(x));
 #pragma unroll
                 for (int k = 0; k < MT; ++k) beta[k] = tot;
-                posterior_to_emission<F, MT>(beta, x, int(obs[a.L - 1]), g);
+                posterior_to_emission<F, MT, NT, ESM>(beta, x, int(obs[a.L - 1]), g, ea);
             }
 #pragma unroll 1
             for (int i = 0; i < 6 * MT; ++i) PHB_GACC_BASE[int64_t(i) * PHB_GACC_STRIDE] = 0.0;
@@ -601,11 +664,24 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
 #pragma unroll
                             for (int q = 0; q < QN; ++q) unpack<F>(seg_s[((kb + j) * QN + q) * 32], &xin[q * W]);
                             const int ob_prev = j > 0 ? ObsWords<K>::byte_of(blk, j - 1) : ob_before;
-                            backward_site<F, MT, T, NT>(beta, xin, ObsWords<K>::byte_of(blk, j), ob_prev, p, pc, et, sub, g);
+                            backward_site<F, MT, T, NT, ESM>(beta, xin, ObsWords<K>::byte_of(blk, j), ob_prev, p, pc, et, sub, g, ea);
                         }
                     }
                 }
-                if ((seg & (kFlushSegs - 1)) == 0) g.flush(PHB_GACC_BASE, PHB_GACC_STRIDE);
+                if ((seg & (kFlushSegs - 1)) == 0) {
+                    double *acc = PHB_GACC_BASE;
+                    const int64_t stride = PHB_GACC_STRIDE;
+                    flush_row<F, MT>(g.b, 0, acc, stride);
+                    flush_row<F, MT>(g.d, 1, acc, stride);
+                    flush_row<F, MT>(g.u, 2, acc, stride);
+                    flush_row<F, MT>(g.v, 3, acc, stride);
+                    if constexpr (ESM) {
+                        ea.flush(acc, stride);
+                    } else {
+                        flush_row<F, MT>(g.e0, 4, acc, stride);
+                        flush_row<F, MT>(g.e1, 5, acc, stride);
+                    }
+                }
             }
             if (writer) {
                 F *out = static_cast<F *>(a.dlog) + pair * 7 * M + sub * MT;
