@@ -124,9 +124,11 @@ const std::vector<Variant> &variants() {
         PHB_GRAD(float, 16, 1, 8, 128, 2)   // M = 16: thread per pair, 255 registers, 2 warps per sub-partition
         PHB_GRAD(float, 8, 2, 16, 128, 3)
         PHB_GRAD(float, 4, 4, 16, 128, 4)
-        PHB_GRAD(float, 8, 4, 16, 128, 3)   // M = 32
+        PHB_GRAD(float, 16, 2, 8, 128, 2)   // M = 32
+        PHB_GRAD(float, 8, 4, 16, 128, 3)
         PHB_GRAD(float, 4, 8, 16, 128, 4)
-        PHB_GRAD(float, 8, 8, 16, 128, 3)   // M = 64
+        PHB_GRAD(float, 16, 4, 8, 128, 2)   // M = 64
+        PHB_GRAD(float, 8, 8, 16, 128, 3)
         PHB_GRAD(float, 4, 16, 16, 128, 4)
         // ---- float, forward only
         PHB_FWD(float, 4, 1, 16, 128, 4)    // M = 4

@@ -95,7 +95,7 @@ def random_data(rng, n, length, het=0.07, miss=0.02):
     return data
 
 
-@pytest.mark.parametrize("M,T", [(4, 0), (8, 0), (8, 2), (32, 0), (32, 8), (64, 0), (64, 16)])
+@pytest.mark.parametrize("M,T", [(4, 0), (8, 0), (8, 2), (16, 1), (32, 0), (32, 2), (32, 8), (64, 0), (64, 4), (64, 16)])
 def test_other_state_counts_fp32(M, T):
     """M = 32 / 64 are BASELINE.json configs 4 and 5; the reference cannot run them end to end
     (params.py:35) so the oracle is the only comparator."""
