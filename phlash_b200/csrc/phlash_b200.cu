@@ -84,6 +84,7 @@ struct phb_kernel {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     int *d_err = nullptr;
+    int *d_flags = nullptr;  // scratch word for validate_params_kernel
     int force_T = 0;
     int num_sms = 0;
     int64_t launches = 0;
@@ -312,6 +313,7 @@ int phb_create(int M, const int8_t *data, int64_t N, int64_t L, int double_preci
     if ((e = cudaStreamCreateWithFlags(&k->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&k->ev0)) != cudaSuccess || (e = cudaEventCreate(&k->ev1)) != cudaSuccess ||
         (e = cudaMalloc(reinterpret_cast<void **>(&k->d_err), sizeof(int))) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void **>(&k->d_flags), sizeof(int))) != cudaSuccess ||
         (e = cudaMemset(k->d_err, 0, sizeof(int))) != cudaSuccess)
         return cleanup(fail(PHB_E_CUDA, "stream/event setup: %s", cudaGetErrorString(e)));
     *out = k;
@@ -330,6 +332,7 @@ void phb_destroy(phb_kernel *k) {
     k->gacc.release();
     if (k->d_data) cudaFree(k->d_data);
     if (k->d_err) cudaFree(k->d_err);
+    if (k->d_flags) cudaFree(k->d_flags);
     if (k->ev0) cudaEventDestroy(k->ev0);
     if (k->ev1) cudaEventDestroy(k->ev1);
     if (k->stream) cudaStreamDestroy(k->stream);
@@ -488,18 +491,46 @@ int phb_loglik_host(phb_kernel *k, const void *params, const int64_t *inds, int6
     const int M = k->M;
     const size_t es = k->elem();
     const int64_t blk = 7 * M;
-    // Are rows b..emis1 identical across the S chunks of every particle (the way the reference
-    // builds its argument, model.py:55)?  Then the kernel can keep one copy per particle.
-    bool shared = true;
-    const char *p = static_cast<const char *>(params);
-    for (int64_t b = 0; b < B && shared; ++b)
-        for (int64_t s = 1; s < S; ++s)
-            if (memcmp(p + (b * S) * blk * es, p + (b * S + s) * blk * es, size_t(6) * M * es) != 0) {
-                shared = false;
-                break;
-            }
-    return host_eval(k, params, size_t(B) * S * blk, S * blk, shared ? 0 : blk, 6 * M, S * blk, blk, nullptr, 0,
-                     inds, B, S, want_grad, ll, dlog);
+    const size_t n_par = size_t(B) * S * blk;
+    for (int64_t s = 0; s < S; ++s)
+        if (inds[s] < 0 || inds[s] >= k->N)
+            return fail(PHB_E_INVALID, "0 <= inds[%lld]=%lld < N=%lld violated", (long long)s, (long long)inds[s], (long long)k->N);
+    PHB_CUDA(cudaSetDevice(k->device));
+    int rc;
+    if ((rc = k->params.reserve(n_par * es)) != PHB_OK) return rc;
+    if ((rc = k->inds.reserve(size_t(S) * sizeof(int64_t))) != PHB_OK) return rc;
+    if ((rc = k->ll.reserve(size_t(B) * S * sizeof(double))) != PHB_OK) return rc;
+    if (want_grad && (rc = k->dlog.reserve(size_t(B) * S * blk * es)) != PHB_OK) return rc;
+    PHB_CUDA(cudaMemcpyAsync(k->params.ptr, params, n_par * es, cudaMemcpyHostToDevice, k->stream));
+    PHB_CUDA(cudaMemcpyAsync(k->inds.ptr, inds, size_t(S) * sizeof(int64_t), cudaMemcpyHostToDevice, k->stream));
+    // On the device: are all parameters finite (gpu.py:214), and are rows b..emis1 identical across
+    // the S chunks of every particle (the way the reference builds its argument, model.py:55)?  Then
+    // the kernel reads one copy per particle.
+    PHB_CUDA(cudaMemsetAsync(k->d_flags, 0, sizeof(int), k->stream));
+    {
+        const int threads = 256;
+        const int blocks = int(std::min<int64_t>((int64_t(n_par) + threads - 1) / threads, int64_t(k->num_sms) * 8));
+        if (k->dbl)
+            phb::validate_params_kernel<double><<<blocks, threads, 0, k->stream>>>(static_cast<const double *>(k->params.ptr), B, S, M, k->d_flags);
+        else
+            phb::validate_params_kernel<float><<<blocks, threads, 0, k->stream>>>(static_cast<const float *>(k->params.ptr), B, S, M, k->d_flags);
+        PHB_CUDA(cudaGetLastError());
+        k->launches += 1;
+    }
+    int flags = 0;
+    PHB_CUDA(cudaMemcpyAsync(&flags, k->d_flags, sizeof(int), cudaMemcpyDeviceToHost, k->stream));
+    PHB_CUDA(cudaStreamSynchronize(k->stream));
+    if (flags & 1) return fail(PHB_E_INVALID, "not all parameters finite");
+    const bool shared = (flags & 2) == 0;
+    const char *d_params = static_cast<const char *>(k->params.ptr);
+    rc = phb_loglik_device(k, d_params, S * blk, shared ? 0 : blk, d_params + size_t(6) * M * es, S * blk, blk,
+                           static_cast<const int64_t *>(k->inds.ptr), B, S, want_grad, static_cast<double *>(k->ll.ptr),
+                           want_grad ? k->dlog.ptr : nullptr, k->stream);
+    if (rc != PHB_OK) return rc;
+    PHB_CUDA(cudaMemcpyAsync(ll, k->ll.ptr, size_t(B) * S * sizeof(double), cudaMemcpyDeviceToHost, k->stream));
+    if (want_grad)
+        PHB_CUDA(cudaMemcpyAsync(dlog, k->dlog.ptr, size_t(B) * S * blk * es, cudaMemcpyDeviceToHost, k->stream));
+    return phb_sync(k);
 }
 
 int phb_loglik_shared_host(phb_kernel *k, const void *params6, const void *pi, int pi_per_pair,

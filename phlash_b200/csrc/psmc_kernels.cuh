@@ -705,6 +705,27 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
     }
 }
 
+// Validation of an uploaded [B, S, 7, M] parameter block (host entry): bit 0 of *flags is set when
+// any value is non-finite, bit 1 when rows b..emis1 of some pair differ from those of pair (b, 0)
+// (i.e. the block is NOT "shared across the chunks of a particle").  Replaces two host passes over
+// the block (133 MB at the benchmark shape).
+template <typename F>
+__global__ void validate_params_kernel(const F *__restrict__ pa, int64_t B, int64_t S, int M, int *flags) {
+    const int64_t n = B * S * 7 * M;
+    const int64_t blk = int64_t(7) * M;
+    int bad = 0;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        const F v = pa[i];
+        if (!(v - v == F(0))) bad |= 1;  // NaN or +-inf
+        const int64_t pair = i / blk, r = i % blk;
+        if (r < int64_t(6) * M && (pair % S) != 0) {
+            const F first = pa[(pair - pair % S) * blk + r];
+            if (!(first == v)) bad |= 2;
+        }
+    }
+    if (bad) atomicOr(flags, bad);
+}
+
 #undef PHB_GACC_STRIDE
 #undef PHB_GACC_BASE
 

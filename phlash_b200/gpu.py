@@ -99,7 +99,7 @@ class _PSMCKernelBase:
         assert pa.shape == (B, S, 7, M)
         assert inds.shape == (S,)
         assert np.all(0 <= inds) & np.all(inds < self._N), f"0 <= {inds.min()=} < {inds.max()=} < N"
-        assert np.isfinite(pa).all(), "not all parameters finite"
+        # (the finiteness check of gpu.py:214 is done on the device by phb_loglik_host)
         pa = np.ascontiguousarray(pa, dtype=self.float_type)
         inds = np.ascontiguousarray(inds, dtype=np.int64)
         ll = np.zeros([B, S], dtype=np.float64) if ll_out is None else ll_out
@@ -341,8 +341,6 @@ class PSMCKernel:
         return self(pp, index, grad=False)
 
     def __call__(self, pp: PSMCParams, index, grad: bool):
-        for a in pp:
-            assert np.isfinite(a).all()
         pa, inds, added_B, added_S = _normalise_call(pp, index, self.M)
         D = len(self.gpu_kernels)
         if D == 1 or inds.shape[0] < D:
