@@ -43,7 +43,7 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
-def build_inputs(seed=0):
+def build_inputs(seed=0, with_full_chunks=False):
     from benchdata import synth
     from phlash_b200.data import _chunk_het_matrix, split_warmup
 
@@ -52,6 +52,8 @@ def build_inputs(seed=0):
     _, data = split_warmup(chunks, OVERLAP)
     # the reference rejects rows without a single observation (gpu.py:111-113)
     assert np.all(data.max(axis=1) > -1)
+    if with_full_chunks:
+        return data, synth.particles(M, N_PARTICLES), chunks
     return data, synth.particles(M, N_PARTICLES)
 
 
@@ -139,6 +141,41 @@ def reference_gpu(data, pps):
             "what": "reference loglik_grad (src/phlash/gpu.py:575-692), fp32, grid (B,S) x block (7,M)"}
 
 
+def likelihood_step(local_rank, chunks_full, rank, world):
+    """One whole likelihood evaluation of an SVGD iteration on the device: particles -> parameters
+    -> fused warm-up loglik+grad over the minibatch -> VJP to the particles (what model.log_density's
+    HMM term and its reverse pass do in the reference: model.py:50-57, params.py:32-55).  Timed at
+    the reference's default minibatch (S = 5, mcmc.py:119-121) and at S = N.  The SVGD update
+    itself (blackjax) is not part of this repository."""
+    import torch
+
+    from phlash_b200 import model
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    dev = torch.device("cuda", local_rank)
+    kern = _PSMCKernelBase(M, chunks_full, double_precision=False, device=local_rank)
+    xs = np.load(os.path.join(ROOT, "benchdata", f"particles_M{M}.npz"))["xs"][:N_PARTICLES]
+    x = torch.tensor(xs, dtype=torch.float64, device=dev)
+    out = {}
+    for name, S in (("S5", 5), ("SN", chunks_full.shape[0])):
+        inds = torch.arange(S, dtype=torch.int64, device=dev) * (chunks_full.shape[0] // S)
+        for _ in range(2):
+            model.hmm_term_value_and_grad(kern, x, "14*1+1*2", 1e-2, inds, OVERLAP, rank=rank, world=world)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5 if S == 5 else 2
+        e0.record()
+        for _ in range(reps):
+            val, grad = model.hmm_term_value_and_grad(kern, x, "14*1+1*2", 1e-2, inds, OVERLAP, rank=rank, world=world)
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        assert torch.isfinite(val).all() and torch.isfinite(grad).all()
+        out[name] = {"particles": N_PARTICLES, "minibatch_chunks": S, "bins_per_chunk": int(chunks_full.shape[1]),
+                     "ms": ms, "evaluations_per_s": 1e3 / ms}
+    return out
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
@@ -191,7 +228,7 @@ def main():
     from phlash_b200.gpu import _PSMCKernelBase
 
     # every rank scores its own diploid (weak scaling; the observation matrix is resident per GPU)
-    data, pps = build_inputs(seed=rank)
+    data, pps, chunks_full = build_inputs(seed=rank, with_full_chunks=True)
     kern = _PSMCKernelBase(M, data, double_precision=False, device=local_rank)
     n_chunks, length = data.shape
     B, S = N_PARTICLES, n_chunks
@@ -267,6 +304,9 @@ def main():
     e2e_value = world * st_per_step / float(t.item())
     assert np.isfinite(ll_np).all() and np.allclose(ll_np, ll_d.cpu().numpy(), rtol=1e-9)
 
+    lik_step = None
+    if not args.skip_baselines:
+        lik_step = likelihood_step(local_rank, chunks_full, rank, world)
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         k_ms = float(np.mean(kernel_ms))
@@ -298,6 +338,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if lik_step is not None:
+            line["likelihood_step"] = lik_step
         if not args.skip_baselines:
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline(data, pps).items() if k != "seconds_per_step"}
             try:
