@@ -239,21 +239,20 @@ __device__ __forceinline__ void forward_site(F (&x)[MT], const Params<F, MT> &p,
         pre_run = lanes_before<F, T>(tu[0] + tu[1], sub);
         suf_run = lanes_after<F, T>(tx[0] + tx[1], sub);
     }
-    F suf[MT];
+    // The ascending chain (prefix of u.*x) and the descending chain (suffix of x) are independent:
+    // walk them from both ends in the same loop so that their latencies overlap (each is MT
+    // dependent operations long), then combine.
+    F part[MT], suf[MT];
 #pragma unroll
-    for (int k = MT - 1; k >= 0; --k) {
-        suf[k] = suf_run;
-        suf_run += x[k];
+    for (int i = 0; i < MT; ++i) {
+        const int k = i, j = MT - 1 - i;
+        part[k] = fma(p.v[k], pre_run, p.d[k] * x[k]);
+        pre_run = fma(p.u[k], x[k], pre_run);
+        suf[j] = suf_run;
+        suf_run += x[j];
     }
 #pragma unroll
-    for (int k = 0; k < MT; ++k) {
-        const F xk = x[k];
-        F o = p.d[k] * xk;
-        o = fma(p.v[k], pre_run, o);
-        o = fma(p.b[k], suf[k], o);
-        pre_run = fma(p.u[k], xk, pre_run);
-        x[k] = o * e[k];
-    }
+    for (int k = 0; k < MT; ++k) x[k] = fma(p.b[k], suf[k], part[k]) * e[k];
 }
 
 // sum of x over the whole pair
@@ -410,25 +409,27 @@ __device__ __forceinline__ void backward_site(F (&beta)[MT], const F (&x)[MT], i
         b_run = lanes_before<F, T>(tb, sub);
         x_run = lanes_before<F, T>(tx, sub);
     }
-    // ascending sweep: heads  Pb_k = sum_{j<k} b_j w_j  and  Px_k = sum_{j<k} u_j x_j
-    // (beta is dead once w has been formed, so it collects the new vector)
+    // Ascending heads  Pb_k = sum_{j<k} b_j w_j,  Px_k = sum_{j<k} u_j x_j  and descending tails
+    // Q_k = sum_{j>k} v_j w_j,  S_k = sum_{j>k} x_j  are independent chains: walk them from both ends
+    // in one loop so that their latencies overlap.  (beta is dead once w has been formed, so it
+    // collects the new vector: head part first, tail part added where the sweeps have crossed.)
+    F tailq[MT];
 #pragma unroll
-    for (int k = 0; k < MT; ++k) {
+    for (int i = 0; i < MT; ++i) {
+        const int k = i, j = MT - 1 - i;
         beta[k] = fma(p.d[k], w[k], b_run);
         g.d[k] = fma(x[k], w[k], g.d[k]);
         g.v[k] = fma(x_run, w[k], g.v[k]);
         b_run = fma(p.b[k], w[k], b_run);
         x_run = fma(p.u[k], x[k], x_run);
+        tailq[j] = q_run;
+        g.u[j] = fma(x[j], q_run, g.u[j]);
+        g.b[j] = fma(s_run, w[j], g.b[j]);
+        q_run = fma(p.v[j], w[j], q_run);
+        s_run += x[j];
     }
-    // descending sweep: tails  Q_k = sum_{j>k} v_j w_j  and  S_k = sum_{j>k} x_j
 #pragma unroll
-    for (int k = MT - 1; k >= 0; --k) {
-        beta[k] = fma(p.u[k], q_run, beta[k]);
-        g.u[k] = fma(x[k], q_run, g.u[k]);
-        g.b[k] = fma(s_run, w[k], g.b[k]);
-        q_run = fma(p.v[k], w[k], q_run);
-        s_run += x[k];
-    }
+    for (int k = 0; k < MT; ++k) beta[k] = fma(p.u[k], tailq[k], beta[k]);
     posterior_to_emission<F, MT, NT, ESM>(beta, x, ob_prev, g, ea);
 }
 
