@@ -57,6 +57,21 @@ int phb_device_count(void);
 int phb_create(int M, const int8_t *data, int64_t N, int64_t L, int double_precision, int device,
                phb_kernel **out);
 
+/* Create a kernel object from BINNED CONTIGS instead of ready-made chunks: het is host int8
+ * [n_rows, length] (one row per diploid of one contig); the overlapping windows of
+ * _chunk_het_matrix (data.py:37-61: ceil(length / W) windows of W = chunk_size + overlap bins per
+ * row, starting every chunk_size bins, padded with -1, values clipped to [-1, 1]) are cut on the
+ * device.  The object then holds N = n_rows * ceil(length / W) rows of W bins - what
+ * Contig.to_chunked + np.concatenate produce (data.py:102-112, 558) - ready for
+ * phb_loglik_warmup_* with the same `overlap`.  Windows without a single observation are rejected
+ * like in phb_create (gpu.py:111-113). */
+int phb_create_from_contig(int M, const int8_t *het, int64_t n_rows, int64_t length, int64_t overlap,
+                           int64_t chunk_size, int double_precision, int device, phb_kernel **out);
+
+/* Copy the resident observation matrix back to the host as [N, L] (tests; the reference keeps its
+ * chunks on the host). */
+int phb_download_data(const phb_kernel *k, int8_t *out);
+
 /* Replaces _PSMCKernelBase.__del__ (gpu.py:153-174).  NULL is allowed. */
 void phb_destroy(phb_kernel *k);
 

@@ -20,6 +20,8 @@ SIGNATURES = {
     "phb_last_error": (ctypes.c_char_p, []),
     "phb_device_count": (_i, []),
     "phb_create": (_i, [_i, _vp, _i64, _i64, _i, _i, ctypes.POINTER(_vp)]),
+    "phb_create_from_contig": (_i, [_i, _vp, _i64, _i64, _i64, _i64, _i, _i, ctypes.POINTER(_vp)]),
+    "phb_download_data": (_i, [_vp, _vp]),
     "phb_destroy": (None, [_vp]),
     "phb_M": (_i, [_vp]),
     "phb_double_precision": (_i, [_vp]),

@@ -255,6 +255,46 @@ int phb_device_count(void) {
     return n;
 }
 
+// Shared part of the constructors: device checks, handle, data buffer [N, pitch], stream, events.
+static int new_kernel(int M, int64_t N, int64_t L, int double_precision, int device, phb_kernel **out) {
+    *out = nullptr;
+    if (!(M == 4 || M == 8 || M == 16 || M == 32 || M == 64))
+        return fail(PHB_E_INVALID, "M=%d is not supported (4, 8, 16, 32 or 64)", M);
+    int ndev = 0;
+    PHB_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(PHB_E_INVALID, "device %d out of range (%d visible)", device, ndev);
+    PHB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PHB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(PHB_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    phb_kernel *k = new (std::nothrow) phb_kernel();
+    if (!k) return fail(PHB_E_NOMEM, "host allocation failed");
+    k->M = M;
+    k->dbl = double_precision ? 1 : 0;
+    k->device = device;
+    k->N = N;
+    k->L = L;
+    k->pitch = (L + 15) / 16 * 16;
+    k->num_sms = prop.multiProcessorCount;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&k->d_data), size_t(N) * size_t(k->pitch));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        phb_destroy(k);
+        return fail(PHB_E_NOMEM, "While trying to allocate %lld bytes on GPU: %s", (long long)(N * k->pitch), cudaGetErrorString(e));
+    }
+    if ((e = cudaStreamCreateWithFlags(&k->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&k->ev0)) != cudaSuccess || (e = cudaEventCreate(&k->ev1)) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void **>(&k->d_err), sizeof(int))) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void **>(&k->d_flags), sizeof(int))) != cudaSuccess ||
+        (e = cudaMemset(k->d_err, 0, sizeof(int))) != cudaSuccess) {
+        phb_destroy(k);
+        return fail(PHB_E_CUDA, "stream/event setup: %s", cudaGetErrorString(e));
+    }
+    *out = k;
+    return PHB_OK;
+}
+
 int phb_create(int M, const int8_t *data, int64_t N, int64_t L, int double_precision, int device,
                phb_kernel **out) {
     if (!out) return fail(PHB_E_INVALID, "out is NULL");
@@ -272,51 +312,73 @@ int phb_create(int M, const int8_t *data, int64_t N, int64_t L, int double_preci
         }
         if (!any) return fail(PHB_E_DATA, "data contains observations with all missing values (row %lld)", (long long)i);
     }
-    int ndev = 0;
-    PHB_CUDA(cudaGetDeviceCount(&ndev));
-    if (device < 0 || device >= ndev) return fail(PHB_E_INVALID, "device %d out of range (%d visible)", device, ndev);
-    PHB_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    PHB_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10)
-        return fail(PHB_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
-
-    phb_kernel *k = new (std::nothrow) phb_kernel();
-    if (!k) return fail(PHB_E_NOMEM, "host allocation failed");
-    k->M = M;
-    k->dbl = double_precision ? 1 : 0;
-    k->device = device;
-    k->N = N;
-    k->L = L;
-    k->pitch = (L + 15) / 16 * 16;
-    k->num_sms = prop.multiProcessorCount;
-    auto cleanup = [&](int rc) {
+    phb_kernel *k = nullptr;
+    if (int rc = new_kernel(M, N, L, double_precision, device, &k)) return rc;
+    // clip to [-1, 1] on the way in (gpu.py:108-110); padding columns are never read as sites
+    std::vector<int8_t> staged(size_t(N) * size_t(k->pitch), int8_t(-1));
+    for (int64_t i = 0; i < N; ++i) {
+        const int8_t *src = data + i * L;
+        int8_t *dst = staged.data() + i * k->pitch;
+        for (int64_t j = 0; j < L; ++j) dst[j] = src[j] > 1 ? int8_t(1) : src[j];
+    }
+    cudaError_t e = cudaMemcpy(k->d_data, staged.data(), staged.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
         phb_destroy(k);
-        return rc;
-    };
-    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&k->d_data), size_t(N) * size_t(k->pitch));
+        return fail(PHB_E_CUDA, "cudaMemcpy(data): %s", cudaGetErrorString(e));
+    }
+    *out = k;
+    return PHB_OK;
+}
+
+int phb_create_from_contig(int M, const int8_t *het, int64_t n_rows, int64_t length, int64_t overlap,
+                           int64_t chunk_size, int double_precision, int device, phb_kernel **out) {
+    if (!out) return fail(PHB_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!het || n_rows <= 0 || length <= 0) return fail(PHB_E_INVALID, "het must be a non-empty [n_rows, length] int8 matrix");
+    if (overlap < 0 || chunk_size <= 0) return fail(PHB_E_INVALID, "need overlap >= 0 and chunk_size > 0");
+    const int64_t width = chunk_size + overlap;
+    const int64_t n_chunks = (length + width - 1) / width;
+    // host-side checks of the reference on the windows (values >= -1; every window has an observation)
+    for (int64_t n = 0; n < n_rows; ++n) {
+        const int8_t *row = het + n * length;
+        for (int64_t j = 0; j < length; ++j)
+            if (row[j] < -1) return fail(PHB_E_DATA, "het[%lld, %lld] = %d < -1", (long long)n, (long long)j, row[j]);
+        for (int64_t kk = 0; kk < n_chunks; ++kk) {
+            bool any = false;
+            const int64_t lo = kk * chunk_size, hi = std::min(length, lo + width);
+            for (int64_t j = lo; j < hi && !any; ++j) any = row[j] > -1;
+            if (!any) return fail(PHB_E_DATA, "data contains observations with all missing values (row %lld, chunk %lld)", (long long)n, (long long)kk);
+        }
+    }
+    phb_kernel *k = nullptr;
+    if (int rc = new_kernel(M, n_rows * n_chunks, width, double_precision, device, &k)) return rc;
+    int8_t *d_het = nullptr;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&d_het), size_t(n_rows) * size_t(length));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_het, het, size_t(n_rows) * size_t(length), cudaMemcpyHostToDevice, k->stream);
+    if (e == cudaSuccess) {
+        const int64_t total = k->N * k->pitch;
+        const int threads = 256;
+        const int blocks = int(std::min<int64_t>((total + threads - 1) / threads, int64_t(k->num_sms) * 16));
+        phb::chunk_het_kernel<<<blocks, threads, 0, k->stream>>>(d_het, n_rows, length, chunk_size, width, n_chunks, k->d_data, k->pitch);
+        e = cudaGetLastError();
+        k->launches += 1;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(k->stream);
+    if (d_het) cudaFree(d_het);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        return cleanup(fail(PHB_E_NOMEM, "While trying to allocate %lld bytes on GPU: %s", (long long)(N * k->pitch), cudaGetErrorString(e)));
+        phb_destroy(k);
+        return fail(e == cudaErrorMemoryAllocation ? PHB_E_NOMEM : PHB_E_CUDA, "chunking on the device: %s", cudaGetErrorString(e));
     }
-    // clip to [-1, 1] on the way in (gpu.py:108-110); padding columns are never read as sites
-    {
-        std::vector<int8_t> staged(size_t(N) * size_t(k->pitch), int8_t(-1));
-        for (int64_t i = 0; i < N; ++i) {
-            const int8_t *src = data + i * L;
-            int8_t *dst = staged.data() + i * k->pitch;
-            for (int64_t j = 0; j < L; ++j) dst[j] = src[j] > 1 ? int8_t(1) : src[j];
-        }
-        e = cudaMemcpy(k->d_data, staged.data(), staged.size(), cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) return cleanup(fail(PHB_E_CUDA, "cudaMemcpy(data): %s", cudaGetErrorString(e)));
-    }
-    if ((e = cudaStreamCreateWithFlags(&k->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaEventCreate(&k->ev0)) != cudaSuccess || (e = cudaEventCreate(&k->ev1)) != cudaSuccess ||
-        (e = cudaMalloc(reinterpret_cast<void **>(&k->d_err), sizeof(int))) != cudaSuccess ||
-        (e = cudaMalloc(reinterpret_cast<void **>(&k->d_flags), sizeof(int))) != cudaSuccess ||
-        (e = cudaMemset(k->d_err, 0, sizeof(int))) != cudaSuccess)
-        return cleanup(fail(PHB_E_CUDA, "stream/event setup: %s", cudaGetErrorString(e)));
     *out = k;
+    return PHB_OK;
+}
+
+int phb_download_data(const phb_kernel *k, int8_t *out) {
+    if (int rc = check_handle(k)) return rc;
+    if (!out) return fail(PHB_E_INVALID, "out is NULL");
+    PHB_CUDA(cudaSetDevice(k->device));
+    PHB_CUDA(cudaMemcpy2D(out, size_t(k->L), k->d_data, size_t(k->pitch), size_t(k->L), size_t(k->N), cudaMemcpyDeviceToHost));
     return PHB_OK;
 }
 

@@ -706,6 +706,25 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
     }
 }
 
+// Device-side chunking (reference: _chunk_het_matrix, data.py:37-61): out[n * n_chunks + k][j] =
+// clip(het[n][k * chunk_size + j], -1, 1) for j < W = chunk_size + overlap, -1 beyond the end of the
+// row (also fills the pitch padding).  One thread per output byte.
+__global__ void chunk_het_kernel(const int8_t *__restrict__ het, int64_t n_rows, int64_t length, int64_t chunk_size,
+                                 int64_t width, int64_t n_chunks, int8_t *__restrict__ out, int64_t pitch) {
+    const int64_t total = n_rows * n_chunks * pitch;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t row = i / pitch, j = i % pitch;
+        const int64_t n = row / n_chunks, k = row % n_chunks;
+        const int64_t src = k * chunk_size + j;
+        int8_t v = -1;
+        if (j < width && src < length) {
+            v = het[n * length + src];
+            v = v > 1 ? int8_t(1) : (v < -1 ? int8_t(-1) : v);
+        }
+        out[i] = v;
+    }
+}
+
 // Validation of an uploaded [B, S, 7, M] parameter block (host entry): bit 0 of *flags is set when
 // any value is non-finite, bit 1 when rows b..emis1 of some pair differ from those of pair (b, 0)
 // (i.e. the block is NOT "shared across the chunks of a particle").  Replaces two host passes over

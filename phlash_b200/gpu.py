@@ -66,6 +66,39 @@ class _PSMCKernelBase:
         self._handle = handle
         self.device = int(device)
 
+    @classmethod
+    def from_contig(cls, M: int, het_matrix: np.ndarray, overlap: int, chunk_size: int,
+                    double_precision: bool = False, device: int = 0) -> "_PSMCKernelBase":
+        """Kernel object on the chunks of one binned contig, cut ON THE DEVICE with the geometry of
+        _chunk_het_matrix (data.py:37-61).  The object holds full chunks [N, overlap + chunk_size]:
+        use evaluate_warmup(..., overlap=overlap)."""
+        het = np.asarray(het_matrix)
+        assert het.ndim == 2
+        assert het.min() >= -1
+        het = np.ascontiguousarray(het.clip(-1, 1).astype(np.int8))
+        self = cls.__new__(cls)
+        self.double_precision = bool(double_precision)
+        self._M = int(M)
+        self._lib = _native.lib()
+        handle = ctypes.c_void_p()
+        _check(
+            self._lib.phb_create_from_contig(
+                self._M, _ptr(het), het.shape[0], het.shape[1], int(overlap), int(chunk_size),
+                int(self.double_precision), int(device), ctypes.byref(handle)
+            )
+        )
+        self._handle = handle
+        self.device = int(device)
+        self._N = int(self._lib.phb_num_rows(handle))
+        self._L = int(self._lib.phb_row_length(handle))
+        return self
+
+    def download_data(self) -> np.ndarray:
+        """The resident observation matrix [N, L] copied back to the host."""
+        out = np.empty((self._N, self._L), dtype=np.int8)
+        _check(self._lib.phb_download_data(self._handle, _ptr(out)))
+        return out
+
     def __del__(self):
         handle = getattr(self, "_handle", None)
         if handle is not None and handle.value:

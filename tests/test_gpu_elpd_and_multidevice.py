@@ -53,3 +53,35 @@ def test_two_devices_in_one_process(golden):
     # a single chunk (fewer chunks than devices) must not dead-lock (reference FIXME, gpu.py:404)
     ll1 = two(PSMCParams.from_block(pa[:, :1]), inds[:1], grad=False)
     np.testing.assert_array_equal(ll1, one[0][:, :1])
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_chunking_on_the_device_is_bit_exact(golden, tag):
+    """phb_create_from_contig cuts the windows of _chunk_het_matrix (data.py:37-61) on the device;
+    compared with the reference function's own output (golden G)."""
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    ov, cs = (int(v) for v in golden[f"chunk_{tag}_geom"])
+    het = golden[f"chunk_{tag}_in"]
+    want = golden[f"chunk_{tag}_out"]
+    if not np.all(want.max(axis=1) > -1):
+        with pytest.raises(AssertionError):
+            _PSMCKernelBase.from_contig(16, het, ov, cs)
+        return
+    kern = _PSMCKernelBase.from_contig(16, het, ov, cs)
+    np.testing.assert_array_equal(kern.download_data(), want)
+
+
+def test_contig_to_likelihood_in_one_object(golden):
+    """binned contig -> device chunking -> fused warm-up evaluation, against the host-chunked path."""
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    het, inds = golden["model_het"], golden["model_inds"]
+    pps = golden["part_pp"][:3]
+    k_dev = _PSMCKernelBase.from_contig(16, het, 50, 500, double_precision=True)
+    k_host = _PSMCKernelBase(16, golden["model_chunks"], double_precision=True)
+    np.testing.assert_array_equal(k_dev.download_data(), golden["model_chunks"])
+    a = k_dev.evaluate_warmup(pps, inds, 50, True)
+    b = k_host.evaluate_warmup(pps, inds, 50, True)
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1], b[1])
