@@ -80,6 +80,46 @@ __global__ void ffma_accumulate(float *out, const float *in) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// packed f32x2 FMA (Blackwell FFMA2): 16 independent float2 chains
+__global__ void ffma2_shared_operands(float *out, float b, float c) {
+    float2 a[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) a[i] = make_float2(threadIdx.x * 1e-3f + i, threadIdx.x * 2e-3f + i);
+    const float2 bb = make_float2(b, b * 0.5f), cc = make_float2(c, c * 2.f);
+    for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) a[i] = __ffma2_rn(a[i], bb, cc);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) s += a[i].x + a[i].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// the same number of FMAs as ffma2_shared_operands but mixed 1:1 with scalar FFMA chains:
+// does FFMA2 leave issue slots for other FMA-pipe instructions?
+__global__ void ffma2_plus_scalar(float *out, float b, float c) {
+    float2 a[8];
+    float s1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        a[i] = make_float2(threadIdx.x * 1e-3f + i, threadIdx.x * 2e-3f + i);
+        s1[i] = threadIdx.x * 3e-3f + i;
+    }
+    const float2 bb = make_float2(b, b * 0.5f), cc = make_float2(c, c * 2.f);
+    for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            a[i] = __ffma2_rn(a[i], bb, cc);
+            s1[i] = fmaf(s1[i], b, c);
+        }
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i].x + a[i].y + s1[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void shfl_rate(float *out) {
     float a[8];
 #pragma unroll
@@ -169,6 +209,8 @@ int main() {
     float t1 = time_ms([&] { ffma_shared_operands<<<ctas, threads>>>(out, 0.999f, 1e-3f); }, 10);
     float t2 = time_ms([&] { ffma_distinct_operands<<<ctas, threads>>>(out, in); }, 10);
     float t3 = time_ms([&] { ffma_accumulate<<<ctas, threads>>>(out, in); }, 10);
+    float t7 = time_ms([&] { ffma2_shared_operands<<<ctas, threads>>>(out, 0.999f, 1e-3f); }, 10);
+    float t8 = time_ms([&] { ffma2_plus_scalar<<<ctas, threads>>>(out, 0.999f, 1e-3f); }, 10);
     float t4 = time_ms([&] { shfl_rate<<<ctas, threads>>>(out); }, 10);
     float t5 = time_ms([&] { lds_broadcast_rate<<<ctas, threads>>>(out); }, 10);
     CHECK(cudaFuncSetAttribute(lds_private_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * threads * 16));
@@ -180,6 +222,8 @@ int main() {
     printf(" \"ffma_shared_operands_tflops\": %.2f,\n", 2 * fma_ops / (t1 * 1e-3) / 1e12);
     printf(" \"ffma_distinct_operands_tflops\": %.2f,\n", 2 * fma_ops / (t2 * 1e-3) / 1e12);
     printf(" \"ffma_accumulate_mix_tflops\": %.2f,\n", 2 * fma_ops / (t3 * 1e-3) / 1e12);
+    printf(" \"ffma2_packed_tflops\": %.2f,\n", 2 * 2 * fma_ops / (t7 * 1e-3) / 1e12);
+    printf(" \"ffma2_plus_scalar_tflops\": %.2f,\n", 2 * (lanes * kIters * 8 * 3) / (t8 * 1e-3) / 1e12);
     printf(" \"shfl_warp_instr_per_sec\": %.4g,\n", lanes / 32 * kIters * 8 / (t4 * 1e-3));
     printf(" \"shfl_warp_instr_per_clk_per_sm_at_1965MHz\": %.3f,\n", lanes / 32 * kIters * 8 / (t4 * 1e-3) / sms / 1.965e9);
     printf(" \"lds128_broadcast_warp_instr_per_clk_per_sm_at_1965MHz\": %.3f,\n", lanes / 32 * kIters * 16 / (t5 * 1e-3) / sms / 1.965e9);
