@@ -8,76 +8,77 @@ NOT installable in this repository's build image, so this module is exercised on
 here - the kernel calls it makes are the ones tests/test_gpu_parity.py covers through the same
 ``PSMCKernel.__call__``.
 
-Glue mirrored from the reference: custom_vjp over (log_params, index) with the kernel as a
-non-differentiable argument, forward ALWAYS evaluates value and gradient, backward is g * dlog
-(src/phlash/gpu.py:441-472); the callback is jax.pure_callback(..., vectorized=True).
+The JAX contract it honours is the reference's (src/phlash/gpu.py:441-472), see
+``_differentiable_loglik``; identity hashing keeps the object usable as a static jit argument
+(src/phlash/mcmc.py:199).
 """
 
 from __future__ import annotations
 
-from functools import partial, singledispatchmethod
-
 import jax
 import jax.numpy as jnp
 import numpy as np
-from jax import custom_vjp
 
 import phlash.size_history
 from phlash.params import PSMCParams
 from phlash_b200.gpu import CudaError, PSMCKernel as _B200Kernel  # noqa: F401  (CudaError re-exported)
+from phlash_b200.params import PSMCParams as _HostParams
+
+
+def _differentiable_loglik(kern: "PSMCKernel"):
+    """log-likelihood as a function of (log-parameters, index) whose reverse rule is the gradient the
+    kernel returns.  Contract of the reference (src/phlash/gpu.py:441-472): the primal call asks the
+    kernel for the value only, the forward rule of the VJP always asks for value + gradient and keeps
+    the gradient as residual, the backward rule scales it by the cotangent; `index` gets no gradient."""
+
+    def host_call(log_params, index, want_grad):
+        params = jax.tree.map(jnp.exp, log_params)
+        value_t = jax.ShapeDtypeStruct((), jnp.float64)
+        if not want_grad:
+            return jax.pure_callback(kern, value_t, pp=params, index=index, grad=False, vectorized=True)
+        leaf_t = jax.ShapeDtypeStruct((kern.M,), kern.float_type)
+        out_t = (value_t, PSMCParams(*([leaf_t] * len(PSMCParams._fields))))
+        return jax.pure_callback(kern, out_t, pp=params, index=index, grad=True, vectorized=True)
+
+    @jax.custom_vjp
+    def loglik(log_params, index):
+        return host_call(log_params, index, False)
+
+    def forward(log_params, index):
+        value, dlog = host_call(log_params, index, True)
+        return value, dlog
+
+    def backward(dlog, cotangent):
+        return jax.tree.map(lambda leaf: cotangent * leaf, dlog), None
+
+    loglik.defvjp(forward, backward)
+    return loglik
 
 
 class PSMCKernel:
-    """Same constructor as the reference (src/phlash/gpu.py:338): M, data, double_precision, num_gpus."""
+    """Same constructor and attributes as the reference class (src/phlash/gpu.py:328-357)."""
 
     def __init__(self, M, data, double_precision=False, num_gpus: int = None):
         self._impl = _B200Kernel(M=M, data=np.asarray(data), double_precision=double_precision, num_gpus=num_gpus)
         self.M = M
         self.double_precision = double_precision
+        self._loglik = _differentiable_loglik(self)
 
     @property
     def float_type(self):
         return self._impl.float_type
 
-    @singledispatchmethod
-    def loglik(self, pp: PSMCParams, index: int):
-        log_params = jax.tree.map(jnp.log, pp)
-        return _psmc_ll(log_params, index=index, kern=self)
+    def loglik(self, pp, index):
+        """Differentiable, vmappable log-likelihood of data[index]; also accepts a DemographicModel
+        like the reference's convenience overload (src/phlash/gpu.py:359-367)."""
+        if isinstance(pp, phlash.size_history.DemographicModel):
+            pp = PSMCParams.from_dm(pp)
+        return self._loglik(jax.tree.map(jnp.log, pp), index)
 
-    @loglik.register
-    def _(self, dm: phlash.size_history.DemographicModel, index):
-        return self.loglik(PSMCParams.from_dm(dm), index)
-
-    def __call__(self, pp: PSMCParams, index, grad: bool):
-        """Host callback: NumPy in, NumPy out (src/phlash/gpu.py:386-423)."""
-        from phlash_b200.params import PSMCParams as HostParams
-
-        out = self._impl(HostParams(*(np.asarray(a) for a in pp)), np.asarray(index), grad)
+    def __call__(self, pp, index, grad: bool):
+        """The host callback: NumPy in, NumPy out."""
+        out = self._impl(_HostParams(*(np.asarray(leaf) for leaf in pp)), np.asarray(index), grad)
         if not grad:
             return out
-        ll, dll = out
-        return ll, PSMCParams(*dll)
-
-
-@partial(custom_vjp, nondiff_argnums=(2,))
-def _psmc_ll(log_params: PSMCParams, index, kern) -> float:
-    return _psmc_ll_helper(log_params, index=index, kern=kern, grad=False)
-
-
-def _psmc_ll_fwd(log_params, index, kern):
-    return _psmc_ll_helper(log_params, index=index, kern=kern, grad=True)
-
-
-def _psmc_ll_helper(log_params: PSMCParams, index, kern, grad):
-    params = jax.tree.map(jnp.exp, log_params)
-    shape = jax.ShapeDtypeStruct(shape=(), dtype=jnp.float64)
-    if grad:
-        shape = (shape, PSMCParams(*[jax.ShapeDtypeStruct(shape=(params.M,), dtype=kern.float_type) for _ in params]))
-    return jax.pure_callback(kern, shape, pp=params, index=index, grad=grad, vectorized=True)
-
-
-def _psmc_ll_bwd(kern, df, g):
-    return jax.tree.map(lambda a: g * a, df), None
-
-
-_psmc_ll.defvjp(_psmc_ll_fwd, _psmc_ll_bwd)
+        value, dlog = out
+        return value, PSMCParams(*dlog)
