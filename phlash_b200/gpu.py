@@ -309,30 +309,31 @@ class _PSMCKernelBase:
 
 
 def _normalise_call(pp: PSMCParams, index, M: int):
-    """Bring (pp, index) to pa [B, S, 7, M], inds [S] the way the reference does
-    (gpu.py:186-213) and remember which axes were added."""
-    pa = np.stack([np.asarray(a) for a in pp], -2)
+    """Bring (pp, index) to a parameter block [B, S, 7, M] and indices [S].
+
+    Accepted ranks, as in the reference (gpu.py:186-213): leaves [M] with a scalar index; leaves [M],
+    [S, M] or [B, S, M] with an index vector [S] ([M] is broadcast over the S chunks).  Returns the
+    block, the index vector and which of the two leading axes were added (so that the caller can
+    strip them from the results, gpu.py:319-325)."""
+    block = np.stack([np.asarray(leaf) for leaf in pp], axis=-2)
+    assert block.shape[-2:] == (7, M), f"expected parameter leaves ending in M={M}"
     index = np.asarray(index)
     assert index.ndim in (0, 1)
-    inds = np.atleast_1d(index)
-    added_S = False
+    inds = index.reshape(-1)
+    n_chunks = inds.shape[0]
+    lead = block.ndim - 2  # number of batch axes the caller supplied
+    assert lead in (0, 1, 2)
     if index.ndim == 0:
-        added_S = True
-        assert pa.shape == (7, M)
-        pa = pa[None]
-    S = inds.shape[0]
-    added_B = False
-    if pa.ndim == 2:
-        assert pa.shape == (7, M)
-        pa = np.repeat(pa[None, None], S, axis=1)
-        added_B = True
-    if pa.ndim == 3:
-        assert pa.shape == (S, 7, M)
-        pa = pa[None]
-        added_B = True
-    assert pa.ndim == 4
-    assert pa.shape[1:] == (S, 7, M)
-    return pa, inds, added_B, added_S
+        assert lead == 0, "a scalar index takes unbatched parameters"
+        return block[None, None], inds, True, True
+    if lead == 0:
+        block = np.broadcast_to(block, (1, n_chunks, 7, M))
+    elif lead == 1:
+        assert block.shape[0] == n_chunks
+        block = block[None]
+    else:
+        assert block.shape[1] == n_chunks
+    return block, inds, lead < 2, False
 
 
 class PSMCKernel:
@@ -396,12 +397,9 @@ class PSMCKernel:
             ret = res
 
         def strip(a):
-            if added_B and added_S:
-                return a[0, 0, ...]
             if added_B:
-                return a[0, ...]
-            if added_S:
-                return a[:, 0, ...]
+                a = a[0]
+                return a[0] if added_S else a
             return a
 
         if grad:
