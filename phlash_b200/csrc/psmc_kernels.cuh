@@ -153,6 +153,42 @@ template <typename F, int MT> struct Params {
     }
 };
 
+// All dynamic shared memory of the kernel.  It is addressed with INTEGER offsets (in 128-bit words)
+// rather than through pointers: a pointer into shared memory stored in a struct is a generic
+// 64-bit address, and the compiler then re-derives the shared-window offset (S2R SR_CgaCtaId, LEA,
+// 64-bit IADD3) inside the hot loops - about 8 % of the stall samples in the profile of the first
+// thread-per-pair kernel.
+extern __shared__ __align__(16) unsigned char phb_smem[];
+
+// Explicit shared-state-space accesses with 32-bit addresses (word index * 16 bytes from the start
+// of the dynamic shared memory).  volatile + "memory": a ring slot is written by the recompute pass
+// and read back by the adjoint pass, so these must not be reordered or merged by the compiler.
+__device__ __forceinline__ uint32_t smem_base_addr() { return static_cast<uint32_t>(__cvta_generic_to_shared(phb_smem)); }
+__device__ __forceinline__ void lds_word(uint32_t addr, float *o) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void lds_word(uint32_t addr, double *o) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void sts_word(uint32_t addr, const float *v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+__device__ __forceinline__ void sts_word(uint32_t addr, const double *v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v[0]), "d"(v[1]) : "memory");
+}
+__device__ __forceinline__ float lds_scalar_f(uint32_t addr, float) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ double lds_scalar_f(uint32_t addr, double) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_scalar(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_scalar(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+
 // Per-lane emission table in shared memory: rows emis0, emis1 of this lane's MT states, laid out
 // [row][MT / W][NT] in 128-bit words so that a warp's access is conflict free.  `base` already
 // points at this thread's column.
@@ -160,8 +196,8 @@ template <typename F, int MT, int NT> struct EmisTable {
     using V = typename Vec<F>::type;
     static constexpr int W = Vec<F>::W;
     static constexpr int QN = MT / W;
-    V *base;
-    const V *ones;  // one 128-bit word of 1.0 shared by the CTA
+    uint32_t base;  // shared address of this thread's column
+    uint32_t ones;  // shared address of the one 128-bit word of 1.0 shared by the CTA
     __device__ __forceinline__ void fill(const F *__restrict__ src, int M) {
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
@@ -170,20 +206,17 @@ template <typename F, int MT, int NT> struct EmisTable {
                 F tmp[W];
 #pragma unroll
                 for (int i = 0; i < W; ++i) tmp[i] = src[(4 + r) * M + q * W + i];
-                base[(r * QN + q) * NT] = pack(tmp);
+                sts_word(base + (r * QN + q) * NT * 16, tmp);
             }
         }
     }
     // emission probabilities of observation `ob` for this lane's states.  A missing observation
     // emits 1 in every state: one word of ones shared by the whole CTA sits behind the table, and
     // the choice is made on the ADDRESS (one select per 128-bit load, not one per state).
-    __device__ __forceinline__ void get(int ob, const V *ones, F (&e)[MT]) const {
-        const int row = ob == 1 ? 1 : 0;
+    __device__ __forceinline__ void get(int ob, F (&e)[MT]) const {
+        const uint32_t row_base = base + (ob == 1 ? QN * NT * 16 : 0);
 #pragma unroll
-        for (int q = 0; q < QN; ++q) {
-            const V *src = ob < 0 ? ones : base + (row * QN + q) * NT;
-            unpack<F>(*src, &e[q * W]);
-        }
+        for (int q = 0; q < QN; ++q) lds_word(ob < 0 ? ones : row_base + q * NT * 16, &e[q * W]);
     }
 };
 
@@ -220,7 +253,7 @@ template <typename F, int MT, int T, bool GRAD, int NT>
 __device__ __forceinline__ void forward_site(F (&x)[MT], const Params<F, MT> &p, const PartnerCoef<F, MT, T, GRAD> &pc,
                                              const EmisTable<F, MT, NT> &et, int ob, int sub) {
     F e[MT];
-    et.get(ob, et.ones, e);
+    et.get(ob, e);
     F pre_run = F(0), suf_run = F(0);
     if constexpr (T == 2) {
         F t[2] = {F(0), F(0)};
@@ -306,13 +339,13 @@ template <typename F, int MT, int NT> struct EmisAcc {
     using V = typename Vec<F>::type;
     static constexpr int W = Vec<F>::W;
     static constexpr int QN = MT / W;
-    V *base;  // this thread's column
+    uint32_t base;  // shared address of this thread's column
     __device__ __forceinline__ void clear() {
         F z[W];
 #pragma unroll
         for (int i = 0; i < W; ++i) z[i] = F(0);
 #pragma unroll
-        for (int i = 0; i < 3 * QN; ++i) base[i * NT] = pack(z);
+        for (int i = 0; i < 3 * QN; ++i) sts_word(base + i * NT * 16, z);
     }
     // row(ob) += x .* beta
     __device__ __forceinline__ void add(int ob, const F (&beta)[MT], const F (&x)[MT]) {
@@ -320,10 +353,10 @@ template <typename F, int MT, int NT> struct EmisAcc {
 #pragma unroll
         for (int q = 0; q < QN; ++q) {
             F a[W];
-            unpack<F>(base[(row * QN + q) * NT], a);
+            lds_word(base + (row * QN + q) * NT * 16, a);
 #pragma unroll
             for (int i = 0; i < W; ++i) a[i] = fma(x[q * W + i], beta[q * W + i], a[i]);
-            base[(row * QN + q) * NT] = pack(a);
+            sts_word(base + (row * QN + q) * NT * 16, a);
         }
     }
     __device__ __forceinline__ void flush(double *acc, int64_t stride) {
@@ -332,13 +365,13 @@ template <typename F, int MT, int NT> struct EmisAcc {
 #pragma unroll
             for (int q = 0; q < QN; ++q) {
                 F a[W], z[W];
-                unpack<F>(base[(r * QN + q) * NT], a);
+                lds_word(base + (r * QN + q) * NT * 16, a);
 #pragma unroll
                 for (int i = 0; i < W; ++i) {
                     atomicAdd(acc + int64_t((4 + r) * MT + q * W + i) * stride, double(a[i]));
                     z[i] = F(0);
                 }
-                base[(r * QN + q) * NT] = pack(z);
+                sts_word(base + (r * QN + q) * NT * 16, z);
             }
         }
     }
@@ -378,7 +411,7 @@ __device__ __forceinline__ void backward_site(F (&beta)[MT], const F (&x)[MT], i
                                               const EmisTable<F, MT, NT> &et, int sub, Grad<F, MT, ESM> &g,
                                               EmisAcc<F, MT, NT> &ea) {
     F w[MT];
-    et.get(ob, et.ones, w);
+    et.get(ob, w);
 #pragma unroll
     for (int k = 0; k < MT; ++k) w[k] *= beta[k];
     F q_run = F(0), s_run = F(0), b_run = F(0), x_run = F(0);
@@ -492,24 +525,31 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
     constexpr int QN = MT / W;
     static_assert(MT % 4 == 0 && K % 8 == 0 && K % kNorm == 0 && T <= 32, "layout assumptions");
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    // emission table [2][QN][NT]; then (gradient kernel) the per-warp ring of forward vectors
-    // [K][QN][32] and block scale factors [K / kNorm][32]
-    EmisTable<F, MT, NT> et;
-    et.ones = reinterpret_cast<const V *>(smem_raw);
-    et.base = reinterpret_cast<V *>(smem_raw) + 1 + threadIdx.x;
-    V *seg_s = reinterpret_cast<V *>(smem_raw) + 1 + 2 * QN * NT + warp * (K * QN * 32) + lane;
-    F *scale_s = reinterpret_cast<F *>(reinterpret_cast<V *>(smem_raw) + 1 + 2 * QN * NT + kWarps * (K * QN * 32)) + warp * (K / kNorm * 32) + lane;
+    // Shared-memory map, in 128-bit words (all indices are ints, see phb_smem):
+    //   [0]                         one word of ones (emission of a missing observation)
+    //   emission table              [2][QN][NT]
+    //   ring of forward vectors     per warp [K][QN][32]                       (gradient kernel)
+    //   block scale factors         per warp [K / kNorm][32] scalars           (gradient kernel)
+    //   emission-row accumulators   [3][QN][NT]                                 (MT >= 16 gradient kernel)
     constexpr bool ESM = GRAD && emis_acc_in_smem<MT>();
+    constexpr int kTabWords = 1 + 2 * QN * NT;
+    constexpr int kRingWords = K * QN * NT;
+    constexpr int kScaleWords = (K / kNorm) * NT / W;  // scalars packed W per word
+    const uint32_t smem0 = smem_base_addr();
+    EmisTable<F, MT, NT> et;
+    et.ones = smem0;
+    et.base = smem0 + (1 + threadIdx.x) * 16;
+    const uint32_t seg_a = smem0 + (kTabWords + warp * (K * QN * 32) + lane) * 16;  // + (k * QN + q) * 32 * 16
+    const uint32_t scale_a = smem0 + (kTabWords + kRingWords) * 16 + (warp * (K / kNorm * 32) + lane) * uint32_t(sizeof(F));
     EmisAcc<F, MT, NT> ea;
-    ea.base = reinterpret_cast<V *>(scale_s - lane - warp * (K / kNorm * 32) + (K / kNorm) * NT) + threadIdx.x;
+    ea.base = smem0 + (kTabWords + kRingWords + kScaleWords + threadIdx.x) * 16;
     if (threadIdx.x == 0) {
         F one[W];
 #pragma unroll
         for (int i = 0; i < W; ++i) one[i] = F(1);
-        *reinterpret_cast<V *>(smem_raw) = pack(one);
+        sts_word(smem0, one);
     }
     __syncthreads();  // the only block-level barrier: publishes the word of ones
 
@@ -605,16 +645,14 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
             }
 #pragma unroll 1
             for (int i = 0; i < 6 * MT; ++i) PHB_GACC_BASE[int64_t(i) * PHB_GACC_STRIDE] = 0.0;
+            ObsWords<K> ow_ahead;  // observations of the next segment to process, one segment ahead
+            ow_ahead.load(obs, (n_seg - 1) * K);
             for (int64_t seg = n_seg - 1; seg >= 0; --seg) {
-                ObsWords<K> ow;
-                ow.load(obs, seg * K);
+                const ObsWords<K> ow = ow_ahead;
                 if (seg > 0) {
-                    prefetch_l2(obs + (seg - 1) * K);
+                    ow_ahead.load(obs, (seg - 1) * K);
                     if (seg > 1) prefetch_l2(&ck[(seg - 1) * QN * 32]);
                 }
-                // observation just before this segment (its posterior is accumulated by the
-                // adjoint step of the segment's first site)
-                const int ob_before_seg = seg > 0 ? int(obs[seg * K - 1]) : -1;
                 const int len = int(min(int64_t(K), a.L - seg * K));
                 // re-run the forward steps of this segment, keeping every input vector
                 F xs[MT];
@@ -631,12 +669,12 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                     for (int j = 0; j < kNorm; ++j) {
                         if (kb + j < len) {
 #pragma unroll
-                            for (int q = 0; q < QN; ++q) seg_s[((kb + j) * QN + q) * 32] = pack(&xs[q * W]);
+                            for (int q = 0; q < QN; ++q) sts_word(seg_a + ((kb + j) * QN + q) * 32 * 16, &xs[q * W]);
                             forward_site<F, MT, T, GRAD, NT>(xs, p, pc, et, ObsWords<K>::byte_of(blk, j), sub);
                         }
                     }
                     const F inv = fast_rcp<F>(pair_sum<F, MT, T>(xs));
-                    scale_s[(kb / kNorm) * 32] = inv;
+                    sts_scalar(scale_a + (kb / kNorm) * 32 * uint32_t(sizeof(F)), inv);
 #pragma unroll
                     for (int j = 0; j < MT; ++j) xs[j] *= inv;
                 }
@@ -652,10 +690,12 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                 }
                 for (int kb = ((len - 1) / kNorm) * kNorm; kb >= 0; kb -= kNorm) {
                     const uint32_t blk = ow.block4(kb);
-                    const int ob_before = kb > 0 ? ow.at(kb - 1) : ob_before_seg;
+                    // the observation just before this block; for the first block of the segment it is
+                    // the last one of the previous segment, whose words are already on their way
+                    const int ob_before = kb > 0 ? ow.at(kb - 1) : (seg > 0 ? ow_ahead.at(K - 1) : -1);
                     // the forward pass multiplied its vector by `scale` after the last site of this
                     // block; carrying the same factor on beta keeps beta . alpha == 1
-                    const F scale = scale_s[(kb / kNorm) * 32];
+                    const F scale = lds_scalar_f(scale_a + (kb / kNorm) * 32 * uint32_t(sizeof(F)), F(0));
 #pragma unroll
                     for (int k = 0; k < MT; ++k) beta[k] *= scale;
 #pragma unroll
@@ -663,7 +703,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                         if (kb + j < len) {
                             F xin[MT];
 #pragma unroll
-                            for (int q = 0; q < QN; ++q) unpack<F>(seg_s[((kb + j) * QN + q) * 32], &xin[q * W]);
+                            for (int q = 0; q < QN; ++q) lds_word(seg_a + ((kb + j) * QN + q) * 32 * 16, &xin[q * W]);
                             const int ob_prev = j > 0 ? ObsWords<K>::byte_of(blk, j - 1) : ob_before;
                             backward_site<F, MT, T, NT, ESM>(beta, xin, ObsWords<K>::byte_of(blk, j), ob_prev, p, pc, et, sub, g, ea);
                         }
