@@ -169,7 +169,11 @@ const std::vector<Variant> &variants() {
 
 const Variant *pick_variant(const phb_kernel *k, bool grad, int64_t n_pairs) {
     const Variant *last = nullptr, *forced = nullptr, *first_fill = nullptr;
-    const int64_t fill = int64_t(k->num_sms) * 256;
+    // Lane layouts are ordered by increasing T (fewer lanes per pair = fewer instructions per pair).
+    // Measured on B200 (profiles/r01_probe_small_minibatch.log): below ~64 threads per SM the run is
+    // bound by the per-site dependency latency (~20 ms per 50 000-bin chunk) and more lanes per pair
+    // help a little; above it the thread-per-pair layout is already the fastest.
+    const int64_t fill = int64_t(k->num_sms) * 64;
     // tuning knob: PHB_NT=<threads per CTA> picks among variants that differ only in CTA size
     const char *nt_env = getenv("PHB_NT");
     const int want_nt = nt_env ? atoi(nt_env) : 0;
