@@ -102,17 +102,20 @@ def cpu_baseline(data, pps, steps=1, warmup=0):
     from oracle import c_oracle
 
     b, s = CPU_SAMPLE
+    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would
+    # otherwise silently make this a single-thread run)
+    n_threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     rows = np.tile(np.arange(s) * (data.shape[0] // s), b)
     params = np.repeat(pps[:b], s, axis=0)
     n_st = b * s * data.shape[1]
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        c_oracle.loglik_batch(data, rows, params, grad=True)
+        c_oracle.loglik_batch(data, rows, params, grad=True, n_threads=n_threads)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     dt = float(np.mean(times))
-    return {"value": n_st / dt, "unit": "site-transitions/s", "cores": c_oracle.max_threads(), "kind": "port",
+    return {"value": n_st / dt, "unit": "site-transitions/s", "cores": n_threads, "kind": "port",
             "sample": f"{b} particles x {s} chunks x {data.shape[1]} bins, loglik+grad, fp64 C/OpenMP restatement "
                       f"of hmm.py:52-82 (the reference's JAX CPU path needs jax, absent here)",
             "seconds_per_step": dt}
