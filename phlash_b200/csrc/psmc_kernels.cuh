@@ -466,7 +466,7 @@ __device__ __forceinline__ void backward_site(F (&beta)[MT], const F (&x)[MT], i
     posterior_to_emission<F, MT, NT, ESM>(beta, x, ob_prev, g, ea);
 }
 
-constexpr int kNorm = 4;  // the forward vector is rescaled after every kNorm-th site of a segment
+constexpr int kNorm = 4;  // the forward vector is rescaled after every kNorm-th site of a segment (8 measured slower: the unrolled blocks outgrow the instruction cache)
 
 // With ~227 KB of shared memory per SM in use there is practically no L1, so every segment's
 // observation / checkpoint load would see L2 or DRAM latency; a hint one segment ahead costs no
@@ -480,14 +480,15 @@ template <int K> struct ObsWords {
 #pragma unroll
         for (int i = 0; i < K / 8; ++i) w[i] = __ldg(reinterpret_cast<const unsigned long long *>(row + site0) + i);
     }
-    // the 4 observations of sites [k0, k0 + 4), k0 a multiple of 4
-    __device__ __forceinline__ uint32_t block4(int k0) const {
+    // the kNorm (4 or 8) observations of sites [k0, k0 + kNorm), k0 a multiple of kNorm, in the low bytes
+    __device__ __forceinline__ uint64_t block(int k0) const {
         uint64_t word = w[0];
         if constexpr (K == 16) word = (k0 & 8) ? w[1] : w[0];
-        return static_cast<uint32_t>(word >> ((k0 & 4) * 8));
+        if constexpr (kNorm == 4) word >>= (k0 & 4) * 8;
+        return word;
     }
-    __device__ __forceinline__ int at(int k) const { return byte_of(block4(k & ~3), k & 3); }
-    static __device__ __forceinline__ int byte_of(uint32_t blk, int j) {
+    __device__ __forceinline__ int at(int k) const { return byte_of(block(k & ~(kNorm - 1)), k & (kNorm - 1)); }
+    static __device__ __forceinline__ int byte_of(uint64_t blk, int j) {
         return static_cast<int>(static_cast<int8_t>((blk >> (8 * j)) & 0xffu));
     }
 };
@@ -523,7 +524,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
     using V = typename Vec<F>::type;
     constexpr int W = Vec<F>::W;
     constexpr int QN = MT / W;
-    static_assert(MT % 4 == 0 && K % 8 == 0 && K % kNorm == 0 && T <= 32, "layout assumptions");
+    static_assert(MT % 4 == 0 && K % 8 == 0 && K % kNorm == 0 && (kNorm == 4 || kNorm == 8) && T <= 32, "layout assumptions");
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -606,7 +607,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
             const int len = int(min(int64_t(K), a.L - seg * K));
             F acc = F(0);
             for (int kb = 0; kb < len; kb += kNorm) {
-                const uint32_t blk = ow.block4(kb);
+                const uint64_t blk = ow.block(kb);
 #pragma unroll
                 for (int j = 0; j < kNorm; ++j)
                     if (kb + j < len) forward_site<F, MT, T, GRAD, NT>(x, p, pc, et, ObsWords<K>::byte_of(blk, j), sub);
@@ -664,7 +665,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                     for (int q = 0; q < QN; ++q) unpack<F>(ck[(seg * QN + q) * 32], &xs[q * W]);
                 }
                 for (int kb = 0; kb < len; kb += kNorm) {
-                    const uint32_t blk = ow.block4(kb);
+                    const uint64_t blk = ow.block(kb);
 #pragma unroll
                     for (int j = 0; j < kNorm; ++j) {
                         if (kb + j < len) {
@@ -689,7 +690,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                     for (int k = 0; k < MT; ++k) beta[k] *= dot;
                 }
                 for (int kb = ((len - 1) / kNorm) * kNorm; kb >= 0; kb -= kNorm) {
-                    const uint32_t blk = ow.block4(kb);
+                    const uint64_t blk = ow.block(kb);
                     // the observation just before this block; for the first block of the segment it is
                     // the last one of the previous segment, whose words are already on their way
                     const int ob_before = kb > 0 ? ow.at(kb - 1) : (seg > 0 ? ow_ahead.at(K - 1) : -1);
