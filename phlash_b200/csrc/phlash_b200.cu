@@ -318,17 +318,26 @@ int phb_create(int M, const int8_t *data, int64_t N, int64_t L, int double_preci
     }
     phb_kernel *k = nullptr;
     if (int rc = new_kernel(M, N, L, double_precision, device, &k)) return rc;
-    // clip to [-1, 1] on the way in (gpu.py:108-110); padding columns are never read as sites
-    std::vector<int8_t> staged(size_t(N) * size_t(k->pitch), int8_t(-1));
-    for (int64_t i = 0; i < N; ++i) {
-        const int8_t *src = data + i * L;
-        int8_t *dst = staged.data() + i * k->pitch;
-        for (int64_t j = 0; j < L; ++j) dst[j] = src[j] > 1 ? int8_t(1) : src[j];
-    }
-    cudaError_t e = cudaMemcpy(k->d_data, staged.data(), staged.size(), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
-        phb_destroy(k);
-        return fail(PHB_E_CUDA, "cudaMemcpy(data): %s", cudaGetErrorString(e));
+    // clip to [-1, 1] on the way in (gpu.py:108-110); padding columns are never read as sites.
+    // Staged in slabs of rows so that a 50 GB matrix (BASELINE config 5) does not need a second
+    // 50 GB host copy.
+    {
+        const int64_t slab_rows = std::max<int64_t>(1, (int64_t(64) << 20) / k->pitch);
+        std::vector<int8_t> staged(size_t(std::min(slab_rows, N)) * size_t(k->pitch));
+        for (int64_t r0 = 0; r0 < N; r0 += slab_rows) {
+            const int64_t nr = std::min(slab_rows, N - r0);
+            std::fill(staged.begin(), staged.begin() + size_t(nr) * size_t(k->pitch), int8_t(-1));
+            for (int64_t i = 0; i < nr; ++i) {
+                const int8_t *src = data + (r0 + i) * L;
+                int8_t *dst = staged.data() + i * k->pitch;
+                for (int64_t j = 0; j < L; ++j) dst[j] = src[j] > 1 ? int8_t(1) : src[j];
+            }
+            cudaError_t e = cudaMemcpy(k->d_data + r0 * k->pitch, staged.data(), size_t(nr) * size_t(k->pitch), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) {
+                phb_destroy(k);
+                return fail(PHB_E_CUDA, "cudaMemcpy(data): %s", cudaGetErrorString(e));
+            }
+        }
     }
     *out = k;
     return PHB_OK;

@@ -51,7 +51,9 @@ class _PSMCKernelBase:
         assert data.ndim == 2
         assert data.dtype == np.int8
         assert data.min() >= -1
-        data = np.ascontiguousarray(data.clip(-1, 1))
+        # values > 1 are clipped to 1 by phb_create while it stages the upload (gpu.py:108-110);
+        # no clipped host copy is made here (the matrix can be tens of GB)
+        data = np.ascontiguousarray(data)
         assert np.all(data.max(axis=1) > -1), "data contains observations with all missing values"
         self.double_precision = bool(double_precision)
         self._N, self._L = data.shape
