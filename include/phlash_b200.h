@@ -20,6 +20,10 @@
  *           already applied here.
  *   ll      always double (reference: gpu.py:216, 535, 583).
  *
+ * Threading: a kernel object is NOT thread-safe (it owns one stream and one set of scratch buffers);
+ * use it from one thread at a time (the reference is driven from XLA's single host-callback
+ * thread) or create one object per thread / per device.  Different objects are independent.
+ *
  * Error handling: every function returns PHB_OK (0) or a negative PHB_E_* code and never
  * throws; phb_last_error() returns a thread-local message for the last failure
  * (reference: CudaError / AssertionError / MemoryError raised from gpu.py:23-46, 106-124, 197-214).

@@ -583,8 +583,9 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
         PartnerCoef<F, MT, T, GRAD> pc;
         pc.init(p, sub);
         int64_t row = a.inds[ps];
-        if (row < 0 || row >= a.n_rows) {
-            if (sub == 0) atomicOr(a.err_flag, 1);
+        const bool bad_row = row < 0 || row >= a.n_rows;
+        if (bad_row) {
+            if (sub == 0) atomicOr(a.err_flag, 1);  // reported by phb_sync(); this pair's ll becomes NaN
             row = 0;
         }
         const int8_t *obs = a.data + row * a.pitch;
@@ -623,6 +624,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
         if (!(ll == ll) || ll > 1e300 || ll < -1e300) {
             if (sub == 0) atomicOr(a.err_flag, 2);
         }
+        if (bad_row) ll = __longlong_as_double(0x7ff8000000000000LL);
         if (writer && sub == 0) a.ll[pair] = a.out_mode ? a.ll[pair] - ll : ll;
         if (writer && a.alpha_out != nullptr) {
             F *ao = static_cast<F *>(a.alpha_out) + pair * M + sub * MT;

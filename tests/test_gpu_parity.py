@@ -314,3 +314,35 @@ def test_full_length_invariants(long_case):
     # forward-only path gives the same likelihood
     ll2 = kern.gpu_kernels[0].evaluate(pa, inds, False)
     np.testing.assert_allclose(ll2, ll, rtol=1e-6)
+
+
+def test_empty_batches(golden):
+    """B = 0 or S = 0: nothing to do, correctly shaped empty results (no launch)."""
+    data, _ = fixture_data(0)
+    kern = make_kernel(16, data).gpu_kernels[0]
+    n0 = kern.launch_count
+    ll, dlog = kern.evaluate(np.zeros((3, 0, 7, 16)), np.zeros(0, dtype=np.int64), True)
+    assert ll.shape == (3, 0) and dlog.shape == (3, 0, 7, 16)
+    ll = kern.evaluate(np.zeros((0, 2, 7, 16)), np.array([1, 2]), False)
+    assert ll.shape == (0, 2)
+    assert kern.launch_count == n0
+
+
+def test_device_entry_reports_bad_index_at_sync(golden):
+    """The device-buffer entry cannot check indices on the host: the kernel flags them, the
+    affected pairs get NaN and phb_sync() raises (include/phlash_b200.h)."""
+    import torch
+
+    data, _ = fixture_data(0)
+    pps = golden["part_pp"][:2]
+    kern = make_kernel(16, data).gpu_kernels[0]
+    dev = torch.device("cuda:0")
+    p6 = torch.tensor(pps[:, :6], dtype=torch.float32, device=dev).contiguous()
+    pi = torch.tensor(pps[:, 6], dtype=torch.float32, device=dev).contiguous()
+    inds = torch.tensor([1, 10, 3], device=dev)  # 10 == N is out of range
+    ll, _ = kern.evaluate_device(p6, pi, inds, True)
+    with pytest.raises(AssertionError):
+        kern.sync()
+    ll = ll.cpu().numpy()
+    assert np.isnan(ll[:, 1]).all() and np.isfinite(ll[:, [0, 2]]).all()
+    kern.sync()  # the flag is cleared once reported
