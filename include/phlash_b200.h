@@ -90,6 +90,13 @@ int phb_device(const phb_kernel *k);
  * (chunk, particle) pair (0 = choose automatically from the number of pairs). */
 int phb_set_threads_per_pair(phb_kernel *k, int threads_per_pair);
 
+/* Small minibatches (the reference default is S <= 5 chunks) are bound by the serial depth of the
+ * recursion; for them a "store-all" gradient kernel keeps every forward vector in HBM instead of
+ * recomputing it (two dependent passes over the chunk instead of three).  mode: -1 = automatic
+ * (few pairs and the scratch fits), 0 = never, 1 = whenever available (float kernels; ignored while
+ * threads_per_pair is forced). */
+int phb_set_store_all(phb_kernel *k, int mode);
+
 /* HOST-buffer evaluation; blocking.  Replaces _PSMCKernelBase.__call__ (gpu.py:182-325) for
  * pa of shape [B, S, 7, M]: pair (b, s) scores data row inds[s] with parameter block
  * params[b, s].  ll is [B, S]; dlog is [B, S, 7, M] and may be NULL together with

@@ -89,7 +89,8 @@ struct phb_kernel {
     int num_sms = 0;
     int64_t launches = 0;
     char last_name[96] = "";
-    DeviceBuffer params, inds, ll, dlog, ckpt, gacc;
+    DeviceBuffer params, inds, ll, dlog, ckpt, gacc, xall, sall;
+    int store_all_mode = -1;  // -1 auto, 0 never, 1 whenever a store-all variant exists
     size_t elem() const { return dbl ? sizeof(double) : sizeof(float); }
 };
 
@@ -167,6 +168,34 @@ const std::vector<Variant> &variants() {
     return table;
 }
 
+// Store-all gradient kernels (small minibatches, see psmc_kernels.cuh): float only.
+struct StoreAllVariant {
+    int M, T, MT, NT;
+    const void *func;
+    size_t smem;
+};
+template <int MT, int T, int NT, int MINB> StoreAllVariant make_storeall() {
+    StoreAllVariant v;
+    v.M = MT * T;
+    v.T = T;
+    v.MT = MT;
+    v.NT = NT;
+    v.func = reinterpret_cast<const void *>(&phb::psmc_loglik_storeall_kernel<float, MT, T, NT, MINB>);
+    v.smem = phb::smem_bytes<float, MT, 8, NT, false>();
+    return v;
+}
+const std::vector<StoreAllVariant> &storeall_variants() {
+    static const std::vector<StoreAllVariant> table = {
+        // (MT = 8 layouts were measured too: same latency at 255 registers, slower at 168)
+        make_storeall<4, 1, 128, 4>(),   // M = 4
+        make_storeall<4, 2, 128, 4>(),   // M = 8
+        make_storeall<4, 4, 128, 4>(),   // M = 16
+        make_storeall<4, 8, 128, 4>(),   // M = 32
+        make_storeall<4, 16, 128, 4>(),  // M = 64
+    };
+    return table;
+}
+
 const Variant *pick_variant(const phb_kernel *k, bool grad, int64_t n_pairs) {
     const Variant *last = nullptr, *forced = nullptr, *first_fill = nullptr;
     // Lane layouts are ordered by increasing T (fewer lanes per pair = fewer instructions per pair).
@@ -203,6 +232,43 @@ int check_handle(const phb_kernel *k) {
 int launch(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream) {
     const int64_t n_pairs = a.B * a.S;
     if (n_pairs == 0) return PHB_OK;
+    if (grad && !k->dbl && k->store_all_mode != 0 && k->force_T == 0) {
+        for (const StoreAllVariant &sv : storeall_variants()) {
+            if (sv.M != k->M) continue;
+            const int pairs_per_cta = sv.NT / sv.T;
+            const int64_t grid = (n_pairs + pairs_per_cta - 1) / pairs_per_cta;
+            const int64_t warps = grid * (sv.NT / 32);
+            const size_t x_bytes = size_t(warps) * size_t(a.L) * sv.MT * 32 * sizeof(float);
+            const size_t s_bytes = size_t(warps) * size_t((a.L + phb::kNorm - 1) / phb::kNorm) * 32 * sizeof(float);
+            bool use = k->store_all_mode == 1;
+            if (k->store_all_mode < 0) {
+                // latency-bound regime (fewer than ~128 threads per SM) and the scratch fits comfortably
+                size_t free_b = 0, total_b = 0;
+                cudaMemGetInfo(&free_b, &total_b);
+                const size_t have = free_b + k->xall.cap + k->sall.cap;
+                use = n_pairs * sv.T <= int64_t(k->num_sms) * 128 && x_bytes + s_bytes <= have / 2;
+            }
+            if (!use) break;
+            int rc;
+            if ((rc = k->xall.reserve(x_bytes)) != PHB_OK) return rc;
+            if ((rc = k->sall.reserve(s_bytes)) != PHB_OK) return rc;
+            if ((rc = k->gacc.reserve(size_t(grid) * sv.NT * 6 * sv.MT * sizeof(double))) != PHB_OK) return rc;
+            a.xall = k->xall.ptr;
+            a.sall = k->sall.ptr;
+            a.gacc = static_cast<double *>(k->gacc.ptr);
+            a.n_groups = grid;
+            a.err_flag = k->d_err;
+            PHB_CUDA(cudaFuncSetAttribute(sv.func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sv.smem)));
+            void *kargs[] = {&a};
+            PHB_CUDA(cudaEventRecord(k->ev0, stream));
+            PHB_CUDA(cudaLaunchKernel(sv.func, dim3(unsigned(grid)), dim3(sv.NT), kargs, sv.smem, stream));
+            PHB_CUDA(cudaEventRecord(k->ev1, stream));
+            k->timed = true;
+            k->launches += 1;
+            snprintf(k->last_name, sizeof k->last_name, "psmc_loglik_storeall_kernel<float,MT=%d,T=%d,NT=%d>", sv.MT, sv.T, sv.NT);
+            return PHB_OK;
+        }
+    }
     const Variant *v = pick_variant(k, grad, n_pairs);
     if (!v) return fail(PHB_E_INVALID, "no kernel variant for M=%d, threads_per_pair=%d", k->M, k->force_T);
     const int pairs_per_cta = v->NT / v->T;
@@ -405,6 +471,8 @@ void phb_destroy(phb_kernel *k) {
     k->dlog.release();
     k->ckpt.release();
     k->gacc.release();
+    k->xall.release();
+    k->sall.release();
     if (k->d_data) cudaFree(k->d_data);
     if (k->d_err) cudaFree(k->d_err);
     if (k->d_flags) cudaFree(k->d_flags);
@@ -426,6 +494,13 @@ const int8_t *phb_device_data(const phb_kernel *k, int64_t *pitch) {
     if (!k) return nullptr;
     if (pitch) *pitch = k->pitch;
     return k->d_data;
+}
+
+int phb_set_store_all(phb_kernel *k, int mode) {
+    if (int rc = check_handle(k)) return rc;
+    if (mode < -1 || mode > 1) return fail(PHB_E_INVALID, "store-all mode must be -1 (auto), 0 (off) or 1 (on)");
+    k->store_all_mode = mode;
+    return PHB_OK;
 }
 
 int phb_set_threads_per_pair(phb_kernel *k, int threads_per_pair) {

@@ -51,6 +51,8 @@ struct KernelArgs {
     void *alpha_out;     // [B, S, M] filtered distribution after the last site, or nullptr
     void *ckpt;          // checkpoint scratch, see ckpt_bytes_per_warp()
     double *gacc;        // fp64 gradient accumulators: [6 * MT][gridDim.x * NT]
+    void *xall;          // store-all kernel: every forward input vector, [warp slot][site][MT / W][32] words
+    void *sall;          // store-all kernel: block scale factors, [warp slot][ceil(L / kNorm)][32]
     int64_t n_groups;    // ceil(B*S / pairs-per-CTA)
     int *err_flag;       // bit 0: index out of range, bit 1: non-finite result
     int out_mode;        // 0: ll / dlog are written;  1: the results are SUBTRACTED from what is there
@@ -77,41 +79,30 @@ __device__ __forceinline__ float4 pack(const float *o) { return make_float4(o[0]
 __device__ __forceinline__ double2 pack(const double *o) { return make_double2(o[0], o[1]); }
 
 // ---- sums across the T lanes that share a pair (lane index inside the pair = sub) ----
+// Butterfly: at level l every lane holds the sum of its aligned block of 2^l lanes and fetches the
+// sibling block's sum with one shfl.xor; a sibling with a smaller lane index contributes to the
+// "before" sum, one with a larger index to the "after" sum.  log2(T) dependent shuffles.
 // sum of `mine` over the lanes with a smaller sub
 template <typename F, int T> __device__ __forceinline__ F lanes_before(F mine, int sub) {
-    if constexpr (T == 1) {
-        return F(0);
-    } else if constexpr (T == 2) {
-        const F other = __shfl_xor_sync(0xffffffffu, mine, 1, T);
-        return sub == 0 ? F(0) : other;
-    } else {
-        F incl = mine;
+    F block = mine, out = F(0);
 #pragma unroll
-        for (int o = 1; o < T; o <<= 1) {
-            const F t = __shfl_up_sync(0xffffffffu, incl, o, T);
-            if (sub >= o) incl += t;
-        }
-        const F ex = __shfl_up_sync(0xffffffffu, incl, 1, T);
-        return sub == 0 ? F(0) : ex;
+    for (int o = 1; o < T; o <<= 1) {
+        const F sibling = __shfl_xor_sync(0xffffffffu, block, o, T);
+        if (sub & o) out += sibling;
+        block += sibling;
     }
+    return out;
 }
 // sum of `mine` over the lanes with a larger sub
 template <typename F, int T> __device__ __forceinline__ F lanes_after(F mine, int sub) {
-    if constexpr (T == 1) {
-        return F(0);
-    } else if constexpr (T == 2) {
-        const F other = __shfl_xor_sync(0xffffffffu, mine, 1, T);
-        return sub == 0 ? other : F(0);
-    } else {
-        F incl = mine;
+    F block = mine, out = F(0);
 #pragma unroll
-        for (int o = 1; o < T; o <<= 1) {
-            const F t = __shfl_down_sync(0xffffffffu, incl, o, T);
-            if (sub + o < T) incl += t;
-        }
-        const F ex = __shfl_down_sync(0xffffffffu, incl, 1, T);
-        return sub == T - 1 ? F(0) : ex;
+    for (int o = 1; o < T; o <<= 1) {
+        const F sibling = __shfl_xor_sync(0xffffffffu, block, o, T);
+        if (!(sub & o)) out += sibling;
+        block += sibling;
     }
+    return out;
 }
 template <typename F, int T> __device__ __forceinline__ F lanes_total(F mine) {
 #pragma unroll
@@ -745,6 +736,213 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                     for (int r = 0; r < 7; ++r) out[r * M + k] = a.out_mode ? out[r * M + k] - val[r] : val[r];
                 }
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// "Store-all" variant of the gradient kernel for SMALL minibatches (the reference's default is
+// S <= 5 chunks, mcmc.py:119-121, i.e. a few thousand pairs).  Those runs are bound by the serial
+// depth of the recursion, not by throughput: three passes (forward, recompute, adjoint) of L
+// dependent site steps.  With few pairs every forward input vector fits in HBM
+// (pairs * L * M * 4 B: 8 GB for 2 500 pairs of 50 500 bins), so pass 1 stores them all and the
+// adjoint pass streams them back with the loads of the next block issued one block ahead - two
+// passes instead of three, nothing recomputed.  One CTA handles exactly one group of pairs (the
+// host launches enough CTAs), so the scratch is indexed by the global warp index.
+template <typename F, int MT, int T, int NT, int MINB>
+__global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_storeall_kernel(const KernelArgs a) {
+    constexpr int M = MT * T;
+    constexpr int PW = 32 / T;
+    constexpr int kWarps = NT / 32;
+    using V = typename Vec<F>::type;
+    constexpr int W = Vec<F>::W;
+    constexpr int QN = MT / W;
+    constexpr int K = 8;  // only used to size the observation words
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t smem0 = smem_base_addr();
+    EmisTable<F, MT, NT> et;
+    et.ones = smem0;
+    et.base = smem0 + (1 + threadIdx.x) * 16;
+    EmisAcc<F, MT, NT> ea;  // unused (register accumulators), needed by the shared site functions
+    ea.base = 0;
+    if (threadIdx.x == 0) {
+        F one[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i) one[i] = F(1);
+        sts_word(smem0, one);
+    }
+    __syncthreads();
+
+    const int sub = lane % T;
+    const int lp = lane / T;
+    const int64_t n_pairs = a.B * a.S;
+    const int64_t n_blocks = (a.L + kNorm - 1) / kNorm;
+    const int64_t warp_slot = int64_t(blockIdx.x) * kWarps + warp;
+    const F *params6 = static_cast<const F *>(a.params6);
+    const F *pi_g = static_cast<const F *>(a.pi);
+    V *xall = reinterpret_cast<V *>(a.xall) + warp_slot * a.L * QN * 32 + lane;  // + (t * QN + q) * 32
+    F *sall = static_cast<F *>(a.sall) + warp_slot * n_blocks * 32 + lane;       // + block * 32
+
+    const int64_t pair_raw = (int64_t(blockIdx.x) * kWarps + warp) * PW + lp;
+    const bool writer = pair_raw < n_pairs;
+    const int64_t pair = writer ? pair_raw : n_pairs - 1;
+    const int64_t pb = pair / a.S, ps = pair % a.S;
+    Params<F, MT> p;
+    p.load(params6 + pb * a.pstride_b + ps * a.pstride_s + sub * MT, M);
+    et.fill(params6 + pb * a.pstride_b + ps * a.pstride_s + sub * MT, M);
+    PartnerCoef<F, MT, T, true> pc;
+    pc.init(p, sub);
+    int64_t row = a.inds[ps];
+    const bool bad_row = row < 0 || row >= a.n_rows;
+    if (bad_row) {
+        if (sub == 0) atomicOr(a.err_flag, 1);
+        row = 0;
+    }
+    const int8_t *obs = a.data + row * a.pitch;
+    const F *pi_p = pi_g + pb * a.pistride_b + ps * a.pistride_s + sub * MT;
+
+    // ---------------------------------------------------------------- pass 1: forward, keep everything
+    F x[MT];
+#pragma unroll
+    for (int k = 0; k < MT; ++k) x[k] = pi_p[k];
+    double ll = 0.0;
+    F acc = F(0);
+    // kNorm (= 4) observation bytes per block, requested one block ahead (rows are padded to a
+    // multiple of 16 bytes, so reading the word that straddles the end of the row is safe)
+    uint32_t blk_next = __ldg(reinterpret_cast<const unsigned int *>(obs));
+    for (int64_t blk_i = 0; blk_i < n_blocks; ++blk_i) {
+        const int64_t t0 = blk_i * kNorm;
+        const uint32_t blk = blk_next;
+        if (blk_i + 1 < n_blocks) blk_next = __ldg(reinterpret_cast<const unsigned int *>(obs + t0 + kNorm));
+        const int len = int(min(int64_t(kNorm), a.L - t0));
+#pragma unroll
+        for (int j = 0; j < kNorm; ++j) {
+            if (j < len) {
+#pragma unroll
+                for (int q = 0; q < QN; ++q) xall[((t0 + j) * QN + q) * 32] = pack(&x[q * W]);
+                forward_site<F, MT, T, true, NT>(x, p, pc, et, ObsWords<K>::byte_of(blk, j), sub);
+            }
+        }
+        const F tot = pair_sum<F, MT, T>(x);
+        const F inv = fast_rcp<F>(tot);
+        sall[blk_i * 32] = inv;
+#pragma unroll
+        for (int j = 0; j < MT; ++j) x[j] *= inv;
+        acc += log2_of<F>(tot);
+        if ((blk_i & 3) == 3) {
+            ll += double(acc);
+            acc = F(0);
+        }
+    }
+    ll = (ll + double(acc)) * 0.69314718055994530942;
+    if (!(ll == ll) || ll > 1e300 || ll < -1e300) {
+        if (sub == 0) atomicOr(a.err_flag, 2);
+    }
+    if (bad_row) ll = __longlong_as_double(0x7ff8000000000000LL);
+    if (writer && sub == 0) a.ll[pair] = a.out_mode ? a.ll[pair] - ll : ll;
+
+    // ---------------------------------------------------------------- pass 2: adjoint, streaming the vectors back
+    Grad<F, MT, false> g;
+    g.clear();
+    F beta[MT];
+    {
+        const F tot = fast_rcp<F>(pair_sum<F, MT, T>(x));
+#pragma unroll
+        for (int k = 0; k < MT; ++k) beta[k] = tot;
+        posterior_to_emission<F, MT, NT, false>(beta, x, int(obs[a.L - 1]), g, ea);
+    }
+    double *gacc_base = a.gacc + int64_t(blockIdx.x) * NT + threadIdx.x;
+    const int64_t gacc_stride = int64_t(gridDim.x) * NT;
+#pragma unroll 1
+    for (int i = 0; i < 6 * MT; ++i) gacc_base[int64_t(i) * gacc_stride] = 0.0;
+    // vectors of the block being processed and of the next one (loaded one block ahead)
+    F xb[kNorm][MT], xn[kNorm][MT];
+    auto load_block = [&](int64_t blk_i, F(&dst)[kNorm][MT]) {
+        const int64_t t0 = blk_i * kNorm;
+#pragma unroll
+        for (int j = 0; j < kNorm; ++j) {
+            if (t0 + j < a.L) {
+#pragma unroll
+                for (int q = 0; q < QN; ++q) unpack<F>(xall[((t0 + j) * QN + q) * 32], &dst[j][q * W]);
+            }
+        }
+    };
+    load_block(n_blocks - 1, xn);
+    uint32_t obs_next = __ldg(reinterpret_cast<const unsigned int *>(obs + (n_blocks - 1) * kNorm));
+    F scale_next = sall[(n_blocks - 1) * 32];
+    F post[MT];  // forward vector after the most recently processed site (for the drift control)
+#pragma unroll
+    for (int k = 0; k < MT; ++k) post[k] = x[k];
+    constexpr int kAhead = 8;  // blocks of lead for the L2 prefetch hints (DRAM latency >> one block)
+    for (int64_t blk_i = n_blocks - 1; blk_i >= 0; --blk_i) {
+        const int64_t t0 = blk_i * kNorm;
+#pragma unroll
+        for (int j = 0; j < kNorm; ++j) {
+#pragma unroll
+            for (int k = 0; k < MT; ++k) xb[j][k] = xn[j][k];
+        }
+        const uint32_t blk = obs_next;
+        const F scale = scale_next;
+        if (blk_i > 0) {
+            // everything the next block needs is requested now, one block ahead
+            load_block(blk_i - 1, xn);
+            obs_next = __ldg(reinterpret_cast<const unsigned int *>(obs + t0 - kNorm));
+            scale_next = sall[(blk_i - 1) * 32];
+        }
+        if (blk_i >= kAhead) {
+#pragma unroll
+            for (int j = 0; j < kNorm; ++j) {
+#pragma unroll
+                for (int q = 0; q < QN; ++q) prefetch_l2(&xall[(((blk_i - kAhead) * kNorm + j) * QN + q) * 32]);
+            }
+        }
+        // the observation just before this block is the last byte of the word that is on its way
+        const int ob_before = t0 > 0 ? ObsWords<K>::byte_of(obs_next, kNorm - 1) : -1;
+        const int len = int(min(int64_t(kNorm), a.L - t0));
+        if ((blk_i & 3) == 3) {
+            // every 16 sites: re-impose beta . alpha == 1 against round-off drift
+            F dot = F(0);
+#pragma unroll
+            for (int k = 0; k < MT; ++k) dot = fma(post[k], beta[k], dot);
+            dot = fast_rcp<F>(lanes_total<F, T>(dot));
+#pragma unroll
+            for (int k = 0; k < MT; ++k) beta[k] *= dot;
+        }
+#pragma unroll
+        for (int k = 0; k < MT; ++k) beta[k] *= scale;
+#pragma unroll
+        for (int j = kNorm - 1; j >= 0; --j) {
+            if (j < len) {
+                const int ob_prev = j > 0 ? ObsWords<K>::byte_of(blk, j - 1) : ob_before;
+                backward_site<F, MT, T, NT, false>(beta, xb[j], ObsWords<K>::byte_of(blk, j), ob_prev, p, pc, et, sub, g, ea);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < MT; ++k) post[k] = xb[0][k];
+        if ((blk_i & (kFlushSites / kNorm - 1)) == 0) {
+            flush_row<F, MT>(g.b, 0, gacc_base, gacc_stride);
+            flush_row<F, MT>(g.d, 1, gacc_base, gacc_stride);
+            flush_row<F, MT>(g.u, 2, gacc_base, gacc_stride);
+            flush_row<F, MT>(g.v, 3, gacc_base, gacc_stride);
+            flush_row<F, MT>(g.e0, 4, gacc_base, gacc_stride);
+            flush_row<F, MT>(g.e1, 5, gacc_base, gacc_stride);
+        }
+    }
+    if (writer) {
+        F *out = static_cast<F *>(a.dlog) + pair * 7 * M + sub * MT;
+#pragma unroll
+        for (int k = 0; k < MT; ++k) {
+            F val[7];
+            val[0] = F(gacc_base[int64_t(0 * MT + k) * gacc_stride] * double(p.b[k]));
+            val[1] = F(gacc_base[int64_t(1 * MT + k) * gacc_stride] * double(p.d[k]));
+            val[2] = F(gacc_base[int64_t(2 * MT + k) * gacc_stride] * double(p.u[k]));
+            val[3] = F(gacc_base[int64_t(3 * MT + k) * gacc_stride] * double(p.v[k]));
+            val[4] = F(gacc_base[int64_t(4 * MT + k) * gacc_stride]);
+            val[5] = F(gacc_base[int64_t(5 * MT + k) * gacc_stride]);
+            val[6] = beta[k] * pi_p[k];
+#pragma unroll
+            for (int r = 0; r < 7; ++r) out[r * M + k] = a.out_mode ? out[r * M + k] - val[r] : val[r];
         }
     }
 }

@@ -114,6 +114,10 @@ class _PSMCKernelBase:
     def set_threads_per_pair(self, t: int) -> None:
         _check(self._lib.phb_set_threads_per_pair(self._handle, int(t)))
 
+    def set_store_all(self, mode: int) -> None:
+        """-1 auto, 0 never, 1 always: the store-all gradient kernel for small minibatches."""
+        _check(self._lib.phb_set_store_all(self._handle, int(mode)))
+
     @property
     def last_kernel_ms(self) -> float:
         return float(self._lib.phb_last_kernel_ms(self._handle))

@@ -346,3 +346,57 @@ def test_device_entry_reports_bad_index_at_sync(golden):
     ll = ll.cpu().numpy()
     assert np.isnan(ll[:, 1]).all() and np.isfinite(ll[:, [0, 2]]).all()
     kern.sync()  # the flag is cleared once reported
+
+
+@pytest.mark.parametrize("M", [4, 8, 16, 32, 64])
+def test_store_all_kernel(M):
+    """The small-minibatch gradient kernel (keeps every forward vector instead of recomputing)
+    against the oracle and against the checkpointing kernel."""
+    rng = np.random.default_rng(200 + M)
+    data = random_data(rng, 5, 1003, het=0.1, miss=0.05)
+    pps, _, _ = orc.synth_particles(M, 6, seed=M + 3)
+    pa = np.broadcast_to(pps[:, None], (6, 3, 7, M)).copy()
+    inds = np.array([4, 0, 2])
+    kern = make_kernel(M, data).gpu_kernels[0]
+    kern.set_store_all(1)
+    ll, dlog = kern.evaluate(pa, inds, True)
+    assert "storeall" in kern.last_kernel_name
+    ref_ll, ref_dlog = oracle_eval(data, inds, pa)
+    np.testing.assert_allclose(ll, ref_ll, rtol=LL_RTOL)
+    grad_close(dlog, ref_dlog, GRAD_RTOL, f"store-all M={M}")
+    kern.set_store_all(0)
+    ll2, dlog2 = kern.evaluate(pa, inds, True)
+    assert "storeall" not in kern.last_kernel_name
+    np.testing.assert_allclose(ll2, ll, rtol=1e-6)
+    grad_close(dlog2, dlog, 1e-4, "store-all vs checkpointing")
+
+
+@pytest.mark.parametrize("length", [1, 3, 4, 5, 17, 64, 130])
+def test_store_all_ragged_lengths(golden, length):
+    rng = np.random.default_rng(length + 77)
+    data = random_data(rng, 3, length, het=0.2, miss=0.1)
+    pp = golden["part_pp"][4]
+    pa = np.broadcast_to(pp, (2, 3, 7, 16)).copy()
+    kern = make_kernel(16, data).gpu_kernels[0]
+    kern.set_store_all(1)
+    ll, dlog = kern.evaluate(pa, np.arange(3), True)
+    ref_ll, ref_dlog = oracle_eval(data, np.arange(3), pa)
+    np.testing.assert_allclose(ll, ref_ll, rtol=LL_RTOL, atol=1e-6)
+    grad_close(dlog, ref_dlog, GRAD_RTOL, f"store-all L={length}")
+
+
+def test_store_all_with_fused_warmup(golden):
+    """The two-launch warm-up evaluation goes through the same dispatcher (second launch subtracts)."""
+    chunks, inds = golden["model_chunks"], golden["model_inds"]
+    pps = golden["part_pp"][:4].astype(np.float32).astype(np.float64)
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    k1 = _PSMCKernelBase(16, chunks)
+    k1.set_store_all(1)
+    a = k1.evaluate_warmup(pps, inds, 50, True)
+    k0 = _PSMCKernelBase(16, chunks)
+    k0.set_store_all(0)
+    b = k0.evaluate_warmup(pps, inds, 50, True)
+    np.testing.assert_allclose(a[0], b[0], rtol=1e-6)
+    scale = np.abs(b[1]).max(-1, keepdims=True)
+    assert np.all(np.abs(a[1] - b[1]) <= 1e-4 * np.abs(b[1]) + 1e-5 * scale)
