@@ -232,7 +232,10 @@ int check_handle(const phb_kernel *k) {
 int launch(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream) {
     const int64_t n_pairs = a.B * a.S;
     if (n_pairs == 0) return PHB_OK;
-    if (grad && !k->dbl && k->store_all_mode != 0 && k->force_T == 0) {
+    // tuning knob for experiments: PHB_STORE_ALL=0/1 overrides the mode set through the API
+    const char *sa_env = getenv("PHB_STORE_ALL");
+    const int sa_mode = sa_env ? atoi(sa_env) : k->store_all_mode;
+    if (grad && !k->dbl && sa_mode != 0 && k->force_T == 0) {
         for (const StoreAllVariant &sv : storeall_variants()) {
             if (sv.M != k->M) continue;
             const int pairs_per_cta = sv.NT / sv.T;
@@ -240,13 +243,15 @@ int launch(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream) {
             const int64_t warps = grid * (sv.NT / 32);
             const size_t x_bytes = size_t(warps) * size_t(a.L) * sv.MT * 32 * sizeof(float);
             const size_t s_bytes = size_t(warps) * size_t((a.L + phb::kNorm - 1) / phb::kNorm) * 32 * sizeof(float);
-            bool use = k->store_all_mode == 1;
-            if (k->store_all_mode < 0) {
-                // latency-bound regime (fewer than ~128 threads per SM) and the scratch fits comfortably
+            bool use = sa_mode == 1;
+            if (sa_mode < 0) {
+                // latency-bound regime and the scratch fits comfortably.  Measured on B200 at M = 16,
+                // B = 500 (profiles/r01_probe_small_minibatch.log): store-all wins up to ~12 000 pairs
+                // (S = 24: 23.4 vs 27.2 ms) and loses from ~16 000 pairs on.
                 size_t free_b = 0, total_b = 0;
                 cudaMemGetInfo(&free_b, &total_b);
                 const size_t have = free_b + k->xall.cap + k->sall.cap;
-                use = n_pairs * sv.T <= int64_t(k->num_sms) * 128 && x_bytes + s_bytes <= have / 2;
+                use = n_pairs * sv.T <= int64_t(k->num_sms) * 320 && x_bytes + s_bytes <= have / 2;
             }
             if (!use) break;
             int rc;
