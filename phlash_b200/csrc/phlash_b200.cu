@@ -251,7 +251,7 @@ int launch(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream) {
                 size_t free_b = 0, total_b = 0;
                 cudaMemGetInfo(&free_b, &total_b);
                 const size_t have = free_b + k->xall.cap + k->sall.cap;
-                use = n_pairs * sv.T <= int64_t(k->num_sms) * 320 && x_bytes + s_bytes <= have / 2;
+                use = n_pairs * sv.T <= int64_t(k->num_sms) * 330 && x_bytes + s_bytes <= have / 2;
             }
             if (!use) break;
             int rc;
