@@ -244,14 +244,14 @@ int launch(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream) {
             const size_t x_bytes = size_t(warps) * size_t(a.L) * sv.MT * 32 * sizeof(float);
             const size_t s_bytes = size_t(warps) * size_t((a.L + phb::kNorm - 1) / phb::kNorm) * 32 * sizeof(float);
             bool use = sa_mode == 1;
-            if (sa_mode < 0) {
+            if (sa_mode < 0 && n_pairs * sv.T <= int64_t(k->num_sms) * 330) {
                 // latency-bound regime and the scratch fits comfortably.  Measured on B200 at M = 16,
                 // B = 500 (profiles/r01_probe_small_minibatch.log): store-all wins up to ~12 000 pairs
-                // (S = 24: 23.4 vs 27.2 ms) and loses from ~16 000 pairs on.
+                // (S = 24: 23.4 vs 27.2 ms) and loses from ~16 000 pairs on.  (The memory query is
+                // only made here: it costs host milliseconds, which a large launch must not pay.)
                 size_t free_b = 0, total_b = 0;
                 cudaMemGetInfo(&free_b, &total_b);
-                const size_t have = free_b + k->xall.cap + k->sall.cap;
-                use = n_pairs * sv.T <= int64_t(k->num_sms) * 330 && x_bytes + s_bytes <= have / 2;
+                use = x_bytes + s_bytes <= (free_b + k->xall.cap + k->sall.cap) / 2;
             }
             if (!use) break;
             int rc;
