@@ -14,6 +14,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 namespace {
@@ -89,6 +90,7 @@ struct phb_kernel {
     int num_sms = 0;
     int64_t launches = 0;
     char last_name[96] = "";
+    std::unordered_map<const void *, int> occupancy;  // per kernel function: attribute set, CTAs per SM
     DeviceBuffer params, inds, ll, dlog, ckpt, gacc, xall, sall;
     int store_all_mode = -1;  // -1 auto, 0 never, 1 whenever a store-all variant exists
     size_t elem() const { return dbl ? sizeof(double) : sizeof(float); }
@@ -263,7 +265,10 @@ int launch(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream) {
             a.gacc = static_cast<double *>(k->gacc.ptr);
             a.n_groups = grid;
             a.err_flag = k->d_err;
-            PHB_CUDA(cudaFuncSetAttribute(sv.func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sv.smem)));
+            if (k->occupancy.find(sv.func) == k->occupancy.end()) {
+                PHB_CUDA(cudaFuncSetAttribute(sv.func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sv.smem)));
+                k->occupancy.emplace(sv.func, 1);
+            }
             void *kargs[] = {&a};
             PHB_CUDA(cudaEventRecord(k->ev0, stream));
             PHB_CUDA(cudaLaunchKernel(sv.func, dim3(unsigned(grid)), dim3(sv.NT), kargs, sv.smem, stream));
@@ -279,9 +284,17 @@ int launch(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream) {
     const int pairs_per_cta = v->NT / v->T;
     a.n_groups = (n_pairs + pairs_per_cta - 1) / pairs_per_cta;
     const size_t smem = v->smem;
-    PHB_CUDA(cudaFuncSetAttribute(v->func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int occ = 0;
-    PHB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v->func, v->NT, smem));
+    {
+        auto it = k->occupancy.find(v->func);
+        if (it == k->occupancy.end()) {
+            PHB_CUDA(cudaFuncSetAttribute(v->func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            PHB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v->func, v->NT, smem));
+            k->occupancy.emplace(v->func, occ);
+        } else {
+            occ = it->second;
+        }
+    }
     if (occ < 1) return fail(PHB_E_CUDA, "kernel does not fit on an SM (smem %zu bytes)", smem);
     const int64_t grid = std::min<int64_t>(a.n_groups, int64_t(occ) * k->num_sms);
     if (grad) {
