@@ -191,31 +191,42 @@ __device__ __forceinline__ void sts_scalar(uint32_t addr, double v) { asm volati
 // Per-lane emission table in shared memory: rows emis0, emis1 of this lane's MT states, laid out
 // [row][MT / W][NT] in 128-bit words so that a warp's access is conflict free.  `base` already
 // points at this thread's column.
+template <int MT> __host__ __device__ constexpr bool emis_acc_in_smem() { return MT >= 16; }
+
 template <typename F, int MT, int NT> struct EmisTable {
     using V = typename Vec<F>::type;
     static constexpr int W = Vec<F>::W;
     static constexpr int QN = MT / W;
+    // MT >= 16 layouts keep a third per-thread row of ones (the emission of a missing observation):
+    // the row is then chosen by ONE address computation and the loads use immediate offsets.  The
+    // other layouts have no shared memory to spare and redirect each load to one shared word of ones.
+    static constexpr bool kOnesRow = emis_acc_in_smem<MT>();
+    static constexpr int kRows = kOnesRow ? 3 : 2;
     uint32_t base;  // shared address of this thread's column
-    uint32_t ones;  // shared address of the one 128-bit word of 1.0 shared by the CTA
+    uint32_t ones;  // shared address of the one 128-bit word of 1.0 shared by the CTA (!kOnesRow)
     __device__ __forceinline__ void fill(const F *__restrict__ src, int M) {
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < kRows; ++r) {
 #pragma unroll
             for (int q = 0; q < QN; ++q) {
                 F tmp[W];
 #pragma unroll
-                for (int i = 0; i < W; ++i) tmp[i] = src[(4 + r) * M + q * W + i];
+                for (int i = 0; i < W; ++i) tmp[i] = r < 2 ? src[(4 + r) * M + q * W + i] : F(1);
                 sts_word(base + (r * QN + q) * NT * 16, tmp);
             }
         }
     }
-    // emission probabilities of observation `ob` for this lane's states.  A missing observation
-    // emits 1 in every state: one word of ones shared by the whole CTA sits behind the table, and
-    // the choice is made on the ADDRESS (one select per 128-bit load, not one per state).
+    // emission probabilities of observation `ob` for this lane's states (missing -> 1)
     __device__ __forceinline__ void get(int ob, F (&e)[MT]) const {
-        const uint32_t row_base = base + (ob == 1 ? QN * NT * 16 : 0);
+        if constexpr (kOnesRow) {
+            const uint32_t row_base = base + (ob < 0 ? 2 : ob) * (QN * NT * 16);
 #pragma unroll
-        for (int q = 0; q < QN; ++q) lds_word(ob < 0 ? ones : row_base + q * NT * 16, &e[q * W]);
+            for (int q = 0; q < QN; ++q) lds_word(row_base + q * NT * 16, &e[q * W]);
+        } else {
+            const uint32_t row_base = base + (ob == 1 ? QN * NT * 16 : 0);
+#pragma unroll
+            for (int q = 0; q < QN; ++q) lds_word(ob < 0 ? ones : row_base + q * NT * 16, &e[q * W]);
+        }
     }
 };
 
@@ -494,9 +505,8 @@ template <int K> struct ObsWords {
 
 // emission table always; the ring of forward vectors and block scales only for the gradient kernel
 // thread-per-pair layouts (MT >= 16) keep the emission-row accumulators in shared memory
-template <int MT> __host__ __device__ constexpr bool emis_acc_in_smem() { return MT >= 16; }
 template <typename F, int MT, int K, int NT, bool GRAD> constexpr size_t smem_bytes() {
-    return 16 + sizeof(F) * (size_t(2) * MT * NT +
+    return (emis_acc_in_smem<MT>() ? 0 : 16) + sizeof(F) * (size_t(emis_acc_in_smem<MT>() ? 3 : 2) * MT * NT +
                              (GRAD ? size_t(K) * MT * NT + size_t(K / kNorm) * NT + (emis_acc_in_smem<MT>() ? size_t(3) * MT * NT : 0) : 0));
 }
 // checkpoint scratch bytes per resident warp
@@ -534,24 +544,27 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
     //   block scale factors         per warp [K / kNorm][32] scalars           (gradient kernel)
     //   emission-row accumulators   [3][QN][NT]                                 (MT >= 16 gradient kernel)
     constexpr bool ESM = GRAD && emis_acc_in_smem<MT>();
-    constexpr int kTabWords = 1 + 2 * QN * NT;
+    constexpr int kOnesWords = EmisTable<F, MT, NT>::kOnesRow ? 0 : 1;
+    constexpr int kTabWords = kOnesWords + EmisTable<F, MT, NT>::kRows * QN * NT;
     constexpr int kRingWords = K * QN * NT;
     constexpr int kScaleWords = (K / kNorm) * NT / W;  // scalars packed W per word
     const uint32_t smem0 = smem_base_addr();
     EmisTable<F, MT, NT> et;
     et.ones = smem0;
-    et.base = smem0 + (1 + threadIdx.x) * 16;
+    et.base = smem0 + (kOnesWords + threadIdx.x) * 16;
     const uint32_t seg_a = smem0 + (kTabWords + warp * (K * QN * 32) + lane) * 16;  // + (k * QN + q) * 32 * 16
     const uint32_t scale_a = smem0 + (kTabWords + kRingWords) * 16 + (warp * (K / kNorm * 32) + lane) * uint32_t(sizeof(F));
     EmisAcc<F, MT, NT> ea;
     ea.base = smem0 + (kTabWords + kRingWords + kScaleWords + threadIdx.x) * 16;
-    if (threadIdx.x == 0) {
-        F one[W];
+    if constexpr (kOnesWords == 1) {
+        if (threadIdx.x == 0) {
+            F one[W];
 #pragma unroll
-        for (int i = 0; i < W; ++i) one[i] = F(1);
-        sts_word(smem0, one);
+            for (int i = 0; i < W; ++i) one[i] = F(1);
+            sts_word(smem0, one);
+        }
+        __syncthreads();  // the only block-level barrier: publishes the word of ones
     }
-    __syncthreads();  // the only block-level barrier: publishes the word of ones
 
     const int sub = lane % T;
     const int lp = lane / T;
