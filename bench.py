@@ -343,6 +343,14 @@ def main():
         }
         if lik_step is not None:
             line["likelihood_step"] = lik_step
+        if not args.skip_baselines and world == 1:
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import svgd_demo
+
+                line["svgd_harness"] = svgd_demo.run(n_iter=40, S=5, device=local_rank)
+            except Exception as e:  # an extra, never allowed to take the benchmark down
+                line["svgd_harness"] = {"unavailable": repr(e)[:200]}
         if not args.skip_baselines:
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline(data, pps).items() if k != "seconds_per_step"}
             try:
