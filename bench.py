@@ -326,6 +326,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload_name(), "M": M, "particles": B, "chunks": S, "chunk_bins": length,
                        "overlap": OVERLAP, "pairs_per_gpu": B * S, "site_transitions_per_step_per_gpu": st_per_step,
+                       "rows_scored_in_double": kern.num_escalated_rows,
                        "l2": "256 MiB L2 flush between timed steps",
                        "parallelism": f"dp{world}: chunks sharded, 1 all-reduce of [B,1+7M] per step" if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",

@@ -97,6 +97,17 @@ int phb_set_threads_per_pair(phb_kernel *k, int threads_per_pair);
  * threads_per_pair is forced). */
 int phb_set_store_all(phb_kernel *k, int mode);
 
+/* PRECISION ESCALATION (single-precision objects, gradient path).  Through a long run of identical
+ * observations (masked centromere, the -1 padding of a contig's last chunk, a run of homozygosity)
+ * fp32 forward / adjoint vectors stagnate at a floating-point fixed point and the transition rows of
+ * that chunk's gradient lose up to ~(run length) x 6e-8 relative - a property of any fp32
+ * implementation of the recursion, the reference's included.  At creation every row that contains an
+ * aligned window of 1024 identical observations is marked; pairs on marked rows are evaluated with
+ * double arithmetic (same float buffers, second launch on the same stream).  enabled: 1 (default) / 0.
+ * phb_num_escalated_rows reports how many rows are marked (0 for double-precision objects). */
+int phb_set_precision_escalation(phb_kernel *k, int enabled);
+int64_t phb_num_escalated_rows(const phb_kernel *k);
+
 /* HOST-buffer evaluation; blocking.  Replaces _PSMCKernelBase.__call__ (gpu.py:182-325) for
  * pa of shape [B, S, 7, M]: pair (b, s) scores data row inds[s] with parameter block
  * params[b, s].  ll is [B, S]; dlog is [B, S, 7, M] and may be NULL together with

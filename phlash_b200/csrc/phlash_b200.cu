@@ -91,14 +91,19 @@ struct phb_kernel {
     int64_t launches = 0;
     char last_name[96] = "";
     std::unordered_map<const void *, int> occupancy;  // per kernel function: attribute set, CTAs per SM
-    DeviceBuffer params, inds, ll, dlog, ckpt, gacc, xall, sall;
+    DeviceBuffer params, inds, ll, dlog, ckpt, gacc, xall, sall, split;
     int store_all_mode = -1;  // -1 auto, 0 never, 1 whenever a store-all variant exists
+    // precision escalation (float objects): rows holding a long run of identical observations are
+    // scored with double arithmetic, see flag_long_runs_kernel
+    uint8_t *d_rowflag = nullptr;  // [N]
+    int64_t n_flagged = 0;
+    int escalate = 1;
     size_t elem() const { return dbl ? sizeof(double) : sizeof(float); }
 };
 
 namespace {
 
-template <typename F, int MT, int T, int K, bool GRAD, int NT, int MINB> Variant make_variant() {
+template <typename F, int MT, int T, int K, bool GRAD, int NT, int MINB, typename IO = F> Variant make_variant() {
     Variant v;
     v.M = MT * T;
     v.T = T;
@@ -106,7 +111,7 @@ template <typename F, int MT, int T, int K, bool GRAD, int NT, int MINB> Variant
     v.NT = NT;
     v.dbl = sizeof(F) == 8;
     v.grad = GRAD;
-    v.func = reinterpret_cast<const void *>(&phb::psmc_loglik_kernel<F, MT, T, K, GRAD, NT, MINB>);
+    v.func = reinterpret_cast<const void *>(&phb::psmc_loglik_kernel<F, MT, T, K, GRAD, NT, MINB, IO>);
     v.smem = phb::smem_bytes<F, MT, K, NT, GRAD>();
     v.ckpt_bytes_per_warp = [](int64_t L) { return phb::ckpt_bytes_per_warp<F, MT, K>(L); };
     return v;
@@ -170,6 +175,20 @@ const std::vector<Variant> &variants() {
     return table;
 }
 
+// Precision-escalation kernels of float objects: double arithmetic on float buffers (gradient path).
+const Variant *escalation_variant(int M) {
+    static const std::vector<Variant> table = {
+        make_variant<double, 4, 1, 8, true, 128, 2, float>(),   // M = 4
+        make_variant<double, 4, 2, 8, true, 128, 2, float>(),   // M = 8
+        make_variant<double, 4, 4, 8, true, 128, 2, float>(),   // M = 16
+        make_variant<double, 4, 8, 8, true, 128, 2, float>(),   // M = 32
+        make_variant<double, 4, 16, 8, true, 128, 2, float>(),  // M = 64
+    };
+    for (const Variant &v : table)
+        if (v.M == M) return &v;
+    return nullptr;
+}
+
 // Store-all gradient kernels (small minibatches, see psmc_kernels.cuh): float only.
 struct StoreAllVariant {
     int M, T, MT, NT;
@@ -230,14 +249,14 @@ int check_handle(const phb_kernel *k) {
     return PHB_OK;
 }
 
-// Launch on `stream`; all pointers in `a` are device pointers except the ones filled in here.
-int launch(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream) {
-    const int64_t n_pairs = a.B * a.S;
-    if (n_pairs == 0) return PHB_OK;
+// One kernel launch on `stream` over the whole minibatch or over the sub-list in `a`; `fixed` pins the
+// kernel variant (precision escalation), nullptr lets the dispatcher choose.
+int launch_one(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream, const Variant *fixed) {
+    const int64_t n_pairs = a.B * a.S;  // upper bound when a sub-list is given
     // tuning knob for experiments: PHB_STORE_ALL=0/1 overrides the mode set through the API
     const char *sa_env = getenv("PHB_STORE_ALL");
     const int sa_mode = sa_env ? atoi(sa_env) : k->store_all_mode;
-    if (grad && !k->dbl && sa_mode != 0 && k->force_T == 0) {
+    if (!fixed && grad && !k->dbl && sa_mode != 0 && k->force_T == 0) {
         for (const StoreAllVariant &sv : storeall_variants()) {
             if (sv.M != k->M) continue;
             const int pairs_per_cta = sv.NT / sv.T;
@@ -270,16 +289,13 @@ int launch(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream) {
                 k->occupancy.emplace(sv.func, 1);
             }
             void *kargs[] = {&a};
-            PHB_CUDA(cudaEventRecord(k->ev0, stream));
             PHB_CUDA(cudaLaunchKernel(sv.func, dim3(unsigned(grid)), dim3(sv.NT), kargs, sv.smem, stream));
-            PHB_CUDA(cudaEventRecord(k->ev1, stream));
-            k->timed = true;
             k->launches += 1;
             snprintf(k->last_name, sizeof k->last_name, "psmc_loglik_storeall_kernel<float,MT=%d,T=%d,NT=%d>", sv.MT, sv.T, sv.NT);
             return PHB_OK;
         }
     }
-    const Variant *v = pick_variant(k, grad, n_pairs);
+    const Variant *v = fixed ? fixed : pick_variant(k, grad, n_pairs);
     if (!v) return fail(PHB_E_INVALID, "no kernel variant for M=%d, threads_per_pair=%d", k->M, k->force_T);
     const int pairs_per_cta = v->NT / v->T;
     a.n_groups = (n_pairs + pairs_per_cta - 1) / pairs_per_cta;
@@ -309,13 +325,44 @@ int launch(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream) {
     }
     a.err_flag = k->d_err;
     void *kargs[] = {&a};
-    PHB_CUDA(cudaEventRecord(k->ev0, stream));
     PHB_CUDA(cudaLaunchKernel(v->func, dim3(unsigned(grid)), dim3(v->NT), kargs, smem, stream));
+    k->launches += 1;
+    if (!fixed)
+        snprintf(k->last_name, sizeof k->last_name, "psmc_loglik_kernel<%s,MT=%d,T=%d,K=%d,%s,NT=%d>", v->dbl ? "double" : "float",
+                 v->M / v->T, v->T, v->K, v->grad ? "grad" : "fwd", v->NT);
+    return PHB_OK;
+}
+
+// Launch on `stream`; all pointers in `a` are device pointers except the ones filled in here.
+int launch(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream) {
+    if (a.B * a.S == 0) return PHB_OK;
+    const Variant *esc = (grad && !k->dbl && k->escalate && k->n_flagged > 0) ? escalation_variant(k->M) : nullptr;
+    PHB_CUDA(cudaEventRecord(k->ev0, stream));
+    int rc;
+    if (!esc) {
+        rc = launch_one(k, a, grad, stream, nullptr);
+    } else {
+        // split the minibatch on the device into un-flagged / flagged chunks; one launch for each
+        if (a.S > int64_t(INT32_MAX)) return fail(PHB_E_INVALID, "minibatch of %lld chunks is too large", (long long)a.S);
+        if ((rc = k->split.reserve((size_t(2) * a.S + 2) * sizeof(int32_t))) != PHB_OK) return rc;
+        int32_t *lists = static_cast<int32_t *>(k->split.ptr);
+        int32_t *counts = lists + 2 * a.S;
+        phb::split_minibatch_kernel<<<1, 1024, 0, stream>>>(a.inds, a.S, k->d_rowflag, k->N, lists, counts);
+        PHB_CUDA(cudaGetLastError());
+        k->launches += 1;
+        phb::KernelArgs part = a;
+        part.s_list = lists;
+        part.s_count = counts;
+        rc = launch_one(k, part, grad, stream, nullptr);
+        if (rc == PHB_OK) {
+            part.s_list = lists + a.S;
+            part.s_count = counts + 1;
+            rc = launch_one(k, part, grad, stream, esc);
+        }
+    }
+    if (rc != PHB_OK) return rc;
     PHB_CUDA(cudaEventRecord(k->ev1, stream));
     k->timed = true;
-    k->launches += 1;
-    snprintf(k->last_name, sizeof k->last_name, "psmc_loglik_kernel<%s,MT=%d,T=%d,K=%d,%s,NT=%d>", v->dbl ? "double" : "float",
-             v->M / v->T, v->T, v->K, v->grad ? "grad" : "fwd", v->NT);
     return PHB_OK;
 }
 
@@ -329,7 +376,7 @@ template <typename F> bool all_finite(const F *p, size_t n) {
 
 extern "C" {
 
-int phb_abi_version(void) { return 1; }
+int phb_abi_version(void) { return 2; }
 
 const char *phb_last_error(void) { return g_err.c_str(); }
 
@@ -383,6 +430,29 @@ static int new_kernel(int M, int64_t N, int64_t L, int double_precision, int dev
     return PHB_OK;
 }
 
+// Marks the rows that hold a long run of identical observations (float objects; see
+// flag_long_runs_kernel).  The data must be resident.
+static int flag_rows(phb_kernel *k) {
+    if (k->dbl) return PHB_OK;
+    PHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&k->d_rowflag), size_t(k->N)));
+    PHB_CUDA(cudaMemsetAsync(k->d_rowflag, 0, size_t(k->N), k->stream));
+    const int64_t n_win = k->L / phb::kRunWindow;
+    if (n_win > 0) {
+        const int threads = 256;
+        const int64_t want = (k->N * n_win * 32 + threads - 1) / threads;
+        phb::flag_long_runs_kernel<<<unsigned(std::min<int64_t>(want, int64_t(k->num_sms) * 32)), threads, 0, k->stream>>>(
+            k->d_data, k->N, k->L, k->pitch, k->d_rowflag);
+        PHB_CUDA(cudaGetLastError());
+        k->launches += 1;
+    }
+    std::vector<uint8_t> flags(size_t(k->N));
+    PHB_CUDA(cudaMemcpyAsync(flags.data(), k->d_rowflag, size_t(k->N), cudaMemcpyDeviceToHost, k->stream));
+    PHB_CUDA(cudaStreamSynchronize(k->stream));
+    k->n_flagged = 0;
+    for (uint8_t f : flags) k->n_flagged += f;
+    return PHB_OK;
+}
+
 int phb_create(int M, const int8_t *data, int64_t N, int64_t L, int double_precision, int device,
                phb_kernel **out) {
     if (!out) return fail(PHB_E_INVALID, "out is NULL");
@@ -422,6 +492,10 @@ int phb_create(int M, const int8_t *data, int64_t N, int64_t L, int double_preci
                 return fail(PHB_E_CUDA, "cudaMemcpy(data): %s", cudaGetErrorString(e));
             }
         }
+    }
+    if (int rc = flag_rows(k)) {
+        phb_destroy(k);
+        return rc;
     }
     *out = k;
     return PHB_OK;
@@ -467,6 +541,10 @@ int phb_create_from_contig(int M, const int8_t *het, int64_t n_rows, int64_t len
         phb_destroy(k);
         return fail(e == cudaErrorMemoryAllocation ? PHB_E_NOMEM : PHB_E_CUDA, "chunking on the device: %s", cudaGetErrorString(e));
     }
+    if (int rc = flag_rows(k)) {
+        phb_destroy(k);
+        return rc;
+    }
     *out = k;
     return PHB_OK;
 }
@@ -491,6 +569,8 @@ void phb_destroy(phb_kernel *k) {
     k->gacc.release();
     k->xall.release();
     k->sall.release();
+    k->split.release();
+    if (k->d_rowflag) cudaFree(k->d_rowflag);
     if (k->d_data) cudaFree(k->d_data);
     if (k->d_err) cudaFree(k->d_err);
     if (k->d_flags) cudaFree(k->d_flags);
@@ -520,6 +600,14 @@ int phb_set_store_all(phb_kernel *k, int mode) {
     k->store_all_mode = mode;
     return PHB_OK;
 }
+
+int phb_set_precision_escalation(phb_kernel *k, int enabled) {
+    if (int rc = check_handle(k)) return rc;
+    k->escalate = enabled ? 1 : 0;
+    return PHB_OK;
+}
+
+int64_t phb_num_escalated_rows(const phb_kernel *k) { return k ? k->n_flagged : 0; }
 
 int phb_set_threads_per_pair(phb_kernel *k, int threads_per_pair) {
     if (int rc = check_handle(k)) return rc;

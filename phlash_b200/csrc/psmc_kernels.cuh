@@ -57,7 +57,26 @@ struct KernelArgs {
     int *err_flag;       // bit 0: index out of range, bit 1: non-finite result
     int out_mode;        // 0: ll / dlog are written;  1: the results are SUBTRACTED from what is there
                          // (second launch of the fused warm-up evaluation, see phb_loglik_warmup_*)
+    // Optional restriction to a SUBSET of the minibatch (precision escalation, see
+    // flag_long_runs_kernel): the launch scores pairs (b, s_list[j]) for j < *s_count only; both live
+    // in device memory, so the split needs no host round trip.  nullptr = all S chunks.
+    const int32_t *s_list;
+    const int32_t *s_count;
 };
+
+// Pair enumeration shared by the kernels: b major, position in the (sub-)list minor.
+struct PairIndex {
+    int64_t b, s, out;  // particle, position in the full minibatch, index into ll / dlog ([B, S])
+};
+__device__ __forceinline__ int64_t listed_chunks(const KernelArgs &a) { return a.s_list ? int64_t(*a.s_count) : a.S; }
+__device__ __forceinline__ PairIndex pair_index(const KernelArgs &a, int64_t pair, int64_t s_eff) {
+    PairIndex r;
+    r.b = pair / s_eff;
+    const int64_t j = pair % s_eff;
+    r.s = a.s_list ? int64_t(a.s_list[j]) : j;
+    r.out = r.b * a.S + r.s;
+    return r;
+}
 
 template <typename F> struct Vec;
 template <> struct Vec<float> {
@@ -141,13 +160,13 @@ __device__ __forceinline__ double bit_select(uint32_t mask, double a, double b) 
 // selects per state and site, the table costs one 128-bit shared load per four states.
 template <typename F, int MT> struct Params {
     F b[MT], d[MT], u[MT], v[MT];
-    __device__ __forceinline__ void load(const F *__restrict__ src, int M) {
+    template <typename IO> __device__ __forceinline__ void load(const IO *__restrict__ src, int M) {
 #pragma unroll
         for (int k = 0; k < MT; ++k) {
-            b[k] = src[0 * M + k];
-            d[k] = src[1 * M + k];
-            u[k] = src[2 * M + k];
-            v[k] = src[3 * M + k];
+            b[k] = F(src[0 * M + k]);
+            d[k] = F(src[1 * M + k]);
+            u[k] = F(src[2 * M + k]);
+            v[k] = F(src[3 * M + k]);
         }
     }
 };
@@ -204,14 +223,14 @@ template <typename F, int MT, int NT> struct EmisTable {
     static constexpr int kRows = kOnesRow ? 3 : 2;
     uint32_t base;  // shared address of this thread's column
     uint32_t ones;  // shared address of the one 128-bit word of 1.0 shared by the CTA (!kOnesRow)
-    __device__ __forceinline__ void fill(const F *__restrict__ src, int M) {
+    template <typename IO> __device__ __forceinline__ void fill(const IO *__restrict__ src, int M) {
 #pragma unroll
         for (int r = 0; r < kRows; ++r) {
 #pragma unroll
             for (int q = 0; q < QN; ++q) {
                 F tmp[W];
 #pragma unroll
-                for (int i = 0; i < W; ++i) tmp[i] = r < 2 ? src[(4 + r) * M + q * W + i] : F(1);
+                for (int i = 0; i < W; ++i) tmp[i] = r < 2 ? F(src[(4 + r) * M + q * W + i]) : F(1);
                 sts_word(base + (r * QN + q) * NT * 16, tmp);
             }
         }
@@ -523,7 +542,9 @@ constexpr int max_regs(int nt, int minb) {
     return r > 255 ? 255 : r;
 }
 
-template <typename F, int MT, int T, int K, bool GRAD, int NT, int MINB>
+// F is the arithmetic type, IO the type of the parameter / gradient buffers (IO = float with
+// F = double is the precision-escalation variant of a single-precision kernel object).
+template <typename F, int MT, int T, int K, bool GRAD, int NT, int MINB, typename IO = F>
 __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelArgs a) {
     constexpr int kThreads = NT;
     constexpr int kWarps = NT / 32;
@@ -568,11 +589,13 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
 
     const int sub = lane % T;
     const int lp = lane / T;
-    const int64_t n_pairs = a.B * a.S;
+    const int64_t s_eff = listed_chunks(a);
+    const int64_t n_pairs = a.B * s_eff;
+    const int64_t n_groups = a.s_list ? (n_pairs + kWarps * PW - 1) / (kWarps * PW) : a.n_groups;
     const int64_t n_seg = (a.L + K - 1) / K;
     const int64_t warp_slot = int64_t(blockIdx.x) * kWarps + warp;
-    const F *params6 = static_cast<const F *>(a.params6);
-    const F *pi_g = static_cast<const F *>(a.pi);
+    const IO *params6 = static_cast<const IO *>(a.params6);
+    const IO *pi_g = static_cast<const IO *>(a.pi);
     V *ck = GRAD ? reinterpret_cast<V *>(static_cast<char *>(a.ckpt) + warp_slot * ckpt_bytes_per_warp<F, MT, K>(a.L)) + lane
                  : nullptr;
     constexpr int kFlushSegs = kFlushSites / K;
@@ -584,11 +607,11 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
 
     // the work list is walked per CTA (not per warp) so that every loop bound below is provably
     // uniform and the shuffles need no reconvergence guards
-    for (int64_t grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
+    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         const int64_t pair_raw = (grp * kWarps + warp) * PW + lp;
         const bool writer = pair_raw < n_pairs;
-        const int64_t pair = writer ? pair_raw : n_pairs - 1;  // idle lanes shadow the last pair
-        const int64_t pb = pair / a.S, ps = pair % a.S;
+        const PairIndex pidx = pair_index(a, writer ? pair_raw : n_pairs - 1, s_eff);  // idle lanes shadow the last pair
+        const int64_t pb = pidx.b, ps = pidx.s, pair = pidx.out;
         Params<F, MT> p;
         p.load(params6 + pb * a.pstride_b + ps * a.pstride_s + sub * MT, M);
         et.fill(params6 + pb * a.pstride_b + ps * a.pstride_s + sub * MT, M);
@@ -601,12 +624,12 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
             row = 0;
         }
         const int8_t *obs = a.data + row * a.pitch;
-        const F *pi_p = pi_g + pb * a.pistride_b + ps * a.pistride_s + sub * MT;
+        const IO *pi_p = pi_g + pb * a.pistride_b + ps * a.pistride_s + sub * MT;
 
         // ------------------------------------------------------------------ pass 1: forward
         F x[MT];
 #pragma unroll
-        for (int k = 0; k < MT; ++k) x[k] = pi_p[k];
+        for (int k = 0; k < MT; ++k) x[k] = F(pi_p[k]);
         double ll = 0.0;
         ObsWords<K> ow_next;
         ow_next.load(obs, 0);
@@ -639,9 +662,9 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
         if (bad_row) ll = __longlong_as_double(0x7ff8000000000000LL);
         if (writer && sub == 0) a.ll[pair] = a.out_mode ? a.ll[pair] - ll : ll;
         if (writer && a.alpha_out != nullptr) {
-            F *ao = static_cast<F *>(a.alpha_out) + pair * M + sub * MT;
+            IO *ao = static_cast<IO *>(a.alpha_out) + pair * M + sub * MT;
 #pragma unroll
-            for (int k = 0; k < MT; ++k) ao[k] = x[k];
+            for (int k = 0; k < MT; ++k) ao[k] = IO(x[k]);
         }
 
         if constexpr (GRAD) {
@@ -673,7 +696,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                 F xs[MT];
                 if (seg == 0) {
 #pragma unroll
-                    for (int k = 0; k < MT; ++k) xs[k] = pi_p[k];
+                    for (int k = 0; k < MT; ++k) xs[k] = F(pi_p[k]);
                 } else {
 #pragma unroll
                     for (int q = 0; q < QN; ++q) unpack<F>(ck[(seg * QN + q) * 32], &xs[q * W]);
@@ -740,7 +763,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                 }
             }
             if (writer) {
-                F *out = static_cast<F *>(a.dlog) + pair * 7 * M + sub * MT;
+                IO *out = static_cast<IO *>(a.dlog) + pair * 7 * M + sub * MT;
                 const double *gacc = PHB_GACC_BASE;
                 const int64_t gacc_stride = PHB_GACC_STRIDE;
 #pragma unroll
@@ -752,9 +775,9 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                     val[3] = F(gacc[int64_t(3 * MT + k) * gacc_stride] * double(p.v[k]));
                     val[4] = F(gacc[int64_t(4 * MT + k) * gacc_stride]);
                     val[5] = F(gacc[int64_t(5 * MT + k) * gacc_stride]);
-                    val[6] = beta[k] * pi_p[k];
+                    val[6] = beta[k] * F(pi_p[k]);
 #pragma unroll
-                    for (int r = 0; r < 7; ++r) out[r * M + k] = a.out_mode ? out[r * M + k] - val[r] : val[r];
+                    for (int r = 0; r < 7; ++r) out[r * M + k] = IO(a.out_mode ? F(out[r * M + k]) - val[r] : val[r]);
                 }
             }
         }
@@ -797,7 +820,11 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_storeall_kernel(cons
 
     const int sub = lane % T;
     const int lp = lane / T;
-    const int64_t n_pairs = a.B * a.S;
+    const int64_t s_eff = listed_chunks(a);
+    const int64_t n_pairs = a.B * s_eff;
+    // the grid is sized for the whole minibatch; with a sub-list the surplus warps have nothing to do
+    // (no block-level barrier follows, so whole warps may leave)
+    if ((int64_t(blockIdx.x) * kWarps + warp) * PW >= n_pairs) return;
     const int64_t n_blocks = (a.L + kNorm - 1) / kNorm;
     const int64_t warp_slot = int64_t(blockIdx.x) * kWarps + warp;
     const F *params6 = static_cast<const F *>(a.params6);
@@ -807,8 +834,8 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_storeall_kernel(cons
 
     const int64_t pair_raw = (int64_t(blockIdx.x) * kWarps + warp) * PW + lp;
     const bool writer = pair_raw < n_pairs;
-    const int64_t pair = writer ? pair_raw : n_pairs - 1;
-    const int64_t pb = pair / a.S, ps = pair % a.S;
+    const PairIndex pidx = pair_index(a, writer ? pair_raw : n_pairs - 1, s_eff);
+    const int64_t pb = pidx.b, ps = pidx.s, pair = pidx.out;
     Params<F, MT> p;
     p.load(params6 + pb * a.pstride_b + ps * a.pstride_s + sub * MT, M);
     et.fill(params6 + pb * a.pstride_b + ps * a.pstride_s + sub * MT, M);
@@ -966,6 +993,58 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_storeall_kernel(cons
             for (int r = 0; r < 7; ++r) out[r * M + k] = a.out_mode ? out[r * M + k] - val[r] : val[r];
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Precision escalation for single-precision kernel objects.
+//
+// Through a long run of IDENTICAL observations (a masked centromere, the -1 padding of a contig's
+// last chunk, a run of homozygosity) the forward and adjoint vectors converge to a fixed point of
+// the site operator.  Near it the true change per site is smaller than half an ulp of the fp32
+// components, the fp32 iteration stops moving, and the vectors are off by up to ~run length x 6e-8
+// relative; a 30 000-site run cost 4e-4 on the transition rows of the gradient
+// (profiles/r01_padded_chunk_accuracy.log).  Rows that contain such a run are rare, so they are simply
+// evaluated with double arithmetic (same float buffers): flag_long_runs_kernel marks them once, when
+// the data is made resident, and split_minibatch_kernel splits every minibatch into the two lists
+// the two launches work through.
+//
+// A row is flagged when one of its ALIGNED windows of kRunWindow sites holds a single value; every
+// constant run of >= 2 * kRunWindow - 1 sites contains such a window.  Un-flagged rows therefore
+// have runs < 2047 sites: <= 6e-5 relative on any gradient entry.
+constexpr int kRunWindow = 1024;
+
+// one warp per (row, window); lane l compares bytes [32 l, 32 l + 32) of the window with its first byte
+__global__ void flag_long_runs_kernel(const int8_t *__restrict__ data, int64_t n_rows, int64_t L, int64_t pitch,
+                                      uint8_t *__restrict__ row_flag) {
+    const int64_t n_win = L / kRunWindow;  // whole windows only
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; i < n_rows * n_win; i += warps) {
+        const int64_t row = i / n_win, win = i % n_win;
+        const uint4 *src = reinterpret_cast<const uint4 *>(data + row * pitch + win * kRunWindow) + 2 * lane;
+        const uint4 lo = __ldg(src), hi = __ldg(src + 1);
+        const uint32_t first = __shfl_sync(0xffffffffu, lo.x, 0) & 0xffu;
+        const uint32_t pat = first * 0x01010101u;
+        const bool same = lo.x == pat && lo.y == pat && lo.z == pat && lo.w == pat && hi.x == pat && hi.y == pat &&
+                          hi.z == pat && hi.w == pat;
+        if (__all_sync(0xffffffffu, same) && lane == 0) row_flag[row] = 1;
+    }
+}
+
+// One CTA.  lists = [2][S]: positions s of the minibatch whose row is un-flagged (list 0) / flagged
+// (list 1); counts = [2].  Out-of-range rows go to list 0, whose kernel reports them.
+__global__ void split_minibatch_kernel(const int64_t *__restrict__ inds, int64_t S, const uint8_t *__restrict__ row_flag,
+                                       int64_t n_rows, int32_t *__restrict__ lists, int32_t *__restrict__ counts) {
+    __shared__ int32_t n[2];
+    if (threadIdx.x < 2) n[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t s = threadIdx.x; s < S; s += blockDim.x) {
+        const int64_t r = inds[s];
+        const int f = (r >= 0 && r < n_rows && row_flag[r]) ? 1 : 0;
+        lists[f * S + atomicAdd(&n[f], 1)] = int32_t(s);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) counts[threadIdx.x] = n[threadIdx.x];
 }
 
 // Device-side chunking (reference: _chunk_het_matrix, data.py:37-61): out[n * n_chunks + k][j] =

@@ -118,6 +118,15 @@ class _PSMCKernelBase:
         """-1 auto, 0 never, 1 always: the store-all gradient kernel for small minibatches."""
         _check(self._lib.phb_set_store_all(self._handle, int(mode)))
 
+    def set_precision_escalation(self, enabled: bool) -> None:
+        """Rows with a long run of identical observations are scored with double arithmetic (default
+        on for single-precision objects; see include/phlash_b200.h)."""
+        _check(self._lib.phb_set_precision_escalation(self._handle, int(bool(enabled))))
+
+    @property
+    def num_escalated_rows(self) -> int:
+        return int(self._lib.phb_num_escalated_rows(self._handle))
+
     @property
     def last_kernel_ms(self) -> float:
         return float(self._lib.phb_last_kernel_ms(self._handle))

@@ -47,7 +47,7 @@ def test_no_torch_or_python_types_in_the_abi():
 
 
 def test_abi_version(lib):
-    assert lib.phb_abi_version() == 1
+    assert lib.phb_abi_version() == 2
 
 
 def test_create_rejects_bad_arguments_before_touching_cuda(lib):

@@ -120,6 +120,57 @@ __global__ void ffma2_plus_scalar(float *out, float b, float c) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// ---- single-warp probes (one warp on an otherwise idle SM), timed with clock64(): what bounds a
+// latency-bound kernel with at most one warp per SM sub-partition (small minibatches, ELPD)
+template <int MODE> __global__ void single_warp_probe(float *out, long long *cycles, float b, float c) {
+    float a[kChains];
+    float2 a2[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) {
+        a[i] = threadIdx.x * 1e-3f + i;
+        a2[i] = make_float2(a[i], a[i] * 0.5f);
+    }
+    const float2 bb = make_float2(b, b * 0.5f), cc = make_float2(c, c * 2.f);
+    int ia = threadIdx.x;
+    const long long t0 = clock64();
+    for (int it = 0; it < kIters; ++it) {
+        if (MODE == 0) {  // 16 independent FFMA
+#pragma unroll
+            for (int i = 0; i < kChains; ++i) a[i] = fmaf(a[i], b, c);
+        } else if (MODE == 1) {  // 16 independent FFMA2
+#pragma unroll
+            for (int i = 0; i < kChains; ++i) a2[i] = __ffma2_rn(a2[i], bb, cc);
+        } else if (MODE == 2) {  // 16 dependent FFMA
+#pragma unroll
+            for (int i = 0; i < kChains; ++i) a[0] = fmaf(a[0], b, c);
+        } else if (MODE == 3) {  // 16 dependent SHFL
+#pragma unroll
+            for (int i = 0; i < kChains; ++i) a[0] = __shfl_xor_sync(0xffffffffu, a[0], 1);
+        } else if (MODE == 4) {  // 16 dependent (SHFL + FFMA)
+#pragma unroll
+            for (int i = 0; i < kChains; ++i) a[0] = fmaf(__shfl_xor_sync(0xffffffffu, a[0], 1), b, c);
+        } else if (MODE == 5) {  // 8 independent FFMA interleaved with 8 independent integer ops (ALU pipe)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                a[i] = fmaf(a[i], b, c);
+                ia = (ia ^ (ia << 1)) + i;
+            }
+        } else if (MODE == 6) {  // 16 dependent FFMA2
+#pragma unroll
+            for (int i = 0; i < kChains; ++i) a2[0] = __ffma2_rn(a2[0], bb, cc);
+        } else if (MODE == 7) {  // 16 dependent MUFU.RCP
+#pragma unroll
+            for (int i = 0; i < kChains; ++i) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[0]));
+        }
+    }
+    const long long t1 = clock64();
+    float s = ia;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) s += a[i] + a2[i].x + a2[i].y;
+    out[threadIdx.x] = s;
+    if (threadIdx.x == 0) cycles[MODE] = t1 - t0;
+}
+
 __global__ void shfl_rate(float *out) {
     float a[8];
 #pragma unroll
@@ -215,6 +266,19 @@ int main() {
     float t5 = time_ms([&] { lds_broadcast_rate<<<ctas, threads>>>(out); }, 10);
     CHECK(cudaFuncSetAttribute(lds_private_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * threads * 16));
     float t6 = time_ms([&] { lds_private_rate<<<ctas, threads, 8 * threads * 16>>>(out); }, 10);
+    long long *cyc;
+    CHECK(cudaMalloc(&cyc, sizeof(long long) * 8));
+    single_warp_probe<0><<<1, 32>>>(out, cyc, 0.999f, 1e-3f);
+    single_warp_probe<1><<<1, 32>>>(out, cyc, 0.999f, 1e-3f);
+    single_warp_probe<2><<<1, 32>>>(out, cyc, 0.999f, 1e-3f);
+    single_warp_probe<3><<<1, 32>>>(out, cyc, 0.999f, 1e-3f);
+    single_warp_probe<4><<<1, 32>>>(out, cyc, 0.999f, 1e-3f);
+    single_warp_probe<5><<<1, 32>>>(out, cyc, 0.999f, 1e-3f);
+    single_warp_probe<6><<<1, 32>>>(out, cyc, 0.999f, 1e-3f);
+    single_warp_probe<7><<<1, 32>>>(out, cyc, 0.999f, 1e-3f);
+    long long hc[8];
+    CHECK(cudaMemcpy(hc, cyc, sizeof hc, cudaMemcpyDeviceToHost));
+    const double per = 1.0 / (double(kIters) * kChains);
     CHECK(cudaGetLastError());
     int clock_khz = 0;
     cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, 0);
@@ -227,6 +291,10 @@ int main() {
     printf(" \"shfl_warp_instr_per_sec\": %.4g,\n", lanes / 32 * kIters * 8 / (t4 * 1e-3));
     printf(" \"shfl_warp_instr_per_clk_per_sm_at_1965MHz\": %.3f,\n", lanes / 32 * kIters * 8 / (t4 * 1e-3) / sms / 1.965e9);
     printf(" \"lds128_broadcast_warp_instr_per_clk_per_sm_at_1965MHz\": %.3f,\n", lanes / 32 * kIters * 16 / (t5 * 1e-3) / sms / 1.965e9);
-    printf(" \"lds128_private_warp_instr_per_clk_per_sm_at_1965MHz\": %.3f}\n", lanes / 32 * kIters * 8 / (t6 * 1e-3) / sms / 1.965e9);
+    printf(" \"lds128_private_warp_instr_per_clk_per_sm_at_1965MHz\": %.3f,\n", lanes / 32 * kIters * 8 / (t6 * 1e-3) / sms / 1.965e9);
+    printf(" \"single_warp_cycles_per_instr\": {\"ffma_independent\": %.2f, \"ffma2_independent\": %.2f, \"ffma_dependent\": %.2f, "
+           "\"shfl_dependent\": %.2f, \"shfl_plus_ffma_dependent\": %.2f, \"ffma_and_alu_interleaved_per_pair\": %.2f, "
+           "\"ffma2_dependent\": %.2f, \"mufu_rcp_dependent\": %.2f}}\n",
+           hc[0] * per, hc[1] * per, hc[2] * per, hc[3] * per, hc[4] * per, hc[5] * per * 2, hc[6] * per, hc[7] * per);
     return 0;
 }
