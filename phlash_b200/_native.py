@@ -49,7 +49,8 @@ SIGNATURES = {
 
 
 def library_path() -> str:
-    return _build.LIB_PATH
+    # PHB_LIBRARY: an alternative build of the same ABI (kernel experiments)
+    return os.environ.get("PHB_LIBRARY") or _build.LIB_PATH
 
 
 def lib() -> ctypes.CDLL:
