@@ -1,11 +1,13 @@
 """Host-side data layer on the hot path: cutting binned contigs into overlapping chunks
 (reference: src/phlash/data.py:22-24, 37-61, 102-112, 506-558).  The reference does this once,
-in NumPy on the host; so does this mirror.  File readers (psmcfa / VCF / tree sequences) are out
-of scope."""
+in NumPy on the host; so does this mirror.  Of the file readers only the .psmcfa one is mirrored
+(data.py:122-149, psmc.py:8-29: plain text, no third-party parser needed); VCF and tree-sequence
+input need pysam / tskit and stay with the reference."""
 
 from __future__ import annotations
 
-from typing import NamedTuple, Optional, Sequence
+import gzip
+from typing import Iterator, List, NamedTuple, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -47,3 +49,44 @@ def init_mcmc_data(het_matrices: Sequence[np.ndarray], overlap: int, chunk_size:
 def split_warmup(chunks: np.ndarray, overlap: int):
     """warmup_chunks, data_chunks = np.split(chunks, [overlap], axis=1) (reference: mcmc.py:203)."""
     return chunks[:, :overlap], np.ascontiguousarray(chunks[:, overlap:])
+
+
+_PSMCFA_CODE = np.zeros(256, dtype=np.int8)  # every letter is "homozygous" ...
+_PSMCFA_CODE[ord("K")] = 1                   # ... except K = at least one heterozygote in the window
+_PSMCFA_CODE[ord("N")] = -1                  # and N = missing (reference: data.py:146-147, case sensitive)
+
+
+def read_psmcfa(path: str) -> Iterator[Tuple[str, np.ndarray]]:
+    """(name, het_matrix int8 [1, L]) for every record of a PSMC FASTA file, one entry per window of
+    the `fq2psmcfa -s` size (reference: RawContig.from_psmcfa_iter, data.py:122-149, which reads the
+    records with pysam.FastxFile; this is a plain FASTA reader, gzip transparently)."""
+    opener = gzip.open if open(path, "rb").read(2) == b"\x1f\x8b" else open
+    name, parts = None, []
+
+    def record():
+        seq = np.frombuffer(b"".join(parts), dtype=np.uint8)
+        return name, _PSMCFA_CODE[seq][None, :]
+
+    with opener(path, "rb") as fh:
+        for line in fh:
+            line = line.strip()
+            if not line:
+                continue
+            if line.startswith(b">"):
+                if name is not None:
+                    yield record()
+                name, parts = line[1:].split()[0].decode() if len(line) > 1 else "", []
+            else:
+                if name is None:
+                    raise ValueError(f"{path}: sequence data before the first '>' header")
+                parts.append(line)
+    if name is not None:
+        yield record()
+
+
+def psmc_inputs(psmcfa_files: Sequence[str], hold_out: bool = True) -> Tuple[List[np.ndarray], Optional[np.ndarray]]:
+    """het matrices of all contigs of the files, in order, and the held-out test contig: the first one,
+    when there is more than one (reference: psmc.psmc, psmc.py:22-28)."""
+    contigs = [het for f in psmcfa_files for _, het in read_psmcfa(f)]
+    test = contigs.pop(0) if hold_out and len(contigs) > 1 else None
+    return contigs, test

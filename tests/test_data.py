@@ -43,3 +43,49 @@ def test_values_are_clipped_and_padding_is_missing():
     assert ch.shape == (2, 5)
     np.testing.assert_array_equal(ch[0], [1, -1, 0, 1, 1])
     np.testing.assert_array_equal(ch[1], [1, 1, 0, 0, -1])
+
+
+def _write_psmcfa(path, records, width=60, gz=False):
+    import gzip
+
+    opener = gzip.open if gz else open
+    with opener(path, "wt") as fh:
+        for name, seq in records:
+            fh.write(f">{name} some description\n")
+            for i in range(0, len(seq), width):
+                fh.write(seq[i : i + width] + "\n")
+            fh.write("\n")
+
+
+@pytest.mark.parametrize("gz", [False, True])
+def test_read_psmcfa_follows_the_reference_decoding(tmp_path, gz):
+    """RawContig.from_psmcfa_iter (data.py:139-149): K -> 1, N -> -1, anything else -> 0 (case
+    sensitive), one row per record, records in file order."""
+    from phlash_b200.data import psmc_inputs, read_psmcfa
+
+    rng = np.random.default_rng(0)
+    records = [(f"chr{i}", "".join(rng.choice(list("TTTTTTKNnk"), size=n))) for i, n in enumerate([1, 59, 60, 61, 1000])]
+    path = str(tmp_path / ("x.psmcfa.gz" if gz else "x.psmcfa"))
+    _write_psmcfa(path, records, gz=gz)
+    got = list(read_psmcfa(path))
+    assert [n for n, _ in got] == [n for n, _ in records]
+    for (_, het), (_, seq) in zip(got, records):
+        arr = np.array(list(seq), dtype="c")            # the reference's own three lines
+        want = (arr == b"K").astype(np.int8)
+        want[arr == b"N"] = -1
+        assert het.dtype == np.int8 and het.shape == (1, len(seq))
+        np.testing.assert_array_equal(het[0], want)
+    contigs, test = psmc_inputs([path, path], hold_out=True)        # psmc.py:22-28
+    assert len(contigs) == 2 * len(records) - 1
+    np.testing.assert_array_equal(test, got[0][1])
+    contigs, test = psmc_inputs([path], hold_out=False)
+    assert test is None and len(contigs) == len(records)
+
+
+def test_read_psmcfa_rejects_headerless_input(tmp_path):
+    from phlash_b200.data import read_psmcfa
+
+    path = tmp_path / "bad.psmcfa"
+    path.write_text("TTTKTT\n")
+    with pytest.raises(ValueError):
+        list(read_psmcfa(str(path)))
