@@ -171,6 +171,31 @@ int phb_params_from_particles(phb_kernel *k, const double *x, int64_t B, const i
 int phb_params_vjp(phb_kernel *k, const double *x, int64_t B, const int32_t *epoch_widths, int n_epochs,
                    double theta, const void *cotangent, double *grad_x, void *stream);
 
+/* THE WHOLE HMM TERM of log_density for all particles (replaces model.py:50-57 with the weights of
+ * model.py:71-72 / mcmc.py:240-247, and JAX's reverse pass through it), asynchronous on `stream`, device
+ * pointers throughout, no host round trip:
+ *     value[b]     = weight * sum_s log p(chunk inds[s] | particle b, warm-up fused)
+ *     grad_x[b, :] = d value[b] / d x[b, :]            (x as in phb_params_from_particles)
+ * i.e. phb_params_from_particles -> phb_loglik_warmup_device -> sum over the minibatch -> phb_params_vjp
+ * on internal scratch.  The kernel object must hold FULL chunks [N, overlap + L].  grad_x == NULL selects
+ * the forward-only evaluation (the reference's ELPD, mcmc.py:221-236, is this with weight 1, overlap 1
+ * and the whole test contigs as "chunks").  A JAX binding is ONE custom_vjp over the flattened particle:
+ * forward = this call, backward = g[b] * grad_x[b, :].
+ *
+ * For one process per GPU the term is split around the collective: _sums_ leaves the per-particle sums
+ * [B, 1 + 7 M] (double: log-likelihood, then d / d log(theta) in params order) of this rank's part of the
+ * minibatch in `sums`; the caller all-reduces them (one NCCL call) and _finish_ maps the total to
+ * value / grad_x.  S == 0 is allowed (a rank without work contributes zeros). */
+int phb_hmm_term_device(phb_kernel *k, const double *x, int64_t B, const int32_t *epoch_widths, int n_epochs,
+                        double theta, const int64_t *inds, int64_t S, int64_t overlap, double weight,
+                        double *value, double *grad_x, void *stream);
+int phb_hmm_term_sums_device(phb_kernel *k, const double *x, int64_t B, const int32_t *epoch_widths, int n_epochs,
+                             double theta, const int64_t *inds, int64_t S, int64_t overlap, int want_grad,
+                             double *sums, void *stream);
+int phb_hmm_term_finish_device(phb_kernel *k, const double *x, int64_t B, const int32_t *epoch_widths,
+                               int n_epochs, double theta, const double *sums, double weight, double *value,
+                               double *grad_x, void *stream);
+
 /* Wait for the kernel object's own stream AND for the stream of the most recent
  * phb_loglik_device call, then report deferred device-side errors. */
 int phb_sync(phb_kernel *k);

@@ -92,6 +92,7 @@ struct phb_kernel {
     char last_name[96] = "";
     std::unordered_map<const void *, int> occupancy;  // per kernel function: attribute set, CTAs per SM
     DeviceBuffer params, inds, ll, dlog, ckpt, gacc, xall, sall, split;
+    DeviceBuffer term_params, term_ll, term_dlog, term_sums;  // scratch of the whole-term entries
     int store_all_mode = -1;  // -1 auto, 0 never, 1 whenever a store-all variant exists
     // precision escalation (float objects): rows holding a long run of identical observations are
     // scored with double arithmetic, see flag_long_runs_kernel
@@ -570,6 +571,10 @@ void phb_destroy(phb_kernel *k) {
     k->xall.release();
     k->sall.release();
     k->split.release();
+    k->term_params.release();
+    k->term_ll.release();
+    k->term_dlog.release();
+    k->term_sums.release();
     if (k->d_rowflag) cudaFree(k->d_rowflag);
     if (k->d_data) cudaFree(k->d_data);
     if (k->d_err) cudaFree(k->d_err);
@@ -888,6 +893,77 @@ int phb_params_vjp(phb_kernel *k, const double *x, int64_t B, const int32_t *epo
     PHB_CUDA(cudaGetLastError());
     k->launches += 1;
     return PHB_OK;
+}
+
+int phb_hmm_term_sums_device(phb_kernel *k, const double *x, int64_t B, const int32_t *epoch_widths, int n_epochs,
+                             double theta, const int64_t *inds, int64_t S, int64_t overlap, int want_grad, double *sums,
+                             void *stream) {
+    phb::ParamsArgs pa{};
+    if (int rc = fill_params_args(k, x, B, epoch_widths, n_epochs, theta, pa)) return rc;
+    if (S < 0) return fail(PHB_E_INVALID, "negative minibatch size");
+    if (!sums || (S > 0 && !inds)) return fail(PHB_E_INVALID, "NULL pointer");
+    if (B == 0) return PHB_OK;
+    PHB_CUDA(cudaSetDevice(k->device));
+    const int C = 7 * k->M;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc;
+    if ((rc = k->term_params.reserve(size_t(B) * C * k->elem())) != PHB_OK) return rc;
+    if ((rc = k->term_ll.reserve(size_t(B) * std::max<int64_t>(S, 1) * sizeof(double))) != PHB_OK) return rc;
+    if (want_grad && (rc = k->term_dlog.reserve(size_t(B) * std::max<int64_t>(S, 1) * C * k->elem())) != PHB_OK) return rc;
+    if (S > 0) {
+        if ((rc = phb_params_from_particles(k, x, B, epoch_widths, n_epochs, theta, k->term_params.ptr, stream)) != PHB_OK) return rc;
+        if ((rc = phb_loglik_warmup_device(k, k->term_params.ptr, inds, B, S, overlap, want_grad, static_cast<double *>(k->term_ll.ptr),
+                                           want_grad ? k->term_dlog.ptr : nullptr, stream)) != PHB_OK)
+            return rc;
+    }
+    const int threads = 128;
+    if (k->dbl)
+        phb::sum_over_chunks_kernel<double><<<unsigned(B), threads, 0, st>>>(static_cast<const double *>(k->term_ll.ptr),
+                                                                            want_grad ? static_cast<const double *>(k->term_dlog.ptr) : nullptr, S, C, sums);
+    else
+        phb::sum_over_chunks_kernel<float><<<unsigned(B), threads, 0, st>>>(static_cast<const double *>(k->term_ll.ptr),
+                                                                           want_grad ? static_cast<const float *>(k->term_dlog.ptr) : nullptr, S, C, sums);
+    PHB_CUDA(cudaGetLastError());
+    k->launches += 1;
+    return PHB_OK;
+}
+
+int phb_hmm_term_finish_device(phb_kernel *k, const double *x, int64_t B, const int32_t *epoch_widths, int n_epochs,
+                               double theta, const double *sums, double weight, double *value, double *grad_x, void *stream) {
+    phb::ParamsArgs pa{};
+    if (int rc = fill_params_args(k, x, B, epoch_widths, n_epochs, theta, pa)) return rc;
+    if (!sums || !value) return fail(PHB_E_INVALID, "NULL pointer");
+    if (B == 0) return PHB_OK;
+    PHB_CUDA(cudaSetDevice(k->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t stride = 1 + 7 * k->M;
+    const int threads = 64;
+    phb::scaled_first_column_kernel<<<unsigned((B + threads - 1) / threads), threads, 0, st>>>(sums, B, stride, weight, value);
+    PHB_CUDA(cudaGetLastError());
+    k->launches += 1;
+    if (grad_x) {
+        pa.cotangent = sums;
+        pa.cot_stride = stride;
+        pa.scale = weight;
+        pa.grad_x = grad_x;
+        const int64_t n = B * pa.P;
+        phb::psmc_params_vjp_kernel<<<unsigned((n + threads - 1) / threads), threads, 0, st>>>(pa);
+        PHB_CUDA(cudaGetLastError());
+        k->launches += 1;
+    }
+    return PHB_OK;
+}
+
+int phb_hmm_term_device(phb_kernel *k, const double *x, int64_t B, const int32_t *epoch_widths, int n_epochs, double theta,
+                        const int64_t *inds, int64_t S, int64_t overlap, double weight, double *value, double *grad_x,
+                        void *stream) {
+    if (int rc = check_handle(k)) return rc;
+    if (B < 0) return fail(PHB_E_INVALID, "negative batch");
+    if (int rc = k->term_sums.reserve(size_t(std::max<int64_t>(B, 1)) * (1 + 7 * k->M) * sizeof(double))) return rc;
+    double *sums = static_cast<double *>(k->term_sums.ptr);
+    if (int rc = phb_hmm_term_sums_device(k, x, B, epoch_widths, n_epochs, theta, inds, S, overlap, grad_x != nullptr, sums, stream))
+        return rc;
+    return phb_hmm_term_finish_device(k, x, B, epoch_widths, n_epochs, theta, sums, weight, value, grad_x, stream);
 }
 
 }  // extern "C"

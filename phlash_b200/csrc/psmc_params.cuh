@@ -229,6 +229,11 @@ struct ParamsArgs {
     const void *cotangent;  // [B, 7, M] FLOAT: d l / d log(theta) (vjp kernel)
     double *grad_x;      // [B, P] out (vjp kernel)
     int out_double;      // FLOAT is double?
+    // vjp kernel, whole-term entry: the cotangent is read as DOUBLE from per-particle sums
+    // [B, cot_stride] (cot_stride > 0; element 0 of a row is the log-likelihood sum) and the result is
+    // multiplied by `scale`
+    int64_t cot_stride;
+    double scale;
 };
 
 // one thread per particle
@@ -258,11 +263,39 @@ __global__ void psmc_params_vjp_kernel(const ParamsArgs a) {
     const int n = 7 * a.M;
     double acc = 0.0;
     for (int i = 0; i < n; ++i) {
-        const double cot = a.out_double ? static_cast<const double *>(a.cotangent)[b * n + i]
-                                        : double(static_cast<const float *>(a.cotangent)[b * n + i]);
+        double cot;
+        if (a.cot_stride > 0) cot = static_cast<const double *>(a.cotangent)[b * a.cot_stride + 1 + i];
+        else cot = a.out_double ? static_cast<const double *>(a.cotangent)[b * n + i]
+                                : double(static_cast<const float *>(a.cotangent)[b * n + i]);
         if (out[i].v != 0.0) acc += cot * out[i].d / out[i].v;
     }
-    a.grad_x[idx] = acc;
+    a.grad_x[idx] = a.cot_stride > 0 ? a.scale * acc : acc;
+}
+
+// Per-particle sums over the chunks of a minibatch (the HMM term is additive over chunks once the
+// warm-up is fused): sums[b, 0] = sum_s ll[b, s], sums[b, 1 + c] = sum_s dlog[b, s, c], c < 7 M.
+// One CTA per particle, one thread per column; coalesced over c.
+template <typename F>
+__global__ void sum_over_chunks_kernel(const double *__restrict__ ll, const F *__restrict__ dlog, int64_t S, int C,
+                                       double *__restrict__ sums) {
+    const int64_t b = blockIdx.x;
+    for (int c = threadIdx.x; c <= C; c += blockDim.x) {
+        double acc = 0.0;
+        if (c == 0) {
+            for (int64_t s = 0; s < S; ++s) acc += ll[b * S + s];
+        } else if (dlog != nullptr) {
+            const F *col = dlog + (b * S) * C + (c - 1);
+            for (int64_t s = 0; s < S; ++s) acc += double(col[s * C]);
+        }
+        sums[b * (C + 1) + c] = acc;
+    }
+}
+
+// value[b] = scale * sums[b, 0]
+__global__ void scaled_first_column_kernel(const double *__restrict__ sums, int64_t B, int64_t stride, double scale,
+                                           double *__restrict__ value) {
+    const int64_t b = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (b < B) value[b] = scale * sums[b * stride];
 }
 
 }  // namespace phb

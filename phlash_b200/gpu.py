@@ -256,6 +256,76 @@ class _PSMCKernelBase:
         )
         return out
 
+    def _term_args(self, x, pattern: str):
+        import torch
+
+        from phlash_b200.params import parse_pattern
+
+        widths = np.ascontiguousarray(parse_pattern(pattern), dtype=np.int32)
+        B, P = int(x.shape[0]), int(x.shape[1])
+        assert P == 2 + len(widths) + 1, "particle length does not match the pattern"
+        assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and x.device.index == self.device
+        return widths, B, P
+
+    def hmm_term_sums(self, x, pattern: str, theta: float, inds, overlap: int, grad: bool = True, stream=None):
+        """Per-particle sums over (this rank's part of) the minibatch: [B, 1 + 7 M] float64 =
+        (sum_s ll, sum_s d ll / d log theta), warm-up fused (include/phlash_b200.h, phb_hmm_term_sums_device).
+        x: torch float64 CUDA [B, P]; inds: torch int64 CUDA [S] (may be empty)."""
+        import torch
+
+        widths, B, _ = self._term_args(x, pattern)
+        S = int(inds.shape[0])
+        assert inds.is_cuda and inds.dtype == torch.int64 and inds.is_contiguous()
+        sums = torch.empty((B, 1 + 7 * self._M), dtype=torch.float64, device=x.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+        _check(
+            self._lib.phb_hmm_term_sums_device(
+                self._handle, x.data_ptr(), B, _ptr(widths), len(widths), float(theta), inds.data_ptr() if S else None,
+                S, int(overlap), int(grad), sums.data_ptr(), ctypes.c_void_p(stream),
+            )
+        )
+        return sums
+
+    def hmm_term_finish(self, x, pattern: str, theta: float, sums, weight: float = 1.0, grad: bool = True, stream=None):
+        """(weight * l2 [B], weight * d l2 / d x [B, P] or None) from the (all-reduced) sums."""
+        import torch
+
+        widths, B, P = self._term_args(x, pattern)
+        assert sums.shape == (B, 1 + 7 * self._M) and sums.dtype == torch.float64 and sums.is_contiguous() and sums.is_cuda
+        value = torch.empty((B,), dtype=torch.float64, device=x.device)
+        grad_x = torch.empty((B, P), dtype=torch.float64, device=x.device) if grad else None
+        if stream is None:
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+        _check(
+            self._lib.phb_hmm_term_finish_device(
+                self._handle, x.data_ptr(), B, _ptr(widths), len(widths), float(theta), sums.data_ptr(), float(weight),
+                value.data_ptr(), grad_x.data_ptr() if grad else None, ctypes.c_void_p(stream),
+            )
+        )
+        return value, grad_x
+
+    def hmm_term(self, x, pattern: str, theta: float, inds, overlap: int, weight: float = 1.0, grad: bool = True, stream=None):
+        """The whole HMM term of log_density and its gradient w.r.t. the particles in ONE library call
+        (phb_hmm_term_device): (weight * l2 [B], weight * d l2 / d x [B, P] or None)."""
+        import torch
+
+        widths, B, P = self._term_args(x, pattern)
+        S = int(inds.shape[0])
+        assert inds.is_cuda and inds.dtype == torch.int64 and inds.is_contiguous()
+        value = torch.empty((B,), dtype=torch.float64, device=x.device)
+        grad_x = torch.empty((B, P), dtype=torch.float64, device=x.device) if grad else None
+        if stream is None:
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+        _check(
+            self._lib.phb_hmm_term_device(
+                self._handle, x.data_ptr(), B, _ptr(widths), len(widths), float(theta), inds.data_ptr() if S else None,
+                S, int(overlap), float(weight), value.data_ptr(), grad_x.data_ptr() if grad else None,
+                ctypes.c_void_p(stream),
+            )
+        )
+        return value, grad_x
+
     def params_vjp(self, x, pattern: str, theta: float, cotangent, stream=None):
         """cotangent [B, 7, M] = d l / d log(theta) (kernel float type).  Returns d l / d x [B, P]."""
         import torch

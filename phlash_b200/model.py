@@ -14,7 +14,7 @@ the caller.
 
 from __future__ import annotations
 
-from phlash_b200.distributed import all_reduce_sum, pack_per_particle, shard_bounds, unpack_per_particle
+from phlash_b200.distributed import all_reduce_sum, shard_bounds
 
 
 def sample_minibatch(rng, n_chunks: int, minibatch_size: int):
@@ -28,24 +28,15 @@ def default_minibatch_size(n_chunks: int, niter: int) -> int:
 
 
 def hmm_term_value_and_grad(kern, x, pattern: str, theta: float, inds, overlap: int, weight: float = 1.0,
-                            rank: int = 0, world: int = 1):
+                            rank: int = 0, world: int = 1, grad: bool = True):
     """kern: ``gpu._PSMCKernelBase`` built on FULL chunks [N, overlap + L]; x: torch float64 CUDA
     tensor [B, P]; inds: torch int64 CUDA tensor [S] (the whole minibatch, identical on all ranks).
-    Returns (weight * l2 [B], weight * d l2 / d x [B, P]) as float64 tensors; with ``world > 1``
-    every rank scores its shard of the minibatch and one all-reduce joins the per-particle sums."""
-    import torch
-
-    B = int(x.shape[0])
-    M = kern._M
-    params7 = kern.params_from_particles(x, pattern, theta)
+    Returns (weight * l2 [B], weight * d l2 / d x [B, P]) as float64 tensors.  One library call on one
+    GPU (phb_hmm_term_device); with ``world > 1`` every rank scores its shard of the minibatch, one
+    all-reduce joins the per-particle sums [B, 1 + 7 M], and every rank finishes on the total."""
+    if world == 1:
+        return kern.hmm_term(x, pattern, theta, inds, overlap, weight, grad)
     lo, hi = shard_bounds(int(inds.shape[0]), rank, world)
-    packed = torch.zeros((B, 1 + 7 * M), dtype=torch.float64, device=x.device)
-    if hi > lo:
-        ll, dlog = kern.evaluate_warmup_device(params7, inds[lo:hi].contiguous(), overlap, True)
-        pack_per_particle(ll, dlog, out=packed)
-    if world > 1:
-        all_reduce_sum(packed)
-    l2, dlog_b = unpack_per_particle(packed, M)
-    cot = dlog_b.to(params7.dtype).contiguous()
-    grad_x = kern.params_vjp(x, pattern, theta, cot)
-    return weight * l2, weight * grad_x
+    sums = kern.hmm_term_sums(x, pattern, theta, inds[lo:hi].contiguous(), overlap, grad)
+    all_reduce_sum(sums)
+    return kern.hmm_term_finish(x, pattern, theta, sums, weight, grad)

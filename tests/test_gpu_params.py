@@ -120,3 +120,63 @@ def test_model_hmm_term(golden):
     np.testing.assert_allclose(val.cpu().numpy(), w * golden["model_l2"], rtol=1e-10)
     assert grad.shape == (3, 18) and torch.isfinite(grad).all()
     assert model.default_minibatch_size(595, 1000) == 1 and model.default_minibatch_size(59500, 1000) == 5
+
+
+@pytest.mark.parametrize("dbl", [True, False])
+def test_whole_term_entry_equals_the_composition(golden, dbl):
+    """phb_hmm_term_device = params_from_particles -> fused warm-up loglik+grad -> sum over the
+    minibatch -> params_vjp; also the split form around the all-reduce (sums / finish)."""
+    import torch
+
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    chunks, inds_np = golden["model_chunks"], golden["model_inds"]
+    kern = _PSMCKernelBase(16, chunks, double_precision=dbl)
+    dev = torch.device("cuda:0")
+    x = torch.tensor(golden["part_x"][:5], device=dev)
+    inds = torch.tensor(inds_np, device=dev)
+    w = 3.5
+    val, grad = kern.hmm_term(x, PATTERN16, 1e-2, inds, 50, weight=w)
+    # the composition, step by step
+    params7 = kern.params_from_particles(x, PATTERN16, 1e-2)
+    ll, dlog = kern.evaluate_warmup_device(params7, inds, 50, True)
+    cot = dlog.double().sum(dim=1)
+    want_val = w * ll.sum(dim=1)
+    want_grad = w * kern.params_vjp(x, PATTERN16, 1e-2, cot.to(params7.dtype).contiguous())
+    torch.testing.assert_close(val, want_val, rtol=1e-13, atol=0)
+    # (the library keeps the cotangent in double; the step-by-step path rounds it to the kernel's type)
+    torch.testing.assert_close(grad, want_grad, rtol=1e-12 if dbl else 2e-6, atol=1e-9 if dbl else 1e-4)
+    # forward only
+    val_f, none = kern.hmm_term(x, PATTERN16, 1e-2, inds, 50, weight=w, grad=False)
+    assert none is None
+    torch.testing.assert_close(val_f, val, rtol=1e-6 if not dbl else 1e-13, atol=0)
+    # split around the collective: two "ranks", one of them possibly without work
+    for cut in (0, 2, len(inds_np)):
+        sums = kern.hmm_term_sums(x, PATTERN16, 1e-2, inds[:cut].contiguous(), 50)
+        sums = sums + kern.hmm_term_sums(x, PATTERN16, 1e-2, inds[cut:].contiguous(), 50)
+        v2, g2 = kern.hmm_term_finish(x, PATTERN16, 1e-2, sums, weight=w)
+        torch.testing.assert_close(v2, val, rtol=1e-13, atol=0)
+        torch.testing.assert_close(g2, grad, rtol=1e-11, atol=1e-9)
+    empty = kern.hmm_term_sums(x, PATTERN16, 1e-2, inds[:0].contiguous(), 50)
+    assert torch.count_nonzero(empty) == 0
+
+
+def test_whole_term_gradient_by_finite_differences(golden):
+    import torch
+
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    chunks, inds_np = golden["model_chunks"], golden["model_inds"]
+    kern = _PSMCKernelBase(16, chunks, double_precision=True)
+    dev = torch.device("cuda:0")
+    x = torch.tensor(golden["part_x"][:2], device=dev)
+    inds = torch.tensor(inds_np, device=dev)
+    val, grad = kern.hmm_term(x, PATTERN16, 1e-2, inds, 50, weight=2.0)
+    h = 1e-5
+    for p in (0, 1, 5, 16, 17):
+        xp, xm = x.clone(), x.clone()
+        xp[:, p] += h
+        xm[:, p] -= h
+        fd = (kern.hmm_term(xp, PATTERN16, 1e-2, inds, 50, 2.0, grad=False)[0]
+              - kern.hmm_term(xm, PATTERN16, 1e-2, inds, 50, 2.0, grad=False)[0]) / (2 * h)
+        torch.testing.assert_close(grad[:, p], fd, rtol=2e-5, atol=1e-5)
