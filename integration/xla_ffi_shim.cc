@@ -62,3 +62,29 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(PhbWarmupLoglikGrad, WarmupLoglikGradImpl,
                                   .Arg<ffi::Buffer<ffi::S64>>()
                                   .Ret<ffi::Buffer<ffi::F64>>()
                                   .Ret<ffi::Buffer<ffi::F32>>());
+
+// the whole HMM term of log_density and its gradient w.r.t. the flattened particles x [B, P]
+// (INTEGRATION.md section 4); `widths` is the parsed pattern (util.py:8-37), one int32 per epoch
+static ffi::Error HmmTermImpl(cudaStream_t stream, int64_t handle, int64_t overlap, double theta, double weight,
+                              ffi::Span<const int32_t> widths, ffi::Buffer<ffi::F64> x, ffi::Buffer<ffi::S64> inds,
+                              ffi::ResultBuffer<ffi::F64> value, ffi::ResultBuffer<ffi::F64> grad_x) {
+    const auto xd = x.dimensions();
+    if (xd.size() != 2 || xd[1] != int64_t(widths.size()) + 3) return ffi::Error::InvalidArgument("x must be [B, 2 + n_epochs + 1]");
+    auto *k = reinterpret_cast<phb_kernel *>(handle);
+    const int rc = phb_hmm_term_device(k, x.typed_data(), xd[0], widths.begin(), int(widths.size()), theta, inds.typed_data(),
+                                       inds.dimensions()[0], overlap, weight, value->typed_data(), grad_x->typed_data(), stream);
+    return rc == PHB_OK ? ffi::Error::Success() : ffi::Error::Internal(phb_last_error());
+}
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(PhbHmmTerm, HmmTermImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Attr<int64_t>("handle")
+                                  .Attr<int64_t>("overlap")
+                                  .Attr<double>("theta")
+                                  .Attr<double>("weight")
+                                  .Attr<ffi::Span<const int32_t>>("widths")
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::S64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>());
