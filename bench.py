@@ -179,6 +179,38 @@ def likelihood_step(local_rank, chunks_full, rank, world):
     return out
 
 
+def elpd_step(local_rank):
+    """The reference's ELPD evaluation (mcmc.py:213-238): forward-only HMM term of all particles over one
+    un-chunked held-out contig (2.5 M bins = a 250 Mb chromosome at 100 bp), through the one-call entry;
+    with the parallel-in-time path (automatic) and with the sequential kernel."""
+    import torch
+
+    from benchdata import synth
+    from phlash_b200 import model
+
+    dev = torch.device("cuda", local_rank)
+    n_bins = 2_500_000
+    tk = model.elpd_kernel(M, synth.het_matrix(1, n_bins, seed=101), device=local_rank)
+    xs = np.load(os.path.join(ROOT, "benchdata", f"particles_M{M}.npz"))["xs"][:N_PARTICLES]
+    x = torch.tensor(xs, dtype=torch.float64, device=dev)
+    out = {"particles": N_PARTICLES, "test_contigs": 1, "bins": n_bins}
+    for name, mode in (("ms", -1), ("ms_sequential_kernel", 0)):
+        tk.set_parallel_in_time(mode)
+        for _ in range(2):
+            e = model.elpd_hmm_term(tk, x, "14*1+1*2", 1e-2)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            e = model.elpd_hmm_term(tk, x, "14*1+1*2", 1e-2)
+        e1.record()
+        e1.synchronize()
+        out[name] = e0.elapsed_time(e1) / 3
+        out["kernel" if mode < 0 else "kernel_sequential"] = tk.last_kernel_name
+        assert bool(torch.isfinite(e))
+    return out
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
@@ -345,6 +377,10 @@ def main():
         if lik_step is not None:
             line["likelihood_step"] = lik_step
         if not args.skip_baselines and world == 1:
+            try:
+                line["elpd_step"] = elpd_step(local_rank)
+            except Exception as e:  # an extra, never allowed to take the benchmark down
+                line["elpd_step"] = {"unavailable": repr(e)[:200]}
             try:
                 sys.path.insert(0, os.path.join(ROOT, "tools"))
                 import svgd_demo

@@ -97,6 +97,16 @@ int phb_set_threads_per_pair(phb_kernel *k, int threads_per_pair);
  * threads_per_pair is forced). */
 int phb_set_store_all(phb_kernel *k, int mode);
 
+/* Forward-only evaluations of FEW, LONG pairs (the reference's ELPD: whole un-chunked test contigs for
+ * every particle, mcmc.py:213-238) cannot fill the GPU with one recursion per pair and last L x the
+ * latency of one site step.  They are evaluated parallel in time instead: the sequence is cut into
+ * segments, the M unit vectors are propagated through every segment (its transfer operator: M x the
+ * arithmetic, M x segments x the parallelism) and the operators are chained in float64.  Exact - no
+ * burn-in approximation.  mode: -1 = automatic (float objects, M <= 16, forward-only, pairs * M below
+ * a quarter of the resident threads, segments >= 4096 sites), 0 = never, 1 = whenever possible
+ * (ignored while threads_per_pair is forced). */
+int phb_set_parallel_in_time(phb_kernel *k, int mode);
+
 /* PRECISION ESCALATION (single-precision objects, gradient path).  Through a long run of identical
  * observations (masked centromere, the -1 padding of a contig's last chunk, a run of homozygosity)
  * fp32 forward / adjoint vectors stagnate at a floating-point fixed point and the transition rows of

@@ -30,6 +30,7 @@ SIGNATURES = {
     "phb_device": (_i, [_vp]),
     "phb_set_threads_per_pair": (_i, [_vp, _i]),
     "phb_set_store_all": (_i, [_vp, _i]),
+    "phb_set_parallel_in_time": (_i, [_vp, _i]),
     "phb_set_precision_escalation": (_i, [_vp, _i]),
     "phb_num_escalated_rows": (_i64, [_vp]),
     "phb_loglik_host": (_i, [_vp, _vp, _vp, _i64, _i64, _i, _vp, _vp]),

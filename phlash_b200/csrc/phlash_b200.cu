@@ -93,6 +93,8 @@ struct phb_kernel {
     std::unordered_map<const void *, int> occupancy;  // per kernel function: attribute set, CTAs per SM
     DeviceBuffer params, inds, ll, dlog, ckpt, gacc, xall, sall, split;
     DeviceBuffer term_params, term_ll, term_dlog, term_sums;  // scratch of the whole-term entries
+    DeviceBuffer transfer_rows, transfer_log;                 // parallel-in-time forward evaluation
+    int parallel_in_time = -1;  // -1 auto, 0 never, 1 whenever possible
     int store_all_mode = -1;  // -1 auto, 0 never, 1 whenever a store-all variant exists
     // precision escalation (float objects): rows holding a long run of identical observations are
     // scored with double arithmetic, see flag_long_runs_kernel
@@ -218,6 +220,24 @@ const std::vector<StoreAllVariant> &storeall_variants() {
     return table;
 }
 
+// Parallel-in-time forward evaluation (few, long pairs; see transfer_rows_kernel): float, M <= 16.
+struct TransferVariant {
+    int M;
+    const void *rows_func, *chain_func;
+    size_t smem;
+};
+template <int M> TransferVariant make_transfer() {
+    return TransferVariant{M, reinterpret_cast<const void *>(&phb::transfer_rows_kernel<float, M, 128>),
+                           reinterpret_cast<const void *>(&phb::chain_transfer_kernel<float, M>),
+                           phb::smem_bytes<float, M, 8, 128, false>()};
+}
+const TransferVariant *transfer_variant(int M) {
+    static const std::vector<TransferVariant> table = {make_transfer<4>(), make_transfer<8>(), make_transfer<16>()};
+    for (const TransferVariant &v : table)
+        if (v.M == M) return &v;
+    return nullptr;
+}
+
 const Variant *pick_variant(const phb_kernel *k, bool grad, int64_t n_pairs) {
     const Variant *last = nullptr, *forced = nullptr, *first_fill = nullptr;
     // Lane layouts are ordered by increasing T (fewer lanes per pair = fewer instructions per pair).
@@ -294,6 +314,48 @@ int launch_one(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream,
             k->launches += 1;
             snprintf(k->last_name, sizeof k->last_name, "psmc_loglik_storeall_kernel<float,MT=%d,T=%d,NT=%d>", sv.MT, sv.T, sv.NT);
             return PHB_OK;
+        }
+    }
+    // Forward-only, few long pairs: segment transfer operators chained afterwards.  The sequential
+    // kernel needs ~80 ns per site whatever the number of pairs (measured, profiles/r01_elpd_shape_probe.log);
+    // M times the work at full throughput is faster while pairs * M is below a quarter of the
+    // resident threads.  PHB_PARALLEL_IN_TIME=0/1 overrides the mode set through the API.
+    const char *pit_env = getenv("PHB_PARALLEL_IN_TIME");
+    const int pit_mode = pit_env ? atoi(pit_env) : k->parallel_in_time;
+    if (!fixed && !grad && !k->dbl && pit_mode != 0 && k->force_T == 0 && a.s_list == nullptr) {
+        if (const TransferVariant *tv = transfer_variant(k->M)) {
+            const int64_t capacity = int64_t(k->num_sms) * 384;  // resident threads of the row kernel
+            const int64_t min_seg = pit_mode == 1 ? 64 : 4096;   // sites; shorter segments are all overhead
+            int64_t n_seg = std::min(capacity / (n_pairs * tv->M), a.L / min_seg);
+            if (pit_mode == 1) n_seg = std::max<int64_t>(n_seg, std::min<int64_t>(3, a.L / min_seg));
+            // (measured at M = 16, L = 2.5 M: 500 pairs -> 7 segments 91 ms vs 209 ms sequential; 1000 pairs ->
+            // 3 segments 213 ms, no gain any more; profiles/r01_elpd_shape_probe.log)
+            if (n_seg >= (pit_mode == 1 ? 3 : 4)) {
+                int64_t seg_len = ((a.L + n_seg - 1) / n_seg + 15) / 16 * 16;
+                n_seg = (a.L + seg_len - 1) / seg_len;
+                const int64_t n_virtual = n_pairs * n_seg * tv->M;
+                int rc;
+                if ((rc = k->transfer_rows.reserve(size_t(n_virtual) * tv->M * sizeof(float))) != PHB_OK) return rc;
+                if ((rc = k->transfer_log.reserve(size_t(n_virtual) * sizeof(double))) != PHB_OK) return rc;
+                phb::TransferArgs ta{};
+                ta.k = a;
+                ta.k.err_flag = k->d_err;
+                ta.n_seg = n_seg;
+                ta.seg_len = seg_len;
+                ta.rows = static_cast<float *>(k->transfer_rows.ptr);
+                ta.row_log2 = static_cast<double *>(k->transfer_log.ptr);
+                if (k->occupancy.find(tv->rows_func) == k->occupancy.end()) {
+                    PHB_CUDA(cudaFuncSetAttribute(tv->rows_func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tv->smem)));
+                    k->occupancy.emplace(tv->rows_func, 1);
+                }
+                void *kargs[] = {&ta};
+                PHB_CUDA(cudaLaunchKernel(tv->rows_func, dim3(unsigned((n_virtual + 127) / 128)), dim3(128), kargs, tv->smem, stream));
+                PHB_CUDA(cudaLaunchKernel(tv->chain_func, dim3(unsigned((n_pairs + 63) / 64)), dim3(64), kargs, 0, stream));
+                k->launches += 2;
+                snprintf(k->last_name, sizeof k->last_name, "transfer_rows_kernel<float,M=%d> x %lld segments + chain_transfer_kernel",
+                         tv->M, (long long)n_seg);
+                return PHB_OK;
+            }
         }
     }
     const Variant *v = fixed ? fixed : pick_variant(k, grad, n_pairs);
@@ -575,6 +637,8 @@ void phb_destroy(phb_kernel *k) {
     k->term_ll.release();
     k->term_dlog.release();
     k->term_sums.release();
+    k->transfer_rows.release();
+    k->transfer_log.release();
     if (k->d_rowflag) cudaFree(k->d_rowflag);
     if (k->d_data) cudaFree(k->d_data);
     if (k->d_err) cudaFree(k->d_err);
@@ -613,6 +677,13 @@ int phb_set_precision_escalation(phb_kernel *k, int enabled) {
 }
 
 int64_t phb_num_escalated_rows(const phb_kernel *k) { return k ? k->n_flagged : 0; }
+
+int phb_set_parallel_in_time(phb_kernel *k, int mode) {
+    if (int rc = check_handle(k)) return rc;
+    if (mode < -1 || mode > 1) return fail(PHB_E_INVALID, "parallel-in-time mode must be -1 (auto), 0 (off) or 1 (on)");
+    k->parallel_in_time = mode;
+    return PHB_OK;
+}
 
 int phb_set_threads_per_pair(phb_kernel *k, int threads_per_pair) {
     if (int rc = check_handle(k)) return rc;

@@ -996,6 +996,143 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_storeall_kernel(cons
 }
 
 // ---------------------------------------------------------------------------------------------
+// Parallel-in-time FORWARD evaluation of FEW, LONG pairs: the reference's ELPD (mcmc.py:213-238) scores
+// whole un-chunked test contigs (millions of bins) for every particle every 10th iteration - a few
+// hundred pairs, which cannot fill the GPU, so the launch lasts L x (latency of one dependent site
+// step), ~80 ns per site whatever the lane layout.  The recursion is linear in the forward vector:
+// cut the sequence into G segments and propagate, for every segment, the M unit vectors instead of
+// the (unknown) incoming vector.  That yields the segment's transfer operator
+//     T_g[i, :] = e_i A diag(emis(ob_t)) ... (all sites of the segment),
+// M x more arithmetic, but M x G x as many independent recursions - enough to fill the machine - and
+// the G operators are chained afterwards in float64:  alpha_{g+1} = alpha_g T_g  (M^2 per segment).
+// Exact (no mixing / burn-in approximation); every row of T_g is an ordinary scaled forward
+// recursion, so the accuracy is that of the sequential kernel.
+//
+// transfer_rows_kernel: one thread per (pair, segment, unit vector) - the M rows of one operator are
+// adjacent lanes, so they read the same observations and parameters - running the same site step
+// as psmc_loglik_kernel (T = 1: thread-private state, no shuffles).  Output per row: the final
+// vector rescaled to sum 1 and the log2 of the total scale.
+struct TransferArgs {
+    KernelArgs k;          // data, inds, B, S, params / pi layout, ll, err_flag, out_mode of the evaluation
+    int64_t n_seg;         // G
+    int64_t seg_len;       // sites per segment (multiple of 16; the last segment takes the rest)
+    float *rows;           // [pair][segment][M rows][M]
+    double *row_log2;      // [pair][segment][M rows]
+};
+
+template <typename F, int M, int NT> __global__ void __maxnreg__(max_regs(NT, 3)) transfer_rows_kernel(const TransferArgs ta) {
+    constexpr int MT = M, T = 1, K = 8;
+    const KernelArgs &a = ta.k;
+    const uint32_t smem0 = smem_base_addr();
+    EmisTable<F, MT, NT> et;
+    et.ones = smem0;
+    et.base = smem0 + ((EmisTable<F, MT, NT>::kOnesRow ? 0 : 1) + threadIdx.x) * 16;
+    if constexpr (!EmisTable<F, MT, NT>::kOnesRow) {
+        if (threadIdx.x == 0) {
+            F one[Vec<F>::W];
+#pragma unroll
+            for (int i = 0; i < Vec<F>::W; ++i) one[i] = F(1);
+            sts_word(smem0, one);
+        }
+        __syncthreads();
+    }
+    const int64_t n_virtual = a.B * a.S * ta.n_seg * M;
+    const int64_t vraw = int64_t(blockIdx.x) * NT + threadIdx.x;
+    const bool writer = vraw < n_virtual;
+    const int64_t v = writer ? vraw : n_virtual - 1;
+    const int unit = int(v % M);
+    const int64_t seg = (v / M) % ta.n_seg;
+    const int64_t pair = v / (M * ta.n_seg);
+    const int64_t pb = pair / a.S, ps = pair % a.S;
+    const F *par = static_cast<const F *>(a.params6) + pb * a.pstride_b + ps * a.pstride_s;
+    Params<F, MT> p;
+    p.load(par, M);
+    et.fill(par, M);
+    PartnerCoef<F, MT, T, false> pc;
+    int64_t row = a.inds[ps];
+    if (row < 0 || row >= a.n_rows) row = 0;  // reported (and the result made NaN) by chain_transfer_kernel
+    const int64_t site0 = seg * ta.seg_len;
+    const int64_t len = min(ta.seg_len, a.L - site0);
+    const int8_t *obs = a.data + row * a.pitch + site0;
+
+    F x[MT];
+#pragma unroll
+    for (int k = 0; k < MT; ++k) x[k] = k == unit ? F(1) : F(0);
+    double log2_scale = 0.0;
+    const int64_t n_blk = (len + K - 1) / K;
+    ObsWords<K> ow_next;
+    ow_next.load(obs, 0);
+    for (int64_t blk = 0; blk < n_blk; ++blk) {
+        const ObsWords<K> ow = ow_next;
+        if (blk + 1 < n_blk) ow_next.load(obs, (blk + 1) * K);
+        const int n = int(min(int64_t(K), len - blk * K));
+        F acc = F(0);
+        for (int kb = 0; kb < n; kb += kNorm) {
+            const uint64_t word = ow.block(kb);
+#pragma unroll
+            for (int j = 0; j < kNorm; ++j)
+                if (kb + j < n) forward_site<F, MT, T, false, NT>(x, p, pc, et, ObsWords<K>::byte_of(word, j), 0);
+            const F tot = pair_sum<F, MT, T>(x);
+            const F inv = fast_rcp<F>(tot);
+#pragma unroll
+            for (int j = 0; j < MT; ++j) x[j] *= inv;
+            acc += log2_of<F>(tot);
+        }
+        log2_scale += double(acc);
+    }
+    if (writer) {
+        // exact normalisation of what is handed on (the reciprocal above is approximate)
+        const F tot = pair_sum<F, MT, T>(x);
+        float *out = ta.rows + v * M;
+#pragma unroll
+        for (int k = 0; k < MT; ++k) out[k] = float(x[k] / tot);
+        ta.row_log2[v] = log2_scale + double(log2_of<F>(tot));
+    }
+}
+
+// chain_transfer_kernel: one thread per pair;  alpha <- alpha T_g  in float64, g = 0 .. G-1, with a common
+// scale per segment taken from the largest contributing row.
+template <typename F, int M> __global__ void chain_transfer_kernel(const TransferArgs ta) {
+    const KernelArgs &a = ta.k;
+    const int64_t pair = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (pair >= a.B * a.S) return;
+    const int64_t pb = pair / a.S, ps = pair % a.S;
+    const F *pi_p = static_cast<const F *>(a.pi) + pb * a.pistride_b + ps * a.pistride_s;
+    double alpha[M];
+    double tot = 0.0;
+    for (int k = 0; k < M; ++k) tot += (alpha[k] = double(pi_p[k]));
+    double ll2 = log2(tot);  // log2 of everything divided out so far
+    for (int k = 0; k < M; ++k) alpha[k] /= tot;
+    for (int64_t g = 0; g < ta.n_seg; ++g) {
+        const float *rows = ta.rows + (pair * ta.n_seg + g) * M * M;
+        const double *lg = ta.row_log2 + (pair * ta.n_seg + g) * M;
+        double top = -1e300;
+        for (int i = 0; i < M; ++i)
+            if (alpha[i] > 0.0 && lg[i] > top) top = lg[i];
+        double next[M];
+        for (int k = 0; k < M; ++k) next[k] = 0.0;
+        for (int i = 0; i < M; ++i) {
+            if (!(alpha[i] > 0.0)) continue;
+            const double w = alpha[i] * exp2(lg[i] - top);
+            for (int k = 0; k < M; ++k) next[k] += w * double(rows[i * M + k]);
+        }
+        tot = 0.0;
+        for (int k = 0; k < M; ++k) tot += next[k];
+        ll2 += top + log2(tot);
+        for (int k = 0; k < M; ++k) alpha[k] = next[k] / tot;
+    }
+    double ll = ll2 * 0.69314718055994530942;
+    const int64_t row = a.inds[ps];
+    if (row < 0 || row >= a.n_rows) {
+        atomicOr(a.err_flag, 1);
+        ll = __longlong_as_double(0x7ff8000000000000LL);
+    } else if (!(ll == ll) || ll > 1e300 || ll < -1e300) {
+        atomicOr(a.err_flag, 2);
+    }
+    a.ll[pair] = a.out_mode ? a.ll[pair] - ll : ll;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Precision escalation for single-precision kernel objects.
 //
 // Through a long run of IDENTICAL observations (a masked centromere, the -1 padding of a contig's

@@ -118,6 +118,11 @@ class _PSMCKernelBase:
         """-1 auto, 0 never, 1 always: the store-all gradient kernel for small minibatches."""
         _check(self._lib.phb_set_store_all(self._handle, int(mode)))
 
+    def set_parallel_in_time(self, mode: int) -> None:
+        """-1 auto, 0 never, 1 whenever possible: forward-only evaluation of few, long pairs through
+        segment transfer operators (include/phlash_b200.h)."""
+        _check(self._lib.phb_set_parallel_in_time(self._handle, int(mode)))
+
     def set_precision_escalation(self, enabled: bool) -> None:
         """Rows with a long run of identical observations are scored with double arithmetic (default
         on for single-precision objects; see include/phlash_b200.h)."""

@@ -40,3 +40,26 @@ def hmm_term_value_and_grad(kern, x, pattern: str, theta: float, inds, overlap: 
     sums = kern.hmm_term_sums(x, pattern, theta, inds[lo:hi].contiguous(), overlap, grad)
     all_reduce_sum(sums)
     return kern.hmm_term_finish(x, pattern, theta, sums, weight, grad)
+
+
+def elpd_kernel(M: int, test_het, double_precision: bool = False, device: int = 0):
+    """Kernel object for the reference's ELPD evaluation (mcmc.py:213-236): the un-chunked test contigs
+    [N_test, L] with ONE missing warm-up bin in front of every row (`warmup = full([N_test, 1], -1)`)."""
+    import numpy as np
+
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    het = np.asarray(test_het)
+    full = np.concatenate([np.full((het.shape[0], 1), -1, dtype=np.int8), np.clip(het, -1, 1).astype(np.int8)], axis=1)
+    return _PSMCKernelBase(M, full, double_precision=double_precision, device=device)
+
+
+def elpd_hmm_term(test_kern, x, pattern: str, theta: float):
+    """HMM part of the expected log-predictive density: mean over particles of log_density with
+    c = (0, 1, 1) over all test contigs (mcmc.py:221-236; the AFS part stays with the caller).
+    Forward only: no gradient is formed."""
+    import torch
+
+    inds = torch.arange(test_kern._N, dtype=torch.int64, device=x.device)
+    value, _ = test_kern.hmm_term(x, pattern, theta, inds, 1, 1.0, grad=False)
+    return value.mean()

@@ -29,6 +29,20 @@ def test_elpd_path_long_unchunked_contig():
     ll_w = kern_w.gpu_kernels[0].evaluate_warmup(pps, inds, 1, False)
     want = np.array([[orc.hmm_term(p, full[i : i + 1, :1], full[i : i + 1, 1:]) for i in range(2)] for p in pps[:2]])
     np.testing.assert_allclose(ll_w[:2], want, rtol=1e-5)
+    # ... and the same through the one-call entry from the particles themselves
+    import torch
+
+    from phlash_b200 import model
+
+    pps_x, xs, pattern = orc.synth_particles(16, 4, seed=5)
+    x = torch.tensor(xs, device="cuda:0")
+    tk = model.elpd_kernel(16, het)
+    np.testing.assert_array_equal(tk.download_data(), full)
+    got = float(model.elpd_hmm_term(tk, x, pattern, 1e-2))
+    # (theta of the synthetic particles is 1e-2, orc.synth_particles)
+    want_e = np.mean([sum(orc.hmm_term(p.astype(np.float32).astype(np.float64), full[i : i + 1, :1], full[i : i + 1, 1:])
+                          for i in range(2)) for p in pps_x])
+    np.testing.assert_allclose(got, want_e, rtol=1e-5)
 
 
 def test_two_devices_in_one_process(golden):

@@ -1,0 +1,111 @@
+"""Parallel-in-time forward evaluation (segment transfer operators chained in float64; the path of
+the reference's ELPD, mcmc.py:213-238) against the fp64 oracle and the sequential kernel."""
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle, psmc_oracle as orc
+from test_gpu_parity import LL_RTOL
+
+pytestmark = pytest.mark.gpu
+
+
+def rows_with_missing(n, L, seed):
+    rng = np.random.default_rng(seed)
+    data = (rng.random((n, L)) < 0.07).astype(np.int8)
+    data[rng.random((n, L)) < 0.02] = -1
+    data[:, 0] = np.where(data[:, 0] < 0, 0, data[:, 0])
+    data[0, 10:90] = -1  # a run of missing observations across a block boundary
+    data[-1, L - 37 :] = -1  # missing tail
+    return data
+
+
+@pytest.mark.parametrize("M", [4, 8, 16])
+@pytest.mark.parametrize("L", [200, 1003, 20_000])
+def test_transfer_operators_match_oracle_and_sequential_kernel(M, L):
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    data = rows_with_missing(3, L, seed=M + L)
+    pps, _, _ = orc.synth_particles(M, 5, seed=3)
+    pps = pps.astype(np.float32).astype(np.float64)
+    inds = np.array([2, 0, 1, 2])
+    pa = np.broadcast_to(pps[:, None], (5, len(inds), 7, M)).copy()
+    want = c_oracle.loglik_batch(data, np.tile(inds, 5), pa.reshape(-1, 7, M)).reshape(5, len(inds))
+    kern = _PSMCKernelBase(M, data)
+    kern.set_parallel_in_time(1)
+    ll_pit = kern.evaluate(pa, inds, False)
+    assert "transfer" in kern.last_kernel_name
+    kern.set_parallel_in_time(0)
+    ll_seq = kern.evaluate(pa, inds, False)
+    assert "transfer" not in kern.last_kernel_name
+    np.testing.assert_allclose(ll_pit, want, rtol=LL_RTOL)
+    np.testing.assert_allclose(ll_pit, ll_seq, rtol=2e-6)
+
+
+def test_dispatch_rules():
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    data = rows_with_missing(2, 40_000, seed=1)
+    pps, _, _ = orc.synth_particles(16, 4, seed=0)
+    kern = _PSMCKernelBase(16, data)
+    pa = np.broadcast_to(pps[:, None], (4, 2, 7, 16)).copy()
+    kern.evaluate(pa, np.arange(2), False)
+    assert "transfer" in kern.last_kernel_name            # 8 pairs x 40 000 sites
+    kern.evaluate(pa, np.arange(2), True)
+    assert "transfer" not in kern.last_kernel_name        # gradient path
+    kern.set_threads_per_pair(2)
+    kern.evaluate(pa, np.arange(2), False)
+    assert "transfer" not in kern.last_kernel_name        # a forced lane layout wins
+    kern.set_threads_per_pair(0)
+    big = np.broadcast_to(pps[:1, None], (1, 3000, 7, 16)).copy()
+    kern.evaluate(big, np.zeros(3000, dtype=np.int64), False)
+    assert "transfer" not in kern.last_kernel_name        # 3000 pairs: the sequential kernel is as fast
+    short = _PSMCKernelBase(16, data[:, :5000].copy())
+    short.evaluate(pa, np.arange(2), False)
+    assert "transfer" not in short.last_kernel_name       # segments would be shorter than 4096 sites
+    dbl = _PSMCKernelBase(16, data, double_precision=True)
+    dbl.evaluate(pa, np.arange(2), False)
+    assert "transfer" not in dbl.last_kernel_name
+
+
+def test_elpd_shape_through_the_one_call_entry():
+    """B particles x one un-chunked contig behind one missing bin (mcmc.py:229-233): the evaluation of
+    all bins goes through the transfer operators, the subtraction of the warm-up bin through the
+    sequential kernel; compared with the same call with the parallel-in-time path switched off."""
+    import torch
+
+    from benchdata import synth
+    from phlash_b200 import model
+
+    het = synth.het_matrix(1, 400_003, seed=4)
+    _, xs, pattern = orc.synth_particles(16, 8, seed=2)
+    x = torch.tensor(xs, device="cuda:0")
+    tk = model.elpd_kernel(16, het)
+    inds = torch.arange(1, device="cuda:0")
+    v_pit, _ = tk.hmm_term(x, pattern, 1e-2, inds, 1, 1.0, grad=False)
+    tk.set_parallel_in_time(0)
+    v_seq, _ = tk.hmm_term(x, pattern, 1e-2, inds, 1, 1.0, grad=False)
+    torch.testing.assert_close(v_pit, v_seq, rtol=2e-6, atol=0)
+    pps = orc.synth_particles(16, 8, seed=2)[0].astype(np.float32).astype(np.float64)
+    full = tk.download_data()
+    want = np.array([orc.hmm_term(p, full[:, :1], full[:, 1:]) for p in pps[:3]])
+    np.testing.assert_allclose(v_pit.cpu().numpy()[:3], want, rtol=LL_RTOL)
+
+
+def test_bad_index_is_reported():
+    import torch
+
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    data = rows_with_missing(2, 40_000, seed=1)
+    pps, _, _ = orc.synth_particles(16, 2, seed=0)
+    kern = _PSMCKernelBase(16, data)
+    dev = torch.device("cuda:0")
+    p6 = torch.tensor(pps[:, :6], dtype=torch.float32, device=dev).contiguous()
+    pi = torch.tensor(pps[:, 6], dtype=torch.float32, device=dev).contiguous()
+    ll, _ = kern.evaluate_device(p6, pi, torch.tensor([0, 2, 1], device=dev), False)
+    assert "transfer" in kern.last_kernel_name
+    with pytest.raises(AssertionError):
+        kern.sync()
+    ll = ll.cpu().numpy()
+    assert np.isnan(ll[:, 1]).all() and np.isfinite(ll[:, [0, 2]]).all()
