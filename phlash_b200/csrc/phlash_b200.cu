@@ -89,11 +89,12 @@ struct phb_kernel {
     int force_T = 0;
     int num_sms = 0;
     int64_t launches = 0;
-    char last_name[96] = "";
+    char last_name[128] = "";
     std::unordered_map<const void *, int> occupancy;  // per kernel function: attribute set, CTAs per SM
     DeviceBuffer params, inds, ll, dlog, ckpt, gacc, xall, sall, split;
     DeviceBuffer term_params, term_ll, term_dlog, term_sums;  // scratch of the whole-term entries
     DeviceBuffer transfer_rows, transfer_log;                 // parallel-in-time forward evaluation
+    DeviceBuffer bnd_alpha, bnd_beta, seg_dlog;               // ... and gradient
     int parallel_in_time = -1;  // -1 auto, 0 never, 1 whenever possible
     int store_all_mode = -1;  // -1 auto, 0 never, 1 whenever a store-all variant exists
     // precision escalation (float objects): rows holding a long run of identical observations are
@@ -196,6 +197,7 @@ const Variant *escalation_variant(int M) {
 struct StoreAllVariant {
     int M, T, MT, NT;
     const void *func;
+    const void *seg_func;  // segment mode (parallel-in-time gradient)
     size_t smem;
 };
 template <int MT, int T, int NT, int MINB> StoreAllVariant make_storeall() {
@@ -205,6 +207,7 @@ template <int MT, int T, int NT, int MINB> StoreAllVariant make_storeall() {
     v.MT = MT;
     v.NT = NT;
     v.func = reinterpret_cast<const void *>(&phb::psmc_loglik_storeall_kernel<float, MT, T, NT, MINB>);
+    v.seg_func = reinterpret_cast<const void *>(&phb::psmc_loglik_storeall_kernel<float, MT, T, NT, MINB, true>);
     v.smem = phb::smem_bytes<float, MT, 8, NT, false>();
     return v;
 }
@@ -223,12 +226,13 @@ const std::vector<StoreAllVariant> &storeall_variants() {
 // Parallel-in-time forward evaluation (few, long pairs; see transfer_rows_kernel): float, M <= 16.
 struct TransferVariant {
     int M;
-    const void *rows_func, *chain_func;
+    const void *rows_func, *chain_func, *boundaries_func;
     size_t smem;
 };
 template <int M> TransferVariant make_transfer() {
     return TransferVariant{M, reinterpret_cast<const void *>(&phb::transfer_rows_kernel<float, M, 128>),
                            reinterpret_cast<const void *>(&phb::chain_transfer_kernel<float, M>),
+                           reinterpret_cast<const void *>(&phb::chain_boundaries_kernel<float, M>),
                            phb::smem_bytes<float, M, 8, 128, false>()};
 }
 const TransferVariant *transfer_variant(int M) {
@@ -277,6 +281,101 @@ int launch_one(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream,
     // tuning knob for experiments: PHB_STORE_ALL=0/1 overrides the mode set through the API
     const char *sa_env = getenv("PHB_STORE_ALL");
     const int sa_mode = sa_env ? atoi(sa_env) : k->store_all_mode;
+    const char *pit_env = getenv("PHB_PARALLEL_IN_TIME");
+    const int pit_mode = pit_env ? atoi(pit_env) : k->parallel_in_time;
+    // Gradient of FEW pairs (the reference's default minibatch for one genome is a single chunk: 500
+    // pairs): parallel in time.  Segment transfer operators give the forward / adjoint vectors at the
+    // segment boundaries (chain_boundaries_kernel), after which the segments are independent short
+    // chunks for the store-all kernel.  Worth it while the operators (M x the forward work, at full
+    // throughput) cost less than the dependent site steps they remove: pairs * M below 0.3 of the
+    // resident threads (measured, profiles/r01_probe_parallel_in_time.log: B = 500, L = 50 000, S = 1 / 2 / 3
+    // chunks 5.3 / 9.5 / 13.6 ms against 13.6 ms sequential).
+    if (!fixed && grad && !k->dbl && pit_mode != 0 && sa_mode != 0 && k->force_T == 0 && a.s_list == nullptr) {
+        const TransferVariant *tv = transfer_variant(k->M);
+        const StoreAllVariant *sv = nullptr;
+        for (const StoreAllVariant &c : storeall_variants())
+            if (c.M == k->M) sv = &c;
+        const int64_t capacity = int64_t(k->num_sms) * 384;
+        const int64_t min_seg = pit_mode == 1 ? 64 : 1024;
+        int64_t n_seg = tv && sv ? std::min(4 * capacity / (n_pairs * tv->M), a.L / min_seg) : 0;
+        if (pit_mode == 1) n_seg = std::max<int64_t>(n_seg, std::min<int64_t>(3, a.L / min_seg));
+        if (const char *g_env = getenv("PHB_PIT_SEGMENTS")) n_seg = std::min<int64_t>(atoi(g_env), a.L / 64);  // experiments
+        const bool worth = pit_mode == 1 || n_pairs * k->M * 10 <= capacity * 3;
+        if (tv && sv && worth && n_seg >= 3) {
+            const int64_t seg_len = ((a.L + n_seg - 1) / n_seg + 15) / 16 * 16;
+            n_seg = (a.L + seg_len - 1) / seg_len;
+            const int M = k->M;
+            const int64_t n_rows_virtual = n_pairs * n_seg * M;
+            // store-all passes: one launch, every CTA inside one segment (uniform loop bounds per CTA)
+            const int pairs_per_cta = sv->NT / sv->T;
+            const int64_t seg_ctas = (n_pairs + pairs_per_cta - 1) / pairs_per_cta;
+            const int64_t grid_full = seg_ctas * n_seg;
+            const int64_t warps = grid_full * (sv->NT / 32);
+            const size_t x_bytes = size_t(warps) * size_t(seg_len) * sv->MT * 32 * sizeof(float);
+            const size_t s_bytes = size_t(warps) * size_t((seg_len + phb::kNorm - 1) / phb::kNorm) * 32 * sizeof(float);
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            if (x_bytes + s_bytes <= (free_b + k->xall.cap + k->sall.cap) / 2) {
+                int rc;
+                if ((rc = k->transfer_rows.reserve(size_t(n_rows_virtual) * M * sizeof(float))) != PHB_OK) return rc;
+                if ((rc = k->transfer_log.reserve(size_t(n_rows_virtual) * sizeof(double))) != PHB_OK) return rc;
+                if ((rc = k->bnd_alpha.reserve(size_t(n_pairs) * (n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
+                if ((rc = k->bnd_beta.reserve(size_t(n_pairs) * (n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
+                if ((rc = k->seg_dlog.reserve(size_t(n_pairs) * n_seg * 7 * M * sizeof(float))) != PHB_OK) return rc;
+                if ((rc = k->xall.reserve(x_bytes)) != PHB_OK) return rc;
+                if ((rc = k->sall.reserve(s_bytes)) != PHB_OK) return rc;
+                if ((rc = k->gacc.reserve(size_t(grid_full) * sv->NT * 6 * sv->MT * sizeof(double))) != PHB_OK) return rc;
+                for (const void *f : {tv->rows_func, sv->seg_func}) {
+                    if (k->occupancy.find(f) == k->occupancy.end()) {
+                        PHB_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, int(f == tv->rows_func ? tv->smem : sv->smem)));
+                        k->occupancy.emplace(f, 1);
+                    }
+                }
+                phb::TransferArgs ta{};
+                ta.k = a;
+                ta.k.err_flag = k->d_err;
+                ta.n_seg = n_seg;
+                ta.seg_len = seg_len;
+                ta.rows = static_cast<float *>(k->transfer_rows.ptr);
+                ta.row_log2 = static_cast<double *>(k->transfer_log.ptr);
+                void *bnd_a = k->bnd_alpha.ptr, *bnd_b = k->bnd_beta.ptr;
+                {
+                    void *kargs[] = {&ta};
+                    PHB_CUDA(cudaLaunchKernel(tv->rows_func, dim3(unsigned((n_rows_virtual + 127) / 128)), dim3(128), kargs, tv->smem, stream));
+                    void *bargs[] = {&ta, &bnd_a, &bnd_b};
+                    PHB_CUDA(cudaLaunchKernel(tv->boundaries_func, dim3(unsigned((n_pairs * M + 127) / 128)), dim3(128), bargs, 0, stream));
+                }
+                phb::KernelArgs sa = a;
+                sa.err_flag = k->d_err;
+                sa.xall = k->xall.ptr;
+                sa.sall = k->sall.ptr;
+                sa.gacc = static_cast<double *>(k->gacc.ptr);
+                sa.seg_count = n_seg;
+                sa.seg_len = seg_len;
+                sa.bnd_alpha = bnd_a;
+                sa.bnd_beta = bnd_b;
+                sa.seg_dlog = k->seg_dlog.ptr;
+                sa.seg_ctas = seg_ctas;
+                sa.n_groups = grid_full;
+                int n_launch = 3;
+                {
+                    void *kargs[] = {&sa};
+                    PHB_CUDA(cudaLaunchKernel(sv->seg_func, dim3(unsigned(grid_full)), dim3(sv->NT), kargs, sv->smem, stream));
+                }
+                {
+                    const int64_t n_out = n_pairs * 7 * M;
+                    phb::sum_segments_kernel<float><<<unsigned((n_out + 255) / 256), 256, 0, stream>>>(
+                        static_cast<const float *>(k->seg_dlog.ptr), n_pairs, n_seg, M, static_cast<float *>(a.dlog), a.out_mode);
+                    PHB_CUDA(cudaGetLastError());
+                    n_launch += 1;
+                }
+                k->launches += n_launch;
+                snprintf(k->last_name, sizeof k->last_name, "transfer_rows_kernel<float,M=%d> + storeall_kernel<SEG> x %lld segments",
+                         M, (long long)n_seg);
+                return PHB_OK;
+            }
+        }
+    }
     if (!fixed && grad && !k->dbl && sa_mode != 0 && k->force_T == 0) {
         for (const StoreAllVariant &sv : storeall_variants()) {
             if (sv.M != k->M) continue;
@@ -320,8 +419,6 @@ int launch_one(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream,
     // kernel needs ~80 ns per site whatever the number of pairs (measured, profiles/r01_elpd_shape_probe.log);
     // M times the work at full throughput is faster while pairs * M is below a quarter of the
     // resident threads.  PHB_PARALLEL_IN_TIME=0/1 overrides the mode set through the API.
-    const char *pit_env = getenv("PHB_PARALLEL_IN_TIME");
-    const int pit_mode = pit_env ? atoi(pit_env) : k->parallel_in_time;
     if (!fixed && !grad && !k->dbl && pit_mode != 0 && k->force_T == 0 && a.s_list == nullptr) {
         if (const TransferVariant *tv = transfer_variant(k->M)) {
             const int64_t capacity = int64_t(k->num_sms) * 384;  // resident threads of the row kernel
@@ -639,6 +736,9 @@ void phb_destroy(phb_kernel *k) {
     k->term_sums.release();
     k->transfer_rows.release();
     k->transfer_log.release();
+    k->bnd_alpha.release();
+    k->bnd_beta.release();
+    k->seg_dlog.release();
     if (k->d_rowflag) cudaFree(k->d_rowflag);
     if (k->d_data) cudaFree(k->d_data);
     if (k->d_err) cudaFree(k->d_err);

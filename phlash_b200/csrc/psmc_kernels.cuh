@@ -62,6 +62,16 @@ struct KernelArgs {
     // in device memory, so the split needs no host round trip.  nullptr = all S chunks.
     const int32_t *s_list;
     const int32_t *s_count;
+    // Segment mode of the store-all kernel (parallel-in-time gradient, see chain_boundaries_kernel): the
+    // launch scores the G segments of every chunk as independent short "pairs" (L = sites per chunk),
+    // started from bnd_alpha and closed with bnd_beta; partial gradients go to seg_dlog.
+    int64_t seg_count;      // G, segments per chunk
+    int64_t seg_len;        // sites per segment (multiple of 16); the last one has L - (G - 1) seg_len
+    int64_t seg_ctas;       // CTAs per segment: CTA c scores segment c / seg_ctas, so that all warps of a CTA
+                            // share the segment length (the loop bounds stay uniform for the shuffles)
+    const void *bnd_alpha;  // [B * S][G + 1][M] FLOAT: forward vector entering segment g (sum 1)
+    const void *bnd_beta;   // [B * S][G + 1][M] FLOAT: adjoint vector behind segment g - 1 (any scale)
+    void *seg_dlog;         // [B * S][G][7][M] FLOAT
 };
 
 // Pair enumeration shared by the kernels: b major, position in the (sub-)list minor.
@@ -793,7 +803,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
 // adjoint pass streams them back with the loads of the next block issued one block ahead - two
 // passes instead of three, nothing recomputed.  One CTA handles exactly one group of pairs (the
 // host launches enough CTAs), so the scratch is indexed by the global warp index.
-template <typename F, int MT, int T, int NT, int MINB>
+template <typename F, int MT, int T, int NT, int MINB, bool SEG = false>
 __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_storeall_kernel(const KernelArgs a) {
     constexpr int M = MT * T;
     constexpr int PW = 32 / T;
@@ -821,21 +831,36 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_storeall_kernel(cons
     const int sub = lane % T;
     const int lp = lane / T;
     const int64_t s_eff = listed_chunks(a);
-    const int64_t n_pairs = a.B * s_eff;
+    const int64_t n_pairs = SEG ? a.B * a.S : a.B * s_eff;
+    // SEG: CTA -> (segment, CTA within the segment); L = length of that segment
+    const int64_t seg = SEG ? int64_t(blockIdx.x) / a.seg_ctas : 0;
+    const int64_t cta = SEG ? int64_t(blockIdx.x) % a.seg_ctas : int64_t(blockIdx.x);
+    const int64_t L = SEG ? min(a.seg_len, a.L - seg * a.seg_len) : a.L;
+    const int64_t L_max = SEG ? a.seg_len : a.L;
     // the grid is sized for the whole minibatch; with a sub-list the surplus warps have nothing to do
     // (no block-level barrier follows, so whole warps may leave)
-    if ((int64_t(blockIdx.x) * kWarps + warp) * PW >= n_pairs) return;
-    const int64_t n_blocks = (a.L + kNorm - 1) / kNorm;
+    if ((cta * kWarps + warp) * PW >= n_pairs) return;
+    const int64_t n_blocks = (L + kNorm - 1) / kNorm;
     const int64_t warp_slot = int64_t(blockIdx.x) * kWarps + warp;
     const F *params6 = static_cast<const F *>(a.params6);
     const F *pi_g = static_cast<const F *>(a.pi);
-    V *xall = reinterpret_cast<V *>(a.xall) + warp_slot * a.L * QN * 32 + lane;  // + (t * QN + q) * 32
-    F *sall = static_cast<F *>(a.sall) + warp_slot * n_blocks * 32 + lane;       // + block * 32
+    V *xall = reinterpret_cast<V *>(a.xall) + warp_slot * L_max * QN * 32 + lane;                  // + (t * QN + q) * 32
+    F *sall = static_cast<F *>(a.sall) + warp_slot * ((L_max + kNorm - 1) / kNorm) * 32 + lane;   // + block * 32
 
-    const int64_t pair_raw = (int64_t(blockIdx.x) * kWarps + warp) * PW + lp;
+    const int64_t pair_raw = (cta * kWarps + warp) * PW + lp;
     const bool writer = pair_raw < n_pairs;
-    const PairIndex pidx = pair_index(a, writer ? pair_raw : n_pairs - 1, s_eff);
-    const int64_t pb = pidx.b, ps = pidx.s, pair = pidx.out;
+    int64_t pb, ps, pair, chunk_pair = 0;
+    if constexpr (SEG) {
+        chunk_pair = writer ? pair_raw : n_pairs - 1;   // (b, s) of the chunk
+        pb = chunk_pair / a.S;
+        ps = chunk_pair % a.S;
+        pair = chunk_pair * a.seg_count + seg;          // slot in seg_dlog
+    } else {
+        const PairIndex pidx = pair_index(a, writer ? pair_raw : n_pairs - 1, s_eff);
+        pb = pidx.b;
+        ps = pidx.s;
+        pair = pidx.out;
+    }
     Params<F, MT> p;
     p.load(params6 + pb * a.pstride_b + ps * a.pstride_s + sub * MT, M);
     et.fill(params6 + pb * a.pstride_b + ps * a.pstride_s + sub * MT, M);
@@ -847,8 +872,9 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_storeall_kernel(cons
         if (sub == 0) atomicOr(a.err_flag, 1);
         row = 0;
     }
-    const int8_t *obs = a.data + row * a.pitch;
-    const F *pi_p = pi_g + pb * a.pistride_b + ps * a.pistride_s + sub * MT;
+    const int8_t *obs = a.data + row * a.pitch + (SEG ? seg * a.seg_len : 0);
+    const F *pi_p = SEG ? static_cast<const F *>(a.bnd_alpha) + (chunk_pair * (a.seg_count + 1) + seg) * M + sub * MT
+                        : pi_g + pb * a.pistride_b + ps * a.pistride_s + sub * MT;
 
     // ---------------------------------------------------------------- pass 1: forward, keep everything
     F x[MT];
@@ -863,7 +889,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_storeall_kernel(cons
         const int64_t t0 = blk_i * kNorm;
         const uint32_t blk = blk_next;
         if (blk_i + 1 < n_blocks) blk_next = __ldg(reinterpret_cast<const unsigned int *>(obs + t0 + kNorm));
-        const int len = int(min(int64_t(kNorm), a.L - t0));
+        const int len = int(min(int64_t(kNorm), L - t0));
 #pragma unroll
         for (int j = 0; j < kNorm; ++j) {
             if (j < len) {
@@ -888,17 +914,32 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_storeall_kernel(cons
         if (sub == 0) atomicOr(a.err_flag, 2);
     }
     if (bad_row) ll = __longlong_as_double(0x7ff8000000000000LL);
-    if (writer && sub == 0) a.ll[pair] = a.out_mode ? a.ll[pair] - ll : ll;
+    if constexpr (!SEG) {  // (the log-likelihood of a segmented chunk comes from chain_boundaries_kernel)
+        if (writer && sub == 0) a.ll[pair] = a.out_mode ? a.ll[pair] - ll : ll;
+    }
 
     // ---------------------------------------------------------------- pass 2: adjoint, streaming the vectors back
     Grad<F, MT, false> g;
     g.clear();
     F beta[MT];
-    {
+    if constexpr (SEG) {
+        // the adjoint vector behind this segment, scaled so that beta . x == 1
+        const F *bb = static_cast<const F *>(a.bnd_beta) + (chunk_pair * (a.seg_count + 1) + seg + 1) * M + sub * MT;
+        F dot = F(0);
+#pragma unroll
+        for (int k = 0; k < MT; ++k) {
+            beta[k] = bb[k];
+            dot = fma(beta[k], x[k], dot);
+        }
+        dot = F(1) / lanes_total<F, T>(dot);
+#pragma unroll
+        for (int k = 0; k < MT; ++k) beta[k] *= dot;
+        posterior_to_emission<F, MT, NT, false>(beta, x, int(obs[L - 1]), g, ea);
+    } else {
         const F tot = fast_rcp<F>(pair_sum<F, MT, T>(x));
 #pragma unroll
         for (int k = 0; k < MT; ++k) beta[k] = tot;
-        posterior_to_emission<F, MT, NT, false>(beta, x, int(obs[a.L - 1]), g, ea);
+        posterior_to_emission<F, MT, NT, false>(beta, x, int(obs[L - 1]), g, ea);
     }
     double *gacc_base = a.gacc + int64_t(blockIdx.x) * NT + threadIdx.x;
     const int64_t gacc_stride = int64_t(gridDim.x) * NT;
@@ -910,7 +951,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_storeall_kernel(cons
         const int64_t t0 = blk_i * kNorm;
 #pragma unroll
         for (int j = 0; j < kNorm; ++j) {
-            if (t0 + j < a.L) {
+            if (t0 + j < L) {
 #pragma unroll
                 for (int q = 0; q < QN; ++q) unpack<F>(xall[((t0 + j) * QN + q) * 32], &dst[j][q * W]);
             }
@@ -947,7 +988,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_storeall_kernel(cons
         }
         // the observation just before this block is the last byte of the word that is on its way
         const int ob_before = t0 > 0 ? ObsWords<K>::byte_of(obs_next, kNorm - 1) : -1;
-        const int len = int(min(int64_t(kNorm), a.L - t0));
+        const int len = int(min(int64_t(kNorm), L - t0));
         if ((blk_i & 3) == 3) {
             // every 16 sites: re-impose beta . alpha == 1 against round-off drift
             F dot = F(0);
@@ -978,7 +1019,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_storeall_kernel(cons
         }
     }
     if (writer) {
-        F *out = static_cast<F *>(a.dlog) + pair * 7 * M + sub * MT;
+        F *out = static_cast<F *>(SEG ? a.seg_dlog : a.dlog) + pair * 7 * M + sub * MT;
 #pragma unroll
         for (int k = 0; k < MT; ++k) {
             F val[7];
@@ -990,7 +1031,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_storeall_kernel(cons
             val[5] = F(gacc_base[int64_t(5 * MT + k) * gacc_stride]);
             val[6] = beta[k] * pi_p[k];
 #pragma unroll
-            for (int r = 0; r < 7; ++r) out[r * M + k] = a.out_mode ? out[r * M + k] - val[r] : val[r];
+            for (int r = 0; r < 7; ++r) out[r * M + k] = (!SEG && a.out_mode) ? out[r * M + k] - val[r] : val[r];
         }
     }
 }
@@ -1130,6 +1171,100 @@ template <typename F, int M> __global__ void chain_transfer_kernel(const Transfe
         atomicOr(a.err_flag, 2);
     }
     a.ll[pair] = a.out_mode ? a.ll[pair] - ll : ll;
+}
+
+// The same operators serve the GRADIENT of few pairs (the reference's default minibatch is ONE chunk
+// for a single genome, mcmc.py:119-121: 500 pairs, 14 ms of dependent site steps): chained forwards
+// they give the forward vector entering every segment, chained backwards (beta_g = T_g beta_{g+1},
+// beta_G = 1) the adjoint vector behind it.  With both boundary vectors known the segments are
+// independent: the store-all kernel runs its two passes over every segment as if it were a short
+// chunk (SEG mode: started from alpha_g, closed with beta_{g+1} rescaled to beta . alpha == 1), and
+// the partial gradients are added up.
+//
+// chain_boundaries_kernel: M lanes per pair (lane k owns component k); writes ll and the G + 1 boundary
+// vectors of both kinds.  Launch with 128 threads per CTA.
+template <int M> __device__ __forceinline__ double group_max(double v) {
+#pragma unroll
+    for (int o = M / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o, M));
+    return v;
+}
+template <int M> __device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+    for (int o = M / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, M);
+    return v;
+}
+template <typename F, int M> __global__ void chain_boundaries_kernel(const TransferArgs ta, F *bnd_alpha, F *bnd_beta) {
+    const KernelArgs &a = ta.k;
+    const int64_t n_pairs = a.B * a.S;
+    const int64_t pair_raw = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) / M;
+    const bool writer = pair_raw < n_pairs;
+    const int64_t pair = writer ? pair_raw : n_pairs - 1;  // idle groups shadow the last pair (whole warps shuffle)
+    const int k = threadIdx.x % M;
+    const int64_t pb = pair / a.S, ps = pair % a.S;
+    const int64_t G = ta.n_seg;
+    const F *pi_p = static_cast<const F *>(a.pi) + pb * a.pistride_b + ps * a.pistride_s;
+    F *al = bnd_alpha + pair * (G + 1) * M;
+    F *be = bnd_beta + pair * (G + 1) * M;
+    double v = double(pi_p[k]);
+    double tot = group_sum<M>(v);
+    double ll2 = log2(tot);
+    v /= tot;
+    if (writer) al[k] = F(v);
+    for (int64_t g = 0; g < G; ++g) {
+        const float *rows = ta.rows + (pair * G + g) * M * M;
+        const double lg = ta.row_log2[(pair * G + g) * M + k];
+        const double top = group_max<M>(v > 0.0 ? lg : -1e300);
+        const double w = v > 0.0 ? v * exp2(lg - top) : 0.0;
+        double next = 0.0;
+#pragma unroll
+        for (int i = 0; i < M; ++i) next += __shfl_sync(0xffffffffu, w, i, M) * double(rows[i * M + k]);
+        tot = group_sum<M>(next);
+        ll2 += top + log2(tot);
+        v = next / tot;
+        if (writer) al[(g + 1) * M + k] = F(v);
+    }
+    // adjoint boundaries: beta_g[i] = 2^lg_i sum_j T_g[i, j] beta_{g+1}[j], kept at maximum 1 (lane k owns row k)
+    v = 1.0;
+    if (writer) be[G * M + k] = F(1);
+    for (int64_t g = G - 1; g >= 0; --g) {
+        const float *rows = ta.rows + (pair * G + g) * M * M;
+        const double lg = ta.row_log2[(pair * G + g) * M + k];
+        const double top = group_max<M>(lg);
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < M; ++j) acc += double(rows[k * M + j]) * __shfl_sync(0xffffffffu, v, j, M);
+        const double next = acc * exp2(lg - top);
+        v = next / group_max<M>(next);
+        if (writer) be[g * M + k] = F(v);
+    }
+    if (writer && k == 0) {
+        double ll = ll2 * 0.69314718055994530942;
+        const int64_t row = a.inds[ps];
+        if (row < 0 || row >= a.n_rows) {
+            atomicOr(a.err_flag, 1);
+            ll = __longlong_as_double(0x7ff8000000000000LL);
+        } else if (!(ll == ll) || ll > 1e300 || ll < -1e300) {
+            atomicOr(a.err_flag, 2);
+        }
+        a.ll[pair] = a.out_mode ? a.ll[pair] - ll : ll;
+    }
+}
+
+// dlog[pair] = sum over the segments of their partial gradients (rows b .. emis1); the pi row is the
+// one of the first segment.  One thread per output entry.
+template <typename F>
+__global__ void sum_segments_kernel(const F *__restrict__ seg_dlog, int64_t n_pairs, int64_t G, int M, F *__restrict__ dlog,
+                                    int out_mode) {
+    const int64_t n = n_pairs * 7 * M;
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t pair = i / (7 * M);
+    const int64_t rm = i % (7 * M);
+    const F *src = seg_dlog + pair * G * 7 * M + rm;
+    double acc = double(src[0]);
+    if (rm < 6 * M)
+        for (int64_t g = 1; g < G; ++g) acc += double(src[g * 7 * M]);
+    dlog[i] = out_mode ? F(double(dlog[i]) - acc) : F(acc);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -52,7 +52,7 @@ def test_dispatch_rules():
     kern.evaluate(pa, np.arange(2), False)
     assert "transfer" in kern.last_kernel_name            # 8 pairs x 40 000 sites
     kern.evaluate(pa, np.arange(2), True)
-    assert "transfer" not in kern.last_kernel_name        # gradient path
+    assert "segments" in kern.last_kernel_name            # gradient path: also parallel in time
     kern.set_threads_per_pair(2)
     kern.evaluate(pa, np.arange(2), False)
     assert "transfer" not in kern.last_kernel_name        # a forced lane layout wins
@@ -109,3 +109,58 @@ def test_bad_index_is_reported():
         kern.sync()
     ll = ll.cpu().numpy()
     assert np.isnan(ll[:, 1]).all() and np.isfinite(ll[:, [0, 2]]).all()
+
+
+@pytest.mark.parametrize("M", [4, 8, 16])
+@pytest.mark.parametrize("L", [200, 3001, 20_000])
+def test_gradient_through_segments_matches_oracle(M, L):
+    """Parallel-in-time gradient: boundary vectors from the chained operators, store-all passes per
+    segment, partial gradients added up - against the fp64 oracle and the sequential kernels."""
+    from test_gpu_parity import GRAD_RTOL, grad_close, oracle_eval
+
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    data = rows_with_missing(3, L, seed=2 * M + L)
+    pps, _, _ = orc.synth_particles(M, 5, seed=7)
+    inds = np.array([2, 0, 1, 2])
+    pa = np.broadcast_to(pps[:, None], (5, len(inds), 7, M)).copy()
+    ref_ll, ref_dlog = oracle_eval(data, inds, pa)
+    kern = _PSMCKernelBase(M, data)
+    kern.set_parallel_in_time(1)
+    ll, dlog = kern.evaluate(pa, inds, True)
+    assert "segments" in kern.last_kernel_name
+    np.testing.assert_allclose(ll, ref_ll, rtol=LL_RTOL)
+    grad_close(dlog, ref_dlog, GRAD_RTOL, f"parallel in time, M={M}, L={L}")
+    kern.set_parallel_in_time(0)
+    ll_s, dlog_s = kern.evaluate(pa, inds, True)
+    assert "segments" not in kern.last_kernel_name
+    np.testing.assert_allclose(ll, ll_s, rtol=2e-6)
+    grad_close(dlog, dlog_s, 2e-5, "vs sequential kernel")
+    # structural zeros stay exactly zero
+    assert np.all(dlog[:, :, 0, -1] == 0) and np.all(dlog[:, :, 2, -1] == 0) and np.all(dlog[:, :, 3, 0] == 0)
+
+
+def test_gradient_dispatch_and_warmup_composition(golden):
+    """automatic choice at the reference's default shape for one genome (S = 1: few pairs, long chunks),
+    and the fused warm-up evaluation (second launch subtracts) on top of it"""
+    from test_gpu_parity import GRAD_RTOL
+
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    ov, L = 100, 12_000
+    data = rows_with_missing(4, ov + L, seed=11)
+    pps, _, _ = orc.synth_particles(16, 6, seed=4)
+    pps = pps.astype(np.float32).astype(np.float64)
+    kern = _PSMCKernelBase(16, data)
+    inds = np.array([3])
+    ll, dlog = kern.evaluate_warmup(pps, inds, ov, True)
+    pa = np.broadcast_to(pps[:, None], (6, 1, 7, 16)).copy()
+    kern.evaluate(pa, inds, True)
+    assert "segments" in kern.last_kernel_name              # 6 pairs x 12 100 sites
+    kern.evaluate(np.broadcast_to(pps[:1, None], (1, 4000, 7, 16)).copy(), np.zeros(4000, dtype=np.int64), True)
+    assert "segments" not in kern.last_kernel_name          # 4000 pairs: not worth M x the forward work
+    kern.set_parallel_in_time(0)
+    ll_s, dlog_s = kern.evaluate_warmup(pps, inds, ov, True)
+    np.testing.assert_allclose(ll, ll_s, rtol=1e-6)
+    scale = np.abs(dlog_s).max(axis=-1, keepdims=True)
+    assert (np.abs(dlog - dlog_s) <= GRAD_RTOL * (np.abs(dlog_s) + 1e-3 * scale)).all()
