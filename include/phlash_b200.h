@@ -97,14 +97,18 @@ int phb_set_threads_per_pair(phb_kernel *k, int threads_per_pair);
  * threads_per_pair is forced). */
 int phb_set_store_all(phb_kernel *k, int mode);
 
-/* Forward-only evaluations of FEW, LONG pairs (the reference's ELPD: whole un-chunked test contigs for
- * every particle, mcmc.py:213-238) cannot fill the GPU with one recursion per pair and last L x the
- * latency of one site step.  They are evaluated parallel in time instead: the sequence is cut into
- * segments, the M unit vectors are propagated through every segment (its transfer operator: M x the
- * arithmetic, M x segments x the parallelism) and the operators are chained in float64.  Exact - no
- * burn-in approximation.  mode: -1 = automatic (float objects, M <= 16, forward-only, pairs * M below
- * a quarter of the resident threads, segments >= 4096 sites), 0 = never, 1 = whenever possible
- * (ignored while threads_per_pair is forced). */
+/* FEW pairs cannot fill the GPU with one recursion each; such a call lasts L x the latency of one
+ * dependent site step whatever the lane layout.  Two cases of the reference are of this kind: the ELPD
+ * evaluation (whole un-chunked test contigs for every particle, forward only, mcmc.py:213-238) and the
+ * default minibatch for a single genome (S = min(5, N / niter) = 1 chunk, mcmc.py:119-121).  They are
+ * evaluated parallel in time: the sequence is cut into segments, the M unit vectors are propagated
+ * through every segment (its transfer operator: M x the forward arithmetic, M x segments x the
+ * parallelism) and the operators are chained in float64 - forwards for the log-likelihood and the
+ * forward vectors at the segment boundaries, backwards for the adjoint vectors there, after which the
+ * gradient passes run over all segments independently.  Exact - no burn-in approximation.
+ * mode: -1 = automatic (float objects, M <= 16; forward-only while pairs * M is below a quarter of the
+ * resident threads and segments stay >= 4096 sites; gradient while pairs * M is below 0.3 of them),
+ * 0 = never, 1 = whenever possible (ignored while threads_per_pair is forced). */
 int phb_set_parallel_in_time(phb_kernel *k, int mode);
 
 /* PRECISION ESCALATION (single-precision objects, gradient path).  Through a long run of identical
