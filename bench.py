@@ -194,7 +194,8 @@ def elpd_step(local_rank):
     tk = model.elpd_kernel(M, synth.het_matrix(1, n_bins, seed=101), device=local_rank)
     xs = np.load(os.path.join(ROOT, "benchdata", f"particles_M{M}.npz"))["xs"][:N_PARTICLES]
     x = torch.tensor(xs, dtype=torch.float64, device=dev)
-    out = {"particles": N_PARTICLES, "test_contigs": 1, "bins": n_bins}
+    out = {"particles": N_PARTICLES, "test_contigs": 1, "bins": n_bins,
+           "path": "transfer_rows_kernel + chain_transfer_kernel (parallel in time), then the 1-bin warm-up term"}
     for name, mode in (("ms", -1), ("ms_sequential_kernel", 0)):
         tk.set_parallel_in_time(mode)
         for _ in range(2):
@@ -207,7 +208,6 @@ def elpd_step(local_rank):
         e1.record()
         e1.synchronize()
         out[name] = e0.elapsed_time(e1) / 3
-        out["kernel" if mode < 0 else "kernel_sequential"] = tk.last_kernel_name
         assert bool(torch.isfinite(e))
     return out
 

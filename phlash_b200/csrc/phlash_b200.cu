@@ -242,6 +242,19 @@ const TransferVariant *transfer_variant(int M) {
     return nullptr;
 }
 
+// Does the store-all scratch (every forward vector + block scales) fit comfortably?  The driver is only
+// asked when the buffers have to grow: cudaMemGetInfo costs host milliseconds in a process with many
+// allocations, which a 3 ms evaluation must not pay on every call.
+bool storeall_scratch_fits(const phb_kernel *k, size_t x_bytes, size_t s_bytes) {
+    if (x_bytes <= k->xall.cap && s_bytes <= k->sall.cap) return true;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return x_bytes + s_bytes <= (free_b + k->xall.cap + k->sall.cap) / 2;
+}
+
 const Variant *pick_variant(const phb_kernel *k, bool grad, int64_t n_pairs) {
     const Variant *last = nullptr, *forced = nullptr, *first_fill = nullptr;
     // Lane layouts are ordered by increasing T (fewer lanes per pair = fewer instructions per pair).
@@ -313,9 +326,7 @@ int launch_one(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream,
             const int64_t warps = grid_full * (sv->NT / 32);
             const size_t x_bytes = size_t(warps) * size_t(seg_len) * sv->MT * 32 * sizeof(float);
             const size_t s_bytes = size_t(warps) * size_t((seg_len + phb::kNorm - 1) / phb::kNorm) * 32 * sizeof(float);
-            size_t free_b = 0, total_b = 0;
-            cudaMemGetInfo(&free_b, &total_b);
-            if (x_bytes + s_bytes <= (free_b + k->xall.cap + k->sall.cap) / 2) {
+            if (storeall_scratch_fits(k, x_bytes, s_bytes)) {
                 int rc;
                 if ((rc = k->transfer_rows.reserve(size_t(n_rows_virtual) * M * sizeof(float))) != PHB_OK) return rc;
                 if ((rc = k->transfer_log.reserve(size_t(n_rows_virtual) * sizeof(double))) != PHB_OK) return rc;
@@ -388,11 +399,8 @@ int launch_one(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream,
             if (sa_mode < 0 && n_pairs * sv.T <= int64_t(k->num_sms) * 330) {
                 // latency-bound regime and the scratch fits comfortably.  Measured on B200 at M = 16,
                 // B = 500 (profiles/r01_probe_small_minibatch.log): store-all wins up to ~12 000 pairs
-                // (S = 24: 23.4 vs 27.2 ms) and loses from ~16 000 pairs on.  (The memory query is
-                // only made here: it costs host milliseconds, which a large launch must not pay.)
-                size_t free_b = 0, total_b = 0;
-                cudaMemGetInfo(&free_b, &total_b);
-                use = x_bytes + s_bytes <= (free_b + k->xall.cap + k->sall.cap) / 2;
+                // (S = 24: 23.4 vs 27.2 ms) and loses from ~16 000 pairs on.
+                use = storeall_scratch_fits(k, x_bytes, s_bytes);
             }
             if (!use) break;
             int rc;
