@@ -164,3 +164,38 @@ def test_gradient_dispatch_and_warmup_composition(golden):
     np.testing.assert_allclose(ll, ll_s, rtol=1e-6)
     scale = np.abs(dlog_s).max(axis=-1, keepdims=True)
     assert (np.abs(dlog - dlog_s) <= GRAD_RTOL * (np.abs(dlog_s) + 1e-3 * scale)).all()
+
+
+def test_per_pair_parameter_blocks_and_subtracting_launch():
+    """(i) parameter rows that differ between the chunks of a particle (pa [B, S, 7, M] not shared);
+    (ii) a warm-up long enough for the SECOND launch of the fused evaluation (which subtracts) to be
+    parallel in time as well."""
+    from test_gpu_parity import GRAD_RTOL, grad_close, oracle_eval
+
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    L = 9000
+    data = rows_with_missing(3, L, seed=21)
+    pps, _, _ = orc.synth_particles(16, 6, seed=9)
+    inds = np.array([1, 2])
+    pa = np.stack([pps[:3], pps[3:6]], axis=1)  # [3, 2, 7, 16]: chunk s of particle b has its own block
+    ref_ll, ref_dlog = oracle_eval(data, inds, pa)
+    kern = _PSMCKernelBase(16, data)
+    kern.set_parallel_in_time(1)
+    ll, dlog = kern.evaluate(pa, inds, True)
+    assert "segments" in kern.last_kernel_name
+    np.testing.assert_allclose(ll, ref_ll, rtol=LL_RTOL)
+    grad_close(dlog, ref_dlog, GRAD_RTOL, "per-pair parameter blocks")
+    ll_f = kern.evaluate(pa, inds, False)
+    assert "transfer" in kern.last_kernel_name
+    np.testing.assert_allclose(ll_f, ref_ll, rtol=LL_RTOL)
+    # (ii)
+    ov = 4000
+    p7 = pps[:4].astype(np.float32).astype(np.float64)
+    got_ll, got_dlog = kern.evaluate_warmup(p7, inds, ov, True)
+    assert "segments" in kern.last_kernel_name           # the launch over the first `ov` bins
+    kern.set_parallel_in_time(0)
+    seq_ll, seq_dlog = kern.evaluate_warmup(p7, inds, ov, True)
+    np.testing.assert_allclose(got_ll, seq_ll, rtol=1e-6)
+    scale = np.abs(seq_dlog).max(axis=-1, keepdims=True)
+    assert (np.abs(got_dlog - seq_dlog) <= GRAD_RTOL * (np.abs(seq_dlog) + 1e-3 * scale) + 2e-6 * scale).all()
