@@ -287,182 +287,194 @@ int check_handle(const phb_kernel *k) {
     return PHB_OK;
 }
 
-// One kernel launch on `stream` over the whole minibatch or over the sub-list in `a`; `fixed` pins the
-// kernel variant (precision escalation), nullptr lets the dispatcher choose.
-int launch_one(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream, const Variant *fixed) {
-    const int64_t n_pairs = a.B * a.S;  // upper bound when a sub-list is given
-    // tuning knob for experiments: PHB_STORE_ALL=0/1 overrides the mode set through the API
-    const char *sa_env = getenv("PHB_STORE_ALL");
-    const int sa_mode = sa_env ? atoi(sa_env) : k->store_all_mode;
-    const char *pit_env = getenv("PHB_PARALLEL_IN_TIME");
-    const int pit_mode = pit_env ? atoi(pit_env) : k->parallel_in_time;
-    // Gradient of FEW pairs (the reference's default minibatch for one genome is a single chunk: 500
-    // pairs): parallel in time.  Segment transfer operators give the forward / adjoint vectors at the
-    // segment boundaries (chain_boundaries_kernel), after which the segments are independent short
-    // chunks for the store-all kernel.  Worth it while the operators (M x the forward work, at full
-    // throughput) cost less than the dependent site steps they remove: pairs * M below 0.3 of the
-    // resident threads (measured, profiles/r01_probe_parallel_in_time.log: B = 500, L = 50 000, S = 1 / 2 / 3
-    // chunks 5.3 / 9.5 / 13.6 ms against 13.6 ms sequential).
-    if (!fixed && grad && !k->dbl && pit_mode != 0 && sa_mode != 0 && k->force_T == 0 && a.s_list == nullptr) {
-        const TransferVariant *tv = transfer_variant(k->M);
-        const StoreAllVariant *sv = nullptr;
-        for (const StoreAllVariant &c : storeall_variants())
-            if (c.M == k->M) sv = &c;
-        const int64_t capacity = int64_t(k->num_sms) * 384;
-        const int64_t min_seg = pit_mode == 1 ? 64 : 1024;
-        int64_t n_seg = tv && sv ? std::min(4 * capacity / (n_pairs * tv->M), a.L / min_seg) : 0;
-        if (pit_mode == 1) n_seg = std::max<int64_t>(n_seg, std::min<int64_t>(3, a.L / min_seg));
-        if (const char *g_env = getenv("PHB_PIT_SEGMENTS")) n_seg = std::min<int64_t>(atoi(g_env), a.L / 64);  // experiments
-        const bool worth = pit_mode == 1 || n_pairs * k->M * 10 <= capacity * 3;
-        if (tv && sv && worth && n_seg >= 3) {
-            const int64_t seg_len = ((a.L + n_seg - 1) / n_seg + 15) / 16 * 16;
-            n_seg = (a.L + seg_len - 1) / seg_len;
-            const int M = k->M;
-            const int64_t n_rows_virtual = n_pairs * n_seg * M;
-            // store-all passes: one launch, every CTA inside one segment (uniform loop bounds per CTA)
-            const int pairs_per_cta = sv->NT / sv->T;
-            const int64_t seg_ctas = (n_pairs + pairs_per_cta - 1) / pairs_per_cta;
-            const int64_t grid_full = seg_ctas * n_seg;
-            const int64_t warps = grid_full * (sv->NT / 32);
-            const size_t x_bytes = size_t(warps) * size_t(seg_len) * sv->MT * 32 * sizeof(float);
-            const size_t s_bytes = size_t(warps) * size_t((seg_len + phb::kNorm - 1) / phb::kNorm) * 32 * sizeof(float);
-            if (storeall_scratch_fits(k, x_bytes, s_bytes)) {
-                int rc;
-                if ((rc = k->transfer_rows.reserve(size_t(n_rows_virtual) * M * sizeof(float))) != PHB_OK) return rc;
-                if ((rc = k->transfer_log.reserve(size_t(n_rows_virtual) * sizeof(double))) != PHB_OK) return rc;
-                if ((rc = k->bnd_alpha.reserve(size_t(n_pairs) * (n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
-                if ((rc = k->bnd_beta.reserve(size_t(n_pairs) * (n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
-                if ((rc = k->seg_dlog.reserve(size_t(n_pairs) * n_seg * 7 * M * sizeof(float))) != PHB_OK) return rc;
-                if ((rc = k->xall.reserve(x_bytes)) != PHB_OK) return rc;
-                if ((rc = k->sall.reserve(s_bytes)) != PHB_OK) return rc;
-                if ((rc = k->gacc.reserve(size_t(grid_full) * sv->NT * 6 * sv->MT * sizeof(double))) != PHB_OK) return rc;
-                for (const void *f : {tv->rows_func, sv->seg_func}) {
-                    if (k->occupancy.find(f) == k->occupancy.end()) {
-                        PHB_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, int(f == tv->rows_func ? tv->smem : sv->smem)));
-                        k->occupancy.emplace(f, 1);
-                    }
-                }
-                phb::TransferArgs ta{};
-                ta.k = a;
-                ta.k.err_flag = k->d_err;
-                ta.n_seg = n_seg;
-                ta.seg_len = seg_len;
-                ta.rows = static_cast<float *>(k->transfer_rows.ptr);
-                ta.row_log2 = static_cast<double *>(k->transfer_log.ptr);
-                void *bnd_a = k->bnd_alpha.ptr, *bnd_b = k->bnd_beta.ptr;
-                {
-                    void *kargs[] = {&ta};
-                    PHB_CUDA(cudaLaunchKernel(tv->rows_func, dim3(unsigned((n_rows_virtual + 127) / 128)), dim3(128), kargs, tv->smem, stream));
-                    void *bargs[] = {&ta, &bnd_a, &bnd_b};
-                    PHB_CUDA(cudaLaunchKernel(tv->boundaries_func, dim3(unsigned((n_pairs * M + 127) / 128)), dim3(128), bargs, 0, stream));
-                }
-                phb::KernelArgs sa = a;
-                sa.err_flag = k->d_err;
-                sa.xall = k->xall.ptr;
-                sa.sall = k->sall.ptr;
-                sa.gacc = static_cast<double *>(k->gacc.ptr);
-                sa.seg_count = n_seg;
-                sa.seg_len = seg_len;
-                sa.bnd_alpha = bnd_a;
-                sa.bnd_beta = bnd_b;
-                sa.seg_dlog = k->seg_dlog.ptr;
-                sa.seg_ctas = seg_ctas;
-                sa.n_groups = grid_full;
-                int n_launch = 3;
-                {
-                    void *kargs[] = {&sa};
-                    PHB_CUDA(cudaLaunchKernel(sv->seg_func, dim3(unsigned(grid_full)), dim3(sv->NT), kargs, sv->smem, stream));
-                }
-                {
-                    const int64_t n_out = n_pairs * 7 * M;
-                    phb::sum_segments_kernel<float><<<unsigned((n_out + 255) / 256), 256, 0, stream>>>(
-                        static_cast<const float *>(k->seg_dlog.ptr), n_pairs, n_seg, M, static_cast<float *>(a.dlog), a.out_mode);
-                    PHB_CUDA(cudaGetLastError());
-                    n_launch += 1;
-                }
-                k->launches += n_launch;
-                snprintf(k->last_name, sizeof k->last_name, "transfer_rows_kernel<float,M=%d> + storeall_kernel<SEG> x %lld segments",
-                         M, (long long)n_seg);
-                return PHB_OK;
-            }
-        }
-    }
-    if (!fixed && grad && !k->dbl && sa_mode != 0 && k->force_T == 0) {
-        for (const StoreAllVariant &sv : storeall_variants()) {
-            if (sv.M != k->M) continue;
-            const int pairs_per_cta = sv.NT / sv.T;
-            const int64_t grid = (n_pairs + pairs_per_cta - 1) / pairs_per_cta;
-            const int64_t warps = grid * (sv.NT / 32);
-            const size_t x_bytes = size_t(warps) * size_t(a.L) * sv.MT * 32 * sizeof(float);
-            const size_t s_bytes = size_t(warps) * size_t((a.L + phb::kNorm - 1) / phb::kNorm) * 32 * sizeof(float);
-            bool use = sa_mode == 1;
-            if (sa_mode < 0 && n_pairs * sv.T <= int64_t(k->num_sms) * 330) {
-                // latency-bound regime and the scratch fits comfortably.  Measured on B200 at M = 16,
-                // B = 500 (profiles/r01_probe_small_minibatch.log): store-all wins up to ~12 000 pairs
-                // (S = 24: 23.4 vs 27.2 ms) and loses from ~16 000 pairs on.
-                use = storeall_scratch_fits(k, x_bytes, s_bytes);
-            }
-            if (!use) break;
+// Dispatch.  A call is served by the first of four paths that applies; kNotTaken = "this path does not
+// apply, try the next one".
+constexpr int kNotTaken = 1;
+
+// (1) Gradient of FEW pairs (the reference's default minibatch for one genome is a single chunk: 500
+// pairs): parallel in time.  Segment transfer operators give the forward / adjoint vectors at the
+// segment boundaries (chain_boundaries_kernel), after which the segments are independent short
+// chunks for the store-all kernel.  Worth it while the operators (M x the forward work, at full
+// throughput) cost less than the dependent site steps they remove: pairs * M below 0.3 of the
+// resident threads (measured, profiles/r01_probe_parallel_in_time.log: B = 500, L = 50 000, S = 1 / 2 / 3
+// chunks 3.4 / 6.5 / 13.6 ms against 13.6 ms sequential).
+int try_parallel_in_time_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t stream, int pit_mode) {
+    const int64_t n_pairs = a.B * a.S;
+    const TransferVariant *tv = transfer_variant(k->M);
+    const StoreAllVariant *sv = nullptr;
+    for (const StoreAllVariant &c : storeall_variants())
+        if (c.M == k->M) sv = &c;
+    const int64_t capacity = int64_t(k->num_sms) * 384;
+    const int64_t min_seg = pit_mode == 1 ? 64 : 1024;
+    int64_t n_seg = tv && sv ? std::min(4 * capacity / (n_pairs * tv->M), a.L / min_seg) : 0;
+    if (pit_mode == 1) n_seg = std::max<int64_t>(n_seg, std::min<int64_t>(3, a.L / min_seg));
+    if (const char *g_env = getenv("PHB_PIT_SEGMENTS")) n_seg = std::min<int64_t>(atoi(g_env), a.L / 64);  // experiments
+    const bool worth = pit_mode == 1 || n_pairs * k->M * 10 <= capacity * 3;
+    if (tv && sv && worth && n_seg >= 3) {
+        const int64_t seg_len = ((a.L + n_seg - 1) / n_seg + 15) / 16 * 16;
+        n_seg = (a.L + seg_len - 1) / seg_len;
+        const int M = k->M;
+        const int64_t n_rows_virtual = n_pairs * n_seg * M;
+        // store-all passes: one launch, every CTA inside one segment (uniform loop bounds per CTA)
+        const int pairs_per_cta = sv->NT / sv->T;
+        const int64_t seg_ctas = (n_pairs + pairs_per_cta - 1) / pairs_per_cta;
+        const int64_t grid_full = seg_ctas * n_seg;
+        const int64_t warps = grid_full * (sv->NT / 32);
+        const size_t x_bytes = size_t(warps) * size_t(seg_len) * sv->MT * 32 * sizeof(float);
+        const size_t s_bytes = size_t(warps) * size_t((seg_len + phb::kNorm - 1) / phb::kNorm) * 32 * sizeof(float);
+        if (storeall_scratch_fits(k, x_bytes, s_bytes)) {
             int rc;
+            if ((rc = k->transfer_rows.reserve(size_t(n_rows_virtual) * M * sizeof(float))) != PHB_OK) return rc;
+            if ((rc = k->transfer_log.reserve(size_t(n_rows_virtual) * sizeof(double))) != PHB_OK) return rc;
+            if ((rc = k->bnd_alpha.reserve(size_t(n_pairs) * (n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
+            if ((rc = k->bnd_beta.reserve(size_t(n_pairs) * (n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
+            if ((rc = k->seg_dlog.reserve(size_t(n_pairs) * n_seg * 7 * M * sizeof(float))) != PHB_OK) return rc;
             if ((rc = k->xall.reserve(x_bytes)) != PHB_OK) return rc;
             if ((rc = k->sall.reserve(s_bytes)) != PHB_OK) return rc;
-            if ((rc = k->gacc.reserve(size_t(grid) * sv.NT * 6 * sv.MT * sizeof(double))) != PHB_OK) return rc;
-            a.xall = k->xall.ptr;
-            a.sall = k->sall.ptr;
-            a.gacc = static_cast<double *>(k->gacc.ptr);
-            a.n_groups = grid;
-            a.err_flag = k->d_err;
-            if (k->occupancy.find(sv.func) == k->occupancy.end()) {
-                PHB_CUDA(cudaFuncSetAttribute(sv.func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sv.smem)));
-                k->occupancy.emplace(sv.func, 1);
+            if ((rc = k->gacc.reserve(size_t(grid_full) * sv->NT * 6 * sv->MT * sizeof(double))) != PHB_OK) return rc;
+            for (const void *f : {tv->rows_func, sv->seg_func}) {
+                if (k->occupancy.find(f) == k->occupancy.end()) {
+                    PHB_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, int(f == tv->rows_func ? tv->smem : sv->smem)));
+                    k->occupancy.emplace(f, 1);
+                }
             }
-            void *kargs[] = {&a};
-            PHB_CUDA(cudaLaunchKernel(sv.func, dim3(unsigned(grid)), dim3(sv.NT), kargs, sv.smem, stream));
-            k->launches += 1;
-            snprintf(k->last_name, sizeof k->last_name, "psmc_loglik_storeall_kernel<float,MT=%d,T=%d,NT=%d>", sv.MT, sv.T, sv.NT);
+            phb::TransferArgs ta{};
+            ta.k = a;
+            ta.k.err_flag = k->d_err;
+            ta.n_seg = n_seg;
+            ta.seg_len = seg_len;
+            ta.rows = static_cast<float *>(k->transfer_rows.ptr);
+            ta.row_log2 = static_cast<double *>(k->transfer_log.ptr);
+            void *bnd_a = k->bnd_alpha.ptr, *bnd_b = k->bnd_beta.ptr;
+            {
+                void *kargs[] = {&ta};
+                PHB_CUDA(cudaLaunchKernel(tv->rows_func, dim3(unsigned((n_rows_virtual + 127) / 128)), dim3(128), kargs, tv->smem, stream));
+                void *bargs[] = {&ta, &bnd_a, &bnd_b};
+                PHB_CUDA(cudaLaunchKernel(tv->boundaries_func, dim3(unsigned((n_pairs * M + 127) / 128)), dim3(128), bargs, 0, stream));
+            }
+            phb::KernelArgs sa = a;
+            sa.err_flag = k->d_err;
+            sa.xall = k->xall.ptr;
+            sa.sall = k->sall.ptr;
+            sa.gacc = static_cast<double *>(k->gacc.ptr);
+            sa.seg_count = n_seg;
+            sa.seg_len = seg_len;
+            sa.bnd_alpha = bnd_a;
+            sa.bnd_beta = bnd_b;
+            sa.seg_dlog = k->seg_dlog.ptr;
+            sa.seg_ctas = seg_ctas;
+            sa.n_groups = grid_full;
+            int n_launch = 3;
+            {
+                void *kargs[] = {&sa};
+                PHB_CUDA(cudaLaunchKernel(sv->seg_func, dim3(unsigned(grid_full)), dim3(sv->NT), kargs, sv->smem, stream));
+            }
+            {
+                const int64_t n_out = n_pairs * 7 * M;
+                phb::sum_segments_kernel<float><<<unsigned((n_out + 255) / 256), 256, 0, stream>>>(
+                    static_cast<const float *>(k->seg_dlog.ptr), n_pairs, n_seg, M, static_cast<float *>(a.dlog), a.out_mode);
+                PHB_CUDA(cudaGetLastError());
+                n_launch += 1;
+            }
+            k->launches += n_launch;
+            snprintf(k->last_name, sizeof k->last_name, "transfer_rows_kernel<float,M=%d> + storeall_kernel<SEG> x %lld segments",
+                     M, (long long)n_seg);
             return PHB_OK;
         }
     }
-    // Forward-only, few long pairs: segment transfer operators chained afterwards.  The sequential
-    // kernel needs ~80 ns per site whatever the number of pairs (measured, profiles/r01_elpd_shape_probe.log);
-    // M times the work at full throughput is faster while pairs * M is below a quarter of the
-    // resident threads.  PHB_PARALLEL_IN_TIME=0/1 overrides the mode set through the API.
-    if (!fixed && !grad && !k->dbl && pit_mode != 0 && k->force_T == 0 && a.s_list == nullptr) {
-        if (const TransferVariant *tv = transfer_variant(k->M)) {
-            const int64_t capacity = int64_t(k->num_sms) * 384;  // resident threads of the row kernel
-            const int64_t min_seg = pit_mode == 1 ? 64 : 4096;   // sites; shorter segments are all overhead
-            int64_t n_seg = std::min(capacity / (n_pairs * tv->M), a.L / min_seg);
-            if (pit_mode == 1) n_seg = std::max<int64_t>(n_seg, std::min<int64_t>(3, a.L / min_seg));
-            // (measured at M = 16, L = 2.5 M: 500 pairs -> 7 segments 91 ms vs 209 ms sequential; 1000 pairs ->
-            // 3 segments 213 ms, no gain any more; profiles/r01_elpd_shape_probe.log)
-            if (n_seg >= (pit_mode == 1 ? 3 : 4)) {
-                int64_t seg_len = ((a.L + n_seg - 1) / n_seg + 15) / 16 * 16;
-                n_seg = (a.L + seg_len - 1) / seg_len;
-                const int64_t n_virtual = n_pairs * n_seg * tv->M;
-                int rc;
-                if ((rc = k->transfer_rows.reserve(size_t(n_virtual) * tv->M * sizeof(float))) != PHB_OK) return rc;
-                if ((rc = k->transfer_log.reserve(size_t(n_virtual) * sizeof(double))) != PHB_OK) return rc;
-                phb::TransferArgs ta{};
-                ta.k = a;
-                ta.k.err_flag = k->d_err;
-                ta.n_seg = n_seg;
-                ta.seg_len = seg_len;
-                ta.rows = static_cast<float *>(k->transfer_rows.ptr);
-                ta.row_log2 = static_cast<double *>(k->transfer_log.ptr);
-                if (k->occupancy.find(tv->rows_func) == k->occupancy.end()) {
-                    PHB_CUDA(cudaFuncSetAttribute(tv->rows_func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tv->smem)));
-                    k->occupancy.emplace(tv->rows_func, 1);
-                }
-                void *kargs[] = {&ta};
-                PHB_CUDA(cudaLaunchKernel(tv->rows_func, dim3(unsigned((n_virtual + 127) / 128)), dim3(128), kargs, tv->smem, stream));
-                PHB_CUDA(cudaLaunchKernel(tv->chain_func, dim3(unsigned((n_pairs + 63) / 64)), dim3(64), kargs, 0, stream));
-                k->launches += 2;
-                snprintf(k->last_name, sizeof k->last_name, "transfer_rows_kernel<float,M=%d> x %lld segments + chain_transfer_kernel",
-                         tv->M, (long long)n_seg);
-                return PHB_OK;
+
+    return kNotTaken;
+}
+
+// (2) Gradient of a small minibatch: the store-all kernel (two dependent passes instead of three).
+int try_store_all(phb_kernel *k, phb::KernelArgs a, cudaStream_t stream, int sa_mode) {
+    const int64_t n_pairs = a.B * a.S;  // upper bound when a sub-list is given
+    for (const StoreAllVariant &sv : storeall_variants()) {
+        if (sv.M != k->M) continue;
+        const int pairs_per_cta = sv.NT / sv.T;
+        const int64_t grid = (n_pairs + pairs_per_cta - 1) / pairs_per_cta;
+        const int64_t warps = grid * (sv.NT / 32);
+        const size_t x_bytes = size_t(warps) * size_t(a.L) * sv.MT * 32 * sizeof(float);
+        const size_t s_bytes = size_t(warps) * size_t((a.L + phb::kNorm - 1) / phb::kNorm) * 32 * sizeof(float);
+        bool use = sa_mode == 1;
+        if (sa_mode < 0 && n_pairs * sv.T <= int64_t(k->num_sms) * 330) {
+            // latency-bound regime and the scratch fits comfortably.  Measured on B200 at M = 16,
+            // B = 500 (profiles/r01_probe_small_minibatch.log): store-all wins up to ~12 000 pairs
+            // (S = 24: 23.4 vs 27.2 ms) and loses from ~16 000 pairs on.
+            use = storeall_scratch_fits(k, x_bytes, s_bytes);
+        }
+        if (!use) break;
+        int rc;
+        if ((rc = k->xall.reserve(x_bytes)) != PHB_OK) return rc;
+        if ((rc = k->sall.reserve(s_bytes)) != PHB_OK) return rc;
+        if ((rc = k->gacc.reserve(size_t(grid) * sv.NT * 6 * sv.MT * sizeof(double))) != PHB_OK) return rc;
+        a.xall = k->xall.ptr;
+        a.sall = k->sall.ptr;
+        a.gacc = static_cast<double *>(k->gacc.ptr);
+        a.n_groups = grid;
+        a.err_flag = k->d_err;
+        if (k->occupancy.find(sv.func) == k->occupancy.end()) {
+            PHB_CUDA(cudaFuncSetAttribute(sv.func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sv.smem)));
+            k->occupancy.emplace(sv.func, 1);
+        }
+        void *kargs[] = {&a};
+        PHB_CUDA(cudaLaunchKernel(sv.func, dim3(unsigned(grid)), dim3(sv.NT), kargs, sv.smem, stream));
+        k->launches += 1;
+        snprintf(k->last_name, sizeof k->last_name, "psmc_loglik_storeall_kernel<float,MT=%d,T=%d,NT=%d>", sv.MT, sv.T, sv.NT);
+        return PHB_OK;
+    }
+
+    return kNotTaken;
+}
+
+// (3) Forward-only, few long pairs: segment transfer operators chained afterwards.  The sequential
+// kernel needs ~80 ns per site whatever the number of pairs (measured, profiles/r01_elpd_shape_probe.log);
+// M times the work at full throughput is faster while pairs * M is below a quarter of the
+// resident threads.
+int try_parallel_in_time_forward(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t stream, int pit_mode) {
+    const int64_t n_pairs = a.B * a.S;
+    if (const TransferVariant *tv = transfer_variant(k->M)) {
+        const int64_t capacity = int64_t(k->num_sms) * 384;  // resident threads of the row kernel
+        const int64_t min_seg = pit_mode == 1 ? 64 : 4096;   // sites; shorter segments are all overhead
+        int64_t n_seg = std::min(capacity / (n_pairs * tv->M), a.L / min_seg);
+        if (pit_mode == 1) n_seg = std::max<int64_t>(n_seg, std::min<int64_t>(3, a.L / min_seg));
+        // (measured at M = 16, L = 2.5 M: 500 pairs -> 7 segments 91 ms vs 209 ms sequential; 1000 pairs ->
+        // 3 segments 213 ms, no gain any more; profiles/r01_elpd_shape_probe.log)
+        if (n_seg >= (pit_mode == 1 ? 3 : 4)) {
+            int64_t seg_len = ((a.L + n_seg - 1) / n_seg + 15) / 16 * 16;
+            n_seg = (a.L + seg_len - 1) / seg_len;
+            const int64_t n_virtual = n_pairs * n_seg * tv->M;
+            int rc;
+            if ((rc = k->transfer_rows.reserve(size_t(n_virtual) * tv->M * sizeof(float))) != PHB_OK) return rc;
+            if ((rc = k->transfer_log.reserve(size_t(n_virtual) * sizeof(double))) != PHB_OK) return rc;
+            phb::TransferArgs ta{};
+            ta.k = a;
+            ta.k.err_flag = k->d_err;
+            ta.n_seg = n_seg;
+            ta.seg_len = seg_len;
+            ta.rows = static_cast<float *>(k->transfer_rows.ptr);
+            ta.row_log2 = static_cast<double *>(k->transfer_log.ptr);
+            if (k->occupancy.find(tv->rows_func) == k->occupancy.end()) {
+                PHB_CUDA(cudaFuncSetAttribute(tv->rows_func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tv->smem)));
+                k->occupancy.emplace(tv->rows_func, 1);
             }
+            void *kargs[] = {&ta};
+            PHB_CUDA(cudaLaunchKernel(tv->rows_func, dim3(unsigned((n_virtual + 127) / 128)), dim3(128), kargs, tv->smem, stream));
+            PHB_CUDA(cudaLaunchKernel(tv->chain_func, dim3(unsigned((n_pairs + 63) / 64)), dim3(64), kargs, 0, stream));
+            k->launches += 2;
+            snprintf(k->last_name, sizeof k->last_name, "transfer_rows_kernel<float,M=%d> x %lld segments + chain_transfer_kernel",
+                     tv->M, (long long)n_seg);
+            return PHB_OK;
         }
     }
+
+    return kNotTaken;
+}
+
+// (4) The throughput kernel: persistent grid, checkpoints + recompute for the gradient.  `fixed` pins the
+// kernel variant (precision escalation), nullptr lets pick_variant choose.
+int launch_throughput_kernel(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream, const Variant *fixed) {
+    const int64_t n_pairs = a.B * a.S;  // upper bound when a sub-list is given
     const Variant *v = fixed ? fixed : pick_variant(k, grad, n_pairs);
     if (!v) return fail(PHB_E_INVALID, "no kernel variant for M=%d, threads_per_pair=%d", k->M, k->force_T);
     const int pairs_per_cta = v->NT / v->T;
@@ -500,6 +512,25 @@ int launch_one(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream,
                  v->M / v->T, v->T, v->K, v->grad ? "grad" : "fwd", v->NT);
     return PHB_OK;
 }
+
+// One evaluation on `stream` over the whole minibatch or over the sub-list in `a`.
+int launch_one(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream, const Variant *fixed) {
+    // tuning knobs for experiments: PHB_STORE_ALL / PHB_PARALLEL_IN_TIME = 0 / 1 override the modes set through the API
+    const char *sa_env = getenv("PHB_STORE_ALL");
+    const int sa_mode = sa_env ? atoi(sa_env) : k->store_all_mode;
+    const char *pit_env = getenv("PHB_PARALLEL_IN_TIME");
+    const int pit_mode = pit_env ? atoi(pit_env) : k->parallel_in_time;
+    const bool free_choice = !fixed && !k->dbl && k->force_T == 0;
+    int rc = kNotTaken;
+    if (free_choice && grad && pit_mode != 0 && sa_mode != 0 && a.s_list == nullptr)
+        rc = try_parallel_in_time_gradient(k, a, stream, pit_mode);
+    if (rc == kNotTaken && free_choice && grad && sa_mode != 0) rc = try_store_all(k, a, stream, sa_mode);
+    if (rc == kNotTaken && free_choice && !grad && pit_mode != 0 && a.s_list == nullptr)
+        rc = try_parallel_in_time_forward(k, a, stream, pit_mode);
+    if (rc == kNotTaken) rc = launch_throughput_kernel(k, a, grad, stream, fixed);
+    return rc;
+}
+
 
 // Launch on `stream`; all pointers in `a` are device pointers except the ones filled in here.
 int launch(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream) {
