@@ -105,10 +105,15 @@ int phb_set_store_all(phb_kernel *k, int mode);
  * through every segment (its transfer operator: M x the forward arithmetic, M x segments x the
  * parallelism) and the operators are chained in float64 - forwards for the log-likelihood and the
  * forward vectors at the segment boundaries, backwards for the adjoint vectors there, after which the
- * gradient passes run over all segments independently.  Exact - no burn-in approximation.
- * mode: -1 = automatic (float objects, M <= 16; forward-only while pairs * M is below a quarter of the
- * resident threads and segments stay >= 4096 sites; gradient while pairs * M is below 0.3 of them),
- * 0 = never, 1 = whenever possible (ignored while threads_per_pair is forced). */
+ * gradient passes run over all segments independently.  Exact - no burn-in approximation.  For somewhat
+ * larger minibatches (the reference's S = 5: 2 500 pairs) the operators cost more than they save; there
+ * the boundary vectors come from two plain sequential sweeps running side by side (forward recursion,
+ * adjoint recursion without gradient bookkeeping), followed by the same segment passes (any M).
+ * mode: -1 = automatic (float objects; operators for M <= 16: forward-only while pairs * M is below a
+ * quarter of the resident threads and segments stay >= 4096 sites, gradient while pairs * M is below 0.3
+ * of them; else sweeps for gradients while they still split into >= 6 segments of >= 1024 sites),
+ * 0 = never, 1 = operators whenever possible, 2 = sweeps whenever possible (ignored while
+ * threads_per_pair is forced). */
 int phb_set_parallel_in_time(phb_kernel *k, int mode);
 
 /* PRECISION ESCALATION (single-precision objects, gradient path).  Through a long run of identical

@@ -197,7 +197,8 @@ const Variant *escalation_variant(int M) {
 struct StoreAllVariant {
     int M, T, MT, NT;
     const void *func;
-    const void *seg_func;  // segment mode (parallel-in-time gradient)
+    const void *seg_func;    // segment mode (parallel-in-time gradient)
+    const void *sweep_func;  // forward / adjoint-only sweeps that leave the boundary vectors
     size_t smem;
 };
 template <int MT, int T, int NT, int MINB> StoreAllVariant make_storeall() {
@@ -208,6 +209,7 @@ template <int MT, int T, int NT, int MINB> StoreAllVariant make_storeall() {
     v.NT = NT;
     v.func = reinterpret_cast<const void *>(&phb::psmc_loglik_storeall_kernel<float, MT, T, NT, MINB>);
     v.seg_func = reinterpret_cast<const void *>(&phb::psmc_loglik_storeall_kernel<float, MT, T, NT, MINB, true>);
+    v.sweep_func = reinterpret_cast<const void *>(&phb::boundary_sweep_kernel<float, MT, T, NT, MINB>);
     v.smem = phb::smem_bytes<float, MT, 8, NT, false>();
     return v;
 }
@@ -386,6 +388,72 @@ int try_parallel_in_time_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaS
     return kNotTaken;
 }
 
+// (1b) Gradient of a small minibatch with too many pairs for the operators (the reference's S = 5: 2 500
+// pairs): the boundary vectors come from two sequential sweeps side by side (boundary_sweep_kernel), then
+// the same segment passes.  Any M.  Latency regime only (the bound of the store-all path).
+int try_two_sweep_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t stream, int pit_mode) {
+    const int64_t n_pairs = a.B * a.S;
+    const StoreAllVariant *sv = nullptr;
+    for (const StoreAllVariant &c : storeall_variants())
+        if (c.M == k->M) sv = &c;
+    if (!sv) return kNotTaken;
+    if (pit_mode != 2 && n_pairs * sv->T > int64_t(k->num_sms) * 330) return kNotTaken;
+    const int64_t min_seg = pit_mode == 2 ? 64 : 1024;
+    const int64_t capacity = int64_t(k->num_sms) * 512;  // resident threads of the store-all kernel
+    int64_t n_seg = std::min(std::max<int64_t>(capacity / (n_pairs * sv->T), 2), a.L / min_seg);
+    if (const char *g_env = getenv("PHB_PIT_SEGMENTS")) n_seg = std::min<int64_t>(atoi(g_env), a.L / 64);  // experiments
+    // measured at B = 500, L = 50 000, M = 16 (profiles/r01_probe_parallel_in_time.log): S = 3 / 5 chunks
+    // (12 / 7 segments) 8.4 / 11.1 ms against 13.6 ms for the store-all kernel alone; S = 8 (4 segments) no gain
+    if (n_seg < (pit_mode == 2 ? 2 : 6)) return kNotTaken;
+    const int64_t seg_len = ((a.L + n_seg - 1) / n_seg + 15) / 16 * 16;
+    n_seg = (a.L + seg_len - 1) / seg_len;
+    if (n_seg < 2) return kNotTaken;
+    const int M = k->M;
+    const int pairs_per_cta = sv->NT / sv->T;
+    const int64_t seg_ctas = (n_pairs + pairs_per_cta - 1) / pairs_per_cta;
+    const int64_t grid_full = seg_ctas * n_seg;
+    const int64_t warps = grid_full * (sv->NT / 32);
+    const size_t x_bytes = size_t(warps) * size_t(seg_len) * sv->MT * 32 * sizeof(float);
+    const size_t s_bytes = size_t(warps) * size_t((seg_len + phb::kNorm - 1) / phb::kNorm) * 32 * sizeof(float);
+    if (!storeall_scratch_fits(k, x_bytes, s_bytes)) return kNotTaken;
+    int rc;
+    if ((rc = k->bnd_alpha.reserve(size_t(n_pairs) * (n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
+    if ((rc = k->bnd_beta.reserve(size_t(n_pairs) * (n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
+    if ((rc = k->seg_dlog.reserve(size_t(n_pairs) * n_seg * 7 * M * sizeof(float))) != PHB_OK) return rc;
+    if ((rc = k->xall.reserve(x_bytes)) != PHB_OK) return rc;
+    if ((rc = k->sall.reserve(s_bytes)) != PHB_OK) return rc;
+    if ((rc = k->gacc.reserve(size_t(grid_full) * sv->NT * 6 * sv->MT * sizeof(double))) != PHB_OK) return rc;
+    for (const void *f : {sv->sweep_func, sv->seg_func}) {
+        if (k->occupancy.find(f) == k->occupancy.end()) {
+            PHB_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sv->smem)));
+            k->occupancy.emplace(f, 1);
+        }
+    }
+    phb::KernelArgs sa = a;
+    sa.err_flag = k->d_err;
+    sa.xall = k->xall.ptr;
+    sa.sall = k->sall.ptr;
+    sa.gacc = static_cast<double *>(k->gacc.ptr);
+    sa.seg_count = n_seg;
+    sa.seg_len = seg_len;
+    sa.bnd_alpha = k->bnd_alpha.ptr;
+    sa.bnd_beta = k->bnd_beta.ptr;
+    sa.seg_dlog = k->seg_dlog.ptr;
+    sa.seg_ctas = seg_ctas;
+    sa.n_groups = grid_full;
+    void *kargs[] = {&sa};
+    PHB_CUDA(cudaLaunchKernel(sv->sweep_func, dim3(unsigned(2 * seg_ctas)), dim3(sv->NT), kargs, sv->smem, stream));
+    PHB_CUDA(cudaLaunchKernel(sv->seg_func, dim3(unsigned(grid_full)), dim3(sv->NT), kargs, sv->smem, stream));
+    const int64_t n_out = n_pairs * 7 * M;
+    phb::sum_segments_kernel<float><<<unsigned((n_out + 255) / 256), 256, 0, stream>>>(
+        static_cast<const float *>(k->seg_dlog.ptr), n_pairs, n_seg, M, static_cast<float *>(a.dlog), a.out_mode);
+    PHB_CUDA(cudaGetLastError());
+    k->launches += 3;
+    snprintf(k->last_name, sizeof k->last_name, "boundary_sweep_kernel<float,MT=%d,T=%d> + storeall_kernel<SEG> x %lld segments", sv->MT,
+             sv->T, (long long)n_seg);
+    return PHB_OK;
+}
+
 // (2) Gradient of a small minibatch: the store-all kernel (two dependent passes instead of three).
 int try_store_all(phb_kernel *k, phb::KernelArgs a, cudaStream_t stream, int sa_mode) {
     const int64_t n_pairs = a.B * a.S;  // upper bound when a sub-list is given
@@ -522,8 +590,10 @@ int launch_one(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream,
     const int pit_mode = pit_env ? atoi(pit_env) : k->parallel_in_time;
     const bool free_choice = !fixed && !k->dbl && k->force_T == 0;
     int rc = kNotTaken;
-    if (free_choice && grad && pit_mode != 0 && sa_mode != 0 && a.s_list == nullptr)
+    if (free_choice && grad && pit_mode != 0 && pit_mode != 2 && sa_mode != 0 && a.s_list == nullptr)
         rc = try_parallel_in_time_gradient(k, a, stream, pit_mode);
+    if (rc == kNotTaken && free_choice && grad && pit_mode != 0 && pit_mode != 1 && sa_mode != 0 && a.s_list == nullptr)
+        rc = try_two_sweep_gradient(k, a, stream, pit_mode);
     if (rc == kNotTaken && free_choice && grad && sa_mode != 0) rc = try_store_all(k, a, stream, sa_mode);
     if (rc == kNotTaken && free_choice && !grad && pit_mode != 0 && a.s_list == nullptr)
         rc = try_parallel_in_time_forward(k, a, stream, pit_mode);
@@ -819,7 +889,8 @@ int64_t phb_num_escalated_rows(const phb_kernel *k) { return k ? k->n_flagged : 
 
 int phb_set_parallel_in_time(phb_kernel *k, int mode) {
     if (int rc = check_handle(k)) return rc;
-    if (mode < -1 || mode > 1) return fail(PHB_E_INVALID, "parallel-in-time mode must be -1 (auto), 0 (off) or 1 (on)");
+    if (mode < -1 || mode > 2)
+        return fail(PHB_E_INVALID, "parallel-in-time mode must be -1 (auto), 0 (off), 1 (operators) or 2 (sweeps)");
     k->parallel_in_time = mode;
     return PHB_OK;
 }

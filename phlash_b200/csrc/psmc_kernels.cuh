@@ -1267,6 +1267,177 @@ __global__ void sum_segments_kernel(const F *__restrict__ seg_dlog, int64_t n_pa
     dlog[i] = out_mode ? F(double(dlog[i]) - acc) : F(acc);
 }
 
+// For MORE pairs than the operators pay for (the reference's default minibatch of 5 chunks: 2 500
+// pairs, still far too few to fill the GPU) the boundary vectors come from two SEQUENTIAL sweeps that run
+// side by side instead: even CTAs run the plain forward recursion and leave the forward vector at every
+// segment boundary (and the log-likelihood), odd CTAs run the adjoint recursion without any gradient
+// bookkeeping, beta <- A (emis .* beta), from the end of the chunk and leave the adjoint vectors.  Each
+// is one dependent pass of the cheap kind (~80 ns per site); the expensive gradient passes then run over
+// all segments at once (store-all kernel, SEG mode) as in the operator variant.
+template <typename F, int MT, int T, int NT>
+__device__ __forceinline__ void adjoint_only_site(F (&beta)[MT], const Params<F, MT> &p, const EmisTable<F, MT, NT> &et, int ob, int sub) {
+    F w[MT];
+    et.get(ob, w);
+#pragma unroll
+    for (int k = 0; k < MT; ++k) w[k] *= beta[k];
+    F q_run = F(0), b_run = F(0);
+    if constexpr (T > 1) {
+        F tq[2] = {F(0), F(0)}, tb[2] = {F(0), F(0)};
+#pragma unroll
+        for (int k = 0; k < MT; ++k) {
+            tq[k & 1] = fma(p.v[k], w[k], tq[k & 1]);
+            tb[k & 1] = fma(p.b[k], w[k], tb[k & 1]);
+        }
+        q_run = lanes_after<F, T>(tq[0] + tq[1], sub);
+        b_run = lanes_before<F, T>(tb[0] + tb[1], sub);
+    }
+    F tailq[MT];
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        const int k = i, j = MT - 1 - i;
+        beta[k] = fma(p.d[k], w[k], b_run);
+        b_run = fma(p.b[k], w[k], b_run);
+        tailq[j] = q_run;
+        q_run = fma(p.v[j], w[j], q_run);
+    }
+#pragma unroll
+    for (int k = 0; k < MT; ++k) beta[k] = fma(p.u[k], tailq[k], beta[k]);
+}
+
+template <typename F, int MT, int T, int NT, int MINB>
+__global__ void __maxnreg__(max_regs(NT, MINB)) boundary_sweep_kernel(const KernelArgs a) {
+    constexpr int M = MT * T;
+    constexpr int PW = 32 / T;
+    constexpr int kWarps = NT / 32;
+    constexpr int W = Vec<F>::W;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t smem0 = smem_base_addr();
+    EmisTable<F, MT, NT> et;
+    et.ones = smem0;
+    et.base = smem0 + ((EmisTable<F, MT, NT>::kOnesRow ? 0 : 1) + threadIdx.x) * 16;
+    if constexpr (!EmisTable<F, MT, NT>::kOnesRow) {
+        if (threadIdx.x == 0) {
+            F one[W];
+#pragma unroll
+            for (int i = 0; i < W; ++i) one[i] = F(1);
+            sts_word(smem0, one);
+        }
+        __syncthreads();
+    }
+    const int sub = lane % T;
+    const int lp = lane / T;
+    const bool backwards = (blockIdx.x & 1) != 0;
+    const int64_t cta = blockIdx.x >> 1;
+    const int64_t n_pairs = a.B * a.S;
+    const int64_t pair_raw = (cta * kWarps + warp) * PW + lp;
+    const bool writer = pair_raw < n_pairs;
+    const int64_t pair = writer ? pair_raw : n_pairs - 1;
+    const int64_t pb = pair / a.S, ps = pair % a.S;
+    const F *par = static_cast<const F *>(a.params6) + pb * a.pstride_b + ps * a.pstride_s + sub * MT;
+    Params<F, MT> p;
+    p.load(par, M);
+    et.fill(par, M);
+    PartnerCoef<F, MT, T, false> pc;
+    pc.init(p, sub);
+    int64_t row = a.inds[ps];
+    const bool bad_row = row < 0 || row >= a.n_rows;
+    if (bad_row) row = 0;
+    const int8_t *obs = a.data + row * a.pitch;
+    const int64_t G = a.seg_count;
+    const int64_t n_blocks = (a.L + kNorm - 1) / kNorm;
+    F *bnd = static_cast<F *>(const_cast<void *>(backwards ? a.bnd_beta : a.bnd_alpha)) + pair * (G + 1) * M + sub * MT;
+
+    if (!backwards) {
+        const F *pi_p = static_cast<const F *>(a.pi) + pb * a.pistride_b + ps * a.pistride_s + sub * MT;
+        F x[MT];
+#pragma unroll
+        for (int k = 0; k < MT; ++k) x[k] = pi_p[k];
+        double ll = 0.0;
+        F acc;
+        {
+            const F tot = pair_sum<F, MT, T>(x);
+            acc = log2_of<F>(tot);
+#pragma unroll
+            for (int k = 0; k < MT; ++k) {
+                x[k] = x[k] / tot;
+                if (writer) bnd[k] = x[k];
+            }
+        }
+        uint32_t blk_next = __ldg(reinterpret_cast<const unsigned int *>(obs));
+        int64_t next_boundary = a.seg_len;  // (a running counter: no 64-bit division in the loop)
+        for (int64_t blk_i = 0; blk_i < n_blocks; ++blk_i) {
+            const int64_t t0 = blk_i * kNorm;
+            const uint32_t blk = blk_next;
+            if (blk_i + 1 < n_blocks) blk_next = __ldg(reinterpret_cast<const unsigned int *>(obs + t0 + kNorm));
+            const int len = int(min(int64_t(kNorm), a.L - t0));
+#pragma unroll
+            for (int j = 0; j < kNorm; ++j)
+                if (j < len) forward_site<F, MT, T, false, NT>(x, p, pc, et, ObsWords<8>::byte_of(blk, j), sub);
+            const F tot = pair_sum<F, MT, T>(x);
+            const F inv = fast_rcp<F>(tot);
+#pragma unroll
+            for (int k = 0; k < MT; ++k) x[k] *= inv;
+            acc += log2_of<F>(tot);
+            if ((blk_i & 3) == 3) {
+                ll += double(acc);
+                acc = F(0);
+            }
+            if (t0 + kNorm == next_boundary) {
+                // the vector entering the next segment (approximately normalised: good enough, the
+                // segment kernel rescales)
+                bnd += M;
+                next_boundary += a.seg_len;
+                if (t0 + kNorm < a.L && writer) {
+#pragma unroll
+                    for (int k = 0; k < MT; ++k) bnd[k] = x[k];
+                }
+            }
+        }
+        // the reciprocal above is approximate: the last total is not exactly 1
+        ll = (ll + double(acc) + double(log2_of<F>(pair_sum<F, MT, T>(x)))) * 0.69314718055994530942;
+        if (!(ll == ll) || ll > 1e300 || ll < -1e300) {
+            if (sub == 0) atomicOr(a.err_flag, 2);
+        }
+        if (bad_row) {
+            if (sub == 0) atomicOr(a.err_flag, 1);
+            ll = __longlong_as_double(0x7ff8000000000000LL);
+        }
+        if (writer && sub == 0) a.ll[pair] = a.out_mode ? a.ll[pair] - ll : ll;
+    } else {
+        F beta[MT];
+#pragma unroll
+        for (int k = 0; k < MT; ++k) {
+            beta[k] = F(1);
+            if (writer) bnd[G * M + k] = F(1);  // behind the last segment: the end of the chunk
+        }
+        uint32_t blk_next = __ldg(reinterpret_cast<const unsigned int *>(obs + (n_blocks - 1) * kNorm));
+        int64_t next_boundary = (G - 1) * a.seg_len;  // start of the last segment
+        bnd += G * M;
+        for (int64_t blk_i = n_blocks - 1; blk_i >= 0; --blk_i) {
+            const int64_t t0 = blk_i * kNorm;
+            const uint32_t blk = blk_next;
+            if (blk_i > 0) blk_next = __ldg(reinterpret_cast<const unsigned int *>(obs + t0 - kNorm));
+            const int len = int(min(int64_t(kNorm), a.L - t0));
+#pragma unroll
+            for (int j = kNorm - 1; j >= 0; --j)
+                if (j < len) adjoint_only_site<F, MT, T, NT>(beta, p, et, ObsWords<8>::byte_of(blk, j), sub);
+            const F inv = fast_rcp<F>(pair_sum<F, MT, T>(beta));
+#pragma unroll
+            for (int k = 0; k < MT; ++k) beta[k] *= inv;
+            if (t0 == next_boundary) {
+                // the adjoint vector behind the previous segment (any scale)
+                bnd -= M;
+                next_boundary -= a.seg_len;
+                if (t0 > 0 && writer) {
+#pragma unroll
+                    for (int k = 0; k < MT; ++k) bnd[k] = beta[k];
+                }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Precision escalation for single-precision kernel objects.
 //

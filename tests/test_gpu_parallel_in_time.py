@@ -158,7 +158,7 @@ def test_gradient_dispatch_and_warmup_composition(golden):
     kern.evaluate(pa, inds, True)
     assert "segments" in kern.last_kernel_name              # 6 pairs x 12 100 sites
     kern.evaluate(np.broadcast_to(pps[:1, None], (1, 4000, 7, 16)).copy(), np.zeros(4000, dtype=np.int64), True)
-    assert "segments" not in kern.last_kernel_name          # 4000 pairs: not worth M x the forward work
+    assert "transfer_rows" not in kern.last_kernel_name     # 4000 pairs: not worth M x the forward work
     kern.set_parallel_in_time(0)
     ll_s, dlog_s = kern.evaluate_warmup(pps, inds, ov, True)
     np.testing.assert_allclose(ll, ll_s, rtol=1e-6)
@@ -199,3 +199,42 @@ def test_per_pair_parameter_blocks_and_subtracting_launch():
     np.testing.assert_allclose(got_ll, seq_ll, rtol=1e-6)
     scale = np.abs(seq_dlog).max(axis=-1, keepdims=True)
     assert (np.abs(got_dlog - seq_dlog) <= GRAD_RTOL * (np.abs(seq_dlog) + 1e-3 * scale) + 2e-6 * scale).all()
+
+
+@pytest.mark.parametrize("M", [4, 8, 16, 32, 64])
+@pytest.mark.parametrize("L", [150, 3001, 20_000])
+def test_two_sweep_gradient_matches_oracle(M, L):
+    """Boundary vectors from the forward / adjoint-only sweeps (mode 2), segment passes, summed partial
+    gradients - against the fp64 oracle and the sequential kernels; any M."""
+    from test_gpu_parity import GRAD_RTOL, grad_close, oracle_eval
+
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    data = rows_with_missing(3, L, seed=3 * M + L)
+    pps, _, _ = orc.synth_particles(M, 5, seed=8)
+    inds = np.array([2, 0, 1, 2])
+    pa = np.broadcast_to(pps[:, None], (5, len(inds), 7, M)).copy()
+    ref_ll, ref_dlog = oracle_eval(data, inds, pa)
+    kern = _PSMCKernelBase(M, data)
+    kern.set_parallel_in_time(2)
+    ll, dlog = kern.evaluate(pa, inds, True)
+    assert "boundary_sweep" in kern.last_kernel_name
+    np.testing.assert_allclose(ll, ref_ll, rtol=LL_RTOL)
+    grad_close(dlog, ref_dlog, GRAD_RTOL, f"two sweeps, M={M}, L={L}")
+    kern.set_parallel_in_time(0)
+    ll_s, dlog_s = kern.evaluate(pa, inds, True)
+    np.testing.assert_allclose(ll, ll_s, rtol=2e-6)
+    grad_close(dlog, dlog_s, 2e-5, "vs sequential kernel")
+    assert np.all(dlog[:, :, 0, -1] == 0) and np.all(dlog[:, :, 2, -1] == 0) and np.all(dlog[:, :, 3, 0] == 0)
+
+
+def test_two_sweep_is_chosen_between_operators_and_store_all():
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    data = rows_with_missing(4, 12_000, seed=5)
+    pps, _, _ = orc.synth_particles(16, 1, seed=4)
+    kern = _PSMCKernelBase(16, data)
+    for n_chunks, expect in ((1, "transfer_rows"), (2500, "boundary_sweep"), (40_000, "psmc_loglik_kernel")):
+        pa = np.broadcast_to(pps[:1, None], (1, n_chunks, 7, 16)).copy()
+        kern.evaluate(pa, np.zeros(n_chunks, dtype=np.int64), True)
+        assert expect in kern.last_kernel_name, (n_chunks, kern.last_kernel_name)
