@@ -107,7 +107,7 @@ struct phb_kernel {
 
 namespace {
 
-template <typename F, int MT, int T, int K, bool GRAD, int NT, int MINB, typename IO = F> Variant make_variant() {
+template <typename F, int MT, int T, int K, bool GRAD, int NT, int MINB, typename IO = F, bool SEG = false> Variant make_variant() {
     Variant v;
     v.M = MT * T;
     v.T = T;
@@ -115,7 +115,7 @@ template <typename F, int MT, int T, int K, bool GRAD, int NT, int MINB, typenam
     v.NT = NT;
     v.dbl = sizeof(F) == 8;
     v.grad = GRAD;
-    v.func = reinterpret_cast<const void *>(&phb::psmc_loglik_kernel<F, MT, T, K, GRAD, NT, MINB, IO>);
+    v.func = reinterpret_cast<const void *>(&phb::psmc_loglik_kernel<F, MT, T, K, GRAD, NT, MINB, IO, SEG>);
     v.smem = phb::smem_bytes<F, MT, K, NT, GRAD>();
     v.ckpt_bytes_per_warp = [](int64_t L) { return phb::ckpt_bytes_per_warp<F, MT, K>(L); };
     return v;
@@ -187,6 +187,21 @@ const Variant *escalation_variant(int M) {
         make_variant<double, 4, 4, 8, true, 128, 2, float>(),   // M = 16
         make_variant<double, 4, 8, 8, true, 128, 2, float>(),   // M = 32
         make_variant<double, 4, 16, 8, true, 128, 2, float>(),  // M = 64
+    };
+    for (const Variant &v : table)
+        if (v.M == M) return &v;
+    return nullptr;
+}
+
+// Segment-mode builds of the throughput gradient kernel (segment passes of the two-sweep gradient once
+// the segments of all pairs fill the GPU): the fastest lane layout of every M.
+const Variant *segment_variant(int M) {
+    static const std::vector<Variant> table = {
+        make_variant<float, 4, 1, 16, true, 128, 4, float, true>(),   // M = 4
+        make_variant<float, 8, 1, 16, true, 128, 3, float, true>(),   // M = 8
+        make_variant<float, 16, 1, 8, true, 128, 2, float, true>(),   // M = 16
+        make_variant<float, 16, 2, 8, true, 128, 2, float, true>(),   // M = 32
+        make_variant<float, 16, 4, 8, true, 128, 2, float, true>(),   // M = 64
     };
     for (const Variant &v : table)
         if (v.M == M) return &v;
@@ -396,43 +411,51 @@ int try_two_sweep_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t
     const StoreAllVariant *sv = nullptr;
     for (const StoreAllVariant &c : storeall_variants())
         if (c.M == k->M) sv = &c;
-    if (!sv) return kNotTaken;
+    const Variant *tv = segment_variant(k->M);
+    if (!sv || !tv) return kNotTaken;
     if (pit_mode != 2 && n_pairs * sv->T > int64_t(k->num_sms) * 330) return kNotTaken;
+    const int M = k->M;
+    // Segment passes on the throughput kernel (thread per pair at M = 16: 1.7 x the throughput of the
+    // store-all layout): as many segments as keep every group resident at once.
+    int occ = 0;
+    {
+        auto it = k->occupancy.find(tv->func);
+        if (it == k->occupancy.end()) {
+            PHB_CUDA(cudaFuncSetAttribute(tv->func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tv->smem)));
+            PHB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tv->func, tv->NT, tv->smem));
+            k->occupancy.emplace(tv->func, occ);
+        } else {
+            occ = it->second;
+        }
+    }
+    if (occ < 1) return kNotTaken;
+    const int64_t resident = int64_t(occ) * k->num_sms;
+    const int pairs_per_group = tv->NT / tv->T;
+    const int64_t seg_ctas = (n_pairs + pairs_per_group - 1) / pairs_per_group;  // groups per segment
     const int64_t min_seg = pit_mode == 2 ? 64 : 1024;
-    const int64_t capacity = int64_t(k->num_sms) * 512;  // resident threads of the store-all kernel
-    int64_t n_seg = std::min(std::max<int64_t>(capacity / (n_pairs * sv->T), 2), a.L / min_seg);
+    int64_t n_seg = std::min(std::max<int64_t>(resident / seg_ctas, 2), a.L / min_seg);
     if (const char *g_env = getenv("PHB_PIT_SEGMENTS")) n_seg = std::min<int64_t>(atoi(g_env), a.L / 64);  // experiments
-    // measured at B = 500, L = 50 000, M = 16 (profiles/r01_probe_parallel_in_time.log): S = 3 / 5 chunks
-    // (12 / 7 segments) 8.4 / 11.1 ms against 13.6 ms for the store-all kernel alone; S = 8 (4 segments) no gain
+    // measured at B = 500, L = 50 000, M = 16 (profiles/r01_probe_parallel_in_time.log)
     if (n_seg < (pit_mode == 2 ? 2 : 6)) return kNotTaken;
     const int64_t seg_len = ((a.L + n_seg - 1) / n_seg + 15) / 16 * 16;
     n_seg = (a.L + seg_len - 1) / seg_len;
     if (n_seg < 2) return kNotTaken;
-    const int M = k->M;
-    const int pairs_per_cta = sv->NT / sv->T;
-    const int64_t seg_ctas = (n_pairs + pairs_per_cta - 1) / pairs_per_cta;
-    const int64_t grid_full = seg_ctas * n_seg;
-    const int64_t warps = grid_full * (sv->NT / 32);
-    const size_t x_bytes = size_t(warps) * size_t(seg_len) * sv->MT * 32 * sizeof(float);
-    const size_t s_bytes = size_t(warps) * size_t((seg_len + phb::kNorm - 1) / phb::kNorm) * 32 * sizeof(float);
-    if (!storeall_scratch_fits(k, x_bytes, s_bytes)) return kNotTaken;
+    const int64_t n_groups = seg_ctas * n_seg;
+    const int64_t grid = std::min<int64_t>(n_groups, resident);
+    const int64_t sweep_ctas = (n_pairs + sv->NT / sv->T - 1) / (sv->NT / sv->T);
     int rc;
     if ((rc = k->bnd_alpha.reserve(size_t(n_pairs) * (n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
     if ((rc = k->bnd_beta.reserve(size_t(n_pairs) * (n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
     if ((rc = k->seg_dlog.reserve(size_t(n_pairs) * n_seg * 7 * M * sizeof(float))) != PHB_OK) return rc;
-    if ((rc = k->xall.reserve(x_bytes)) != PHB_OK) return rc;
-    if ((rc = k->sall.reserve(s_bytes)) != PHB_OK) return rc;
-    if ((rc = k->gacc.reserve(size_t(grid_full) * sv->NT * 6 * sv->MT * sizeof(double))) != PHB_OK) return rc;
-    for (const void *f : {sv->sweep_func, sv->seg_func}) {
-        if (k->occupancy.find(f) == k->occupancy.end()) {
-            PHB_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sv->smem)));
-            k->occupancy.emplace(f, 1);
-        }
+    if ((rc = k->ckpt.reserve(size_t(grid) * (tv->NT / 32) * size_t(tv->ckpt_bytes_per_warp(seg_len)))) != PHB_OK) return rc;
+    if ((rc = k->gacc.reserve(size_t(grid) * tv->NT * 6 * (tv->M / tv->T) * sizeof(double))) != PHB_OK) return rc;
+    if (k->occupancy.find(sv->sweep_func) == k->occupancy.end()) {
+        PHB_CUDA(cudaFuncSetAttribute(sv->sweep_func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sv->smem)));
+        k->occupancy.emplace(sv->sweep_func, 1);
     }
     phb::KernelArgs sa = a;
     sa.err_flag = k->d_err;
-    sa.xall = k->xall.ptr;
-    sa.sall = k->sall.ptr;
+    sa.ckpt = k->ckpt.ptr;
     sa.gacc = static_cast<double *>(k->gacc.ptr);
     sa.seg_count = n_seg;
     sa.seg_len = seg_len;
@@ -440,17 +463,17 @@ int try_two_sweep_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t
     sa.bnd_beta = k->bnd_beta.ptr;
     sa.seg_dlog = k->seg_dlog.ptr;
     sa.seg_ctas = seg_ctas;
-    sa.n_groups = grid_full;
+    sa.n_groups = n_groups;
     void *kargs[] = {&sa};
-    PHB_CUDA(cudaLaunchKernel(sv->sweep_func, dim3(unsigned(2 * seg_ctas)), dim3(sv->NT), kargs, sv->smem, stream));
-    PHB_CUDA(cudaLaunchKernel(sv->seg_func, dim3(unsigned(grid_full)), dim3(sv->NT), kargs, sv->smem, stream));
+    PHB_CUDA(cudaLaunchKernel(sv->sweep_func, dim3(unsigned(2 * sweep_ctas)), dim3(sv->NT), kargs, sv->smem, stream));
+    PHB_CUDA(cudaLaunchKernel(tv->func, dim3(unsigned(grid)), dim3(tv->NT), kargs, tv->smem, stream));
     const int64_t n_out = n_pairs * 7 * M;
     phb::sum_segments_kernel<float><<<unsigned((n_out + 255) / 256), 256, 0, stream>>>(
         static_cast<const float *>(k->seg_dlog.ptr), n_pairs, n_seg, M, static_cast<float *>(a.dlog), a.out_mode);
     PHB_CUDA(cudaGetLastError());
     k->launches += 3;
-    snprintf(k->last_name, sizeof k->last_name, "boundary_sweep_kernel<float,MT=%d,T=%d> + storeall_kernel<SEG> x %lld segments", sv->MT,
-             sv->T, (long long)n_seg);
+    snprintf(k->last_name, sizeof k->last_name, "boundary_sweep_kernel<float,MT=%d,T=%d> + psmc_loglik_kernel<SEG,MT=%d,T=%d> x %lld segments",
+             sv->MT, sv->T, tv->M / tv->T, tv->T, (long long)n_seg);
     return PHB_OK;
 }
 

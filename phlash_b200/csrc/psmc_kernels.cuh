@@ -554,7 +554,10 @@ constexpr int max_regs(int nt, int minb) {
 
 // F is the arithmetic type, IO the type of the parameter / gradient buffers (IO = float with
 // F = double is the precision-escalation variant of a single-precision kernel object).
-template <typename F, int MT, int T, int K, bool GRAD, int NT, int MINB, typename IO = F>
+// SEG = segment mode of the gradient kernel (parallel-in-time gradient of larger minibatches, see
+// boundary_sweep_kernel): group grp scores segment grp / seg_ctas of the chunks it covers, started from
+// bnd_alpha, closed with bnd_beta, partial gradient to seg_dlog.
+template <typename F, int MT, int T, int K, bool GRAD, int NT, int MINB, typename IO = F, bool SEG = false>
 __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelArgs a) {
     constexpr int kThreads = NT;
     constexpr int kWarps = NT / 32;
@@ -599,14 +602,15 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
 
     const int sub = lane % T;
     const int lp = lane / T;
+    static_assert(!SEG || (GRAD && sizeof(IO) == sizeof(F)), "segment mode: gradient kernel, plain buffers");
     const int64_t s_eff = listed_chunks(a);
-    const int64_t n_pairs = a.B * s_eff;
-    const int64_t n_groups = a.s_list ? (n_pairs + kWarps * PW - 1) / (kWarps * PW) : a.n_groups;
-    const int64_t n_seg = (a.L + K - 1) / K;
+    const int64_t n_pairs = SEG ? a.B * a.S : a.B * s_eff;
+    const int64_t n_groups = (!SEG && a.s_list) ? (n_pairs + kWarps * PW - 1) / (kWarps * PW) : a.n_groups;
+    const int64_t L_max = SEG ? a.seg_len : a.L;
     const int64_t warp_slot = int64_t(blockIdx.x) * kWarps + warp;
     const IO *params6 = static_cast<const IO *>(a.params6);
     const IO *pi_g = static_cast<const IO *>(a.pi);
-    V *ck = GRAD ? reinterpret_cast<V *>(static_cast<char *>(a.ckpt) + warp_slot * ckpt_bytes_per_warp<F, MT, K>(a.L)) + lane
+    V *ck = GRAD ? reinterpret_cast<V *>(static_cast<char *>(a.ckpt) + warp_slot * ckpt_bytes_per_warp<F, MT, K>(L_max)) + lane
                  : nullptr;
     constexpr int kFlushSegs = kFlushSites / K;
     static_assert((kFlushSegs & (kFlushSegs - 1)) == 0, "flush cadence must be a power of two");
@@ -618,10 +622,24 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
     // the work list is walked per CTA (not per warp) so that every loop bound below is provably
     // uniform and the shuffles need no reconvergence guards
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-        const int64_t pair_raw = (grp * kWarps + warp) * PW + lp;
+        // SEG: group -> (segment of the chunk, group within the segment); L = sites of that segment
+        const int64_t pseg = SEG ? grp / a.seg_ctas : 0;
+        const int64_t L = SEG ? min(a.seg_len, a.L - pseg * a.seg_len) : a.L;
+        const int64_t n_seg = (L + K - 1) / K;
+        const int64_t pair_raw = ((SEG ? grp % a.seg_ctas : grp) * kWarps + warp) * PW + lp;
         const bool writer = pair_raw < n_pairs;
-        const PairIndex pidx = pair_index(a, writer ? pair_raw : n_pairs - 1, s_eff);  // idle lanes shadow the last pair
-        const int64_t pb = pidx.b, ps = pidx.s, pair = pidx.out;
+        int64_t pb, ps, pair, chunk_pair = 0;
+        if constexpr (SEG) {
+            chunk_pair = writer ? pair_raw : n_pairs - 1;
+            pb = chunk_pair / a.S;
+            ps = chunk_pair % a.S;
+            pair = chunk_pair * a.seg_count + pseg;  // slot in seg_dlog
+        } else {
+            const PairIndex pidx = pair_index(a, writer ? pair_raw : n_pairs - 1, s_eff);  // idle lanes shadow the last pair
+            pb = pidx.b;
+            ps = pidx.s;
+            pair = pidx.out;
+        }
         Params<F, MT> p;
         p.load(params6 + pb * a.pstride_b + ps * a.pstride_s + sub * MT, M);
         et.fill(params6 + pb * a.pstride_b + ps * a.pstride_s + sub * MT, M);
@@ -633,8 +651,9 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
             if (sub == 0) atomicOr(a.err_flag, 1);  // reported by phb_sync(); this pair's ll becomes NaN
             row = 0;
         }
-        const int8_t *obs = a.data + row * a.pitch;
-        const IO *pi_p = pi_g + pb * a.pistride_b + ps * a.pistride_s + sub * MT;
+        const int8_t *obs = a.data + row * a.pitch + (SEG ? pseg * a.seg_len : 0);
+        const IO *pi_p = SEG ? static_cast<const IO *>(a.bnd_alpha) + (chunk_pair * (a.seg_count + 1) + pseg) * M + sub * MT
+                             : pi_g + pb * a.pistride_b + ps * a.pistride_s + sub * MT;
 
         // ------------------------------------------------------------------ pass 1: forward
         F x[MT];
@@ -650,7 +669,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
             }
             const ObsWords<K> ow = ow_next;
             if (seg + 1 < n_seg) ow_next.load(obs, (seg + 1) * K);  // one segment ahead
-            const int len = int(min(int64_t(K), a.L - seg * K));
+            const int len = int(min(int64_t(K), L - seg * K));
             F acc = F(0);
             for (int kb = 0; kb < len; kb += kNorm) {
                 const uint64_t blk = ow.block(kb);
@@ -670,8 +689,10 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
             if (sub == 0) atomicOr(a.err_flag, 2);
         }
         if (bad_row) ll = __longlong_as_double(0x7ff8000000000000LL);
-        if (writer && sub == 0) a.ll[pair] = a.out_mode ? a.ll[pair] - ll : ll;
-        if (writer && a.alpha_out != nullptr) {
+        if constexpr (!SEG) {
+            if (writer && sub == 0) a.ll[pair] = a.out_mode ? a.ll[pair] - ll : ll;
+        }
+        if (!SEG && writer && a.alpha_out != nullptr) {
             IO *ao = static_cast<IO *>(a.alpha_out) + pair * M + sub * MT;
 #pragma unroll
             for (int k = 0; k < MT; ++k) ao[k] = IO(x[k]);
@@ -683,13 +704,26 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
             g.clear();
             if constexpr (ESM) ea.clear();
             F beta[MT];
-            {
+            if constexpr (SEG) {
+                // the adjoint vector behind this segment, scaled so that beta . x == 1
+                const F *bb = static_cast<const F *>(a.bnd_beta) + (chunk_pair * (a.seg_count + 1) + pseg + 1) * M + sub * MT;
+                F dot = F(0);
+#pragma unroll
+                for (int k = 0; k < MT; ++k) {
+                    beta[k] = bb[k];
+                    dot = fma(beta[k], x[k], dot);
+                }
+                dot = F(1) / lanes_total<F, T>(dot);
+#pragma unroll
+                for (int k = 0; k < MT; ++k) beta[k] *= dot;
+                posterior_to_emission<F, MT, NT, ESM>(beta, x, int(obs[L - 1]), g, ea);
+            } else {
                 // after the last site: beta = 1 / sum(x) so that beta . x == 1, and the posterior of
                 // the last site is x .* beta
                 const F tot = fast_rcp<F>(pair_sum<F, MT, T>(x));
 #pragma unroll
                 for (int k = 0; k < MT; ++k) beta[k] = tot;
-                posterior_to_emission<F, MT, NT, ESM>(beta, x, int(obs[a.L - 1]), g, ea);
+                posterior_to_emission<F, MT, NT, ESM>(beta, x, int(obs[L - 1]), g, ea);
             }
 #pragma unroll 1
             for (int i = 0; i < 6 * MT; ++i) PHB_GACC_BASE[int64_t(i) * PHB_GACC_STRIDE] = 0.0;
@@ -701,7 +735,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                     ow_ahead.load(obs, (seg - 1) * K);
                     if (seg > 1) prefetch_l2(&ck[(seg - 1) * QN * 32]);
                 }
-                const int len = int(min(int64_t(K), a.L - seg * K));
+                const int len = int(min(int64_t(K), L - seg * K));
                 // re-run the forward steps of this segment, keeping every input vector
                 F xs[MT];
                 if (seg == 0) {
@@ -773,7 +807,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                 }
             }
             if (writer) {
-                IO *out = static_cast<IO *>(a.dlog) + pair * 7 * M + sub * MT;
+                IO *out = static_cast<IO *>(SEG ? a.seg_dlog : a.dlog) + pair * 7 * M + sub * MT;
                 const double *gacc = PHB_GACC_BASE;
                 const int64_t gacc_stride = PHB_GACC_STRIDE;
 #pragma unroll
@@ -787,7 +821,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                     val[5] = F(gacc[int64_t(5 * MT + k) * gacc_stride]);
                     val[6] = beta[k] * F(pi_p[k]);
 #pragma unroll
-                    for (int r = 0; r < 7; ++r) out[r * M + k] = IO(a.out_mode ? F(out[r * M + k]) - val[r] : val[r]);
+                    for (int r = 0; r < 7; ++r) out[r * M + k] = IO((!SEG && a.out_mode) ? F(out[r * M + k]) - val[r] : val[r]);
                 }
             }
         }
