@@ -212,7 +212,6 @@ const Variant *segment_variant(int M) {
 struct StoreAllVariant {
     int M, T, MT, NT;
     const void *func;
-    const void *seg_func;    // segment mode (parallel-in-time gradient)
     const void *sweep_func;  // forward / adjoint-only sweeps that leave the boundary vectors
     size_t smem;
 };
@@ -223,7 +222,6 @@ template <int MT, int T, int NT, int MINB> StoreAllVariant make_storeall() {
     v.MT = MT;
     v.NT = NT;
     v.func = reinterpret_cast<const void *>(&phb::psmc_loglik_storeall_kernel<float, MT, T, NT, MINB>);
-    v.seg_func = reinterpret_cast<const void *>(&phb::psmc_loglik_storeall_kernel<float, MT, T, NT, MINB, true>);
     v.sweep_func = reinterpret_cast<const void *>(&phb::boundary_sweep_kernel<float, MT, T, NT, MINB>);
     v.smem = phb::smem_bytes<float, MT, 8, NT, false>();
     return v;
@@ -318,89 +316,86 @@ constexpr int kNotTaken = 1;
 int try_parallel_in_time_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t stream, int pit_mode) {
     const int64_t n_pairs = a.B * a.S;
     const TransferVariant *tv = transfer_variant(k->M);
-    const StoreAllVariant *sv = nullptr;
-    for (const StoreAllVariant &c : storeall_variants())
-        if (c.M == k->M) sv = &c;
-    const int64_t capacity = int64_t(k->num_sms) * 384;
-    const int64_t min_seg = pit_mode == 1 ? 64 : 1024;
-    int64_t n_seg = tv && sv ? std::min(4 * capacity / (n_pairs * tv->M), a.L / min_seg) : 0;
-    if (pit_mode == 1) n_seg = std::max<int64_t>(n_seg, std::min<int64_t>(3, a.L / min_seg));
-    if (const char *g_env = getenv("PHB_PIT_SEGMENTS")) n_seg = std::min<int64_t>(atoi(g_env), a.L / 64);  // experiments
-    const bool worth = pit_mode == 1 || n_pairs * k->M * 10 <= capacity * 3;
-    if (tv && sv && worth && n_seg >= 3) {
-        const int64_t seg_len = ((a.L + n_seg - 1) / n_seg + 15) / 16 * 16;
-        n_seg = (a.L + seg_len - 1) / seg_len;
-        const int M = k->M;
-        const int64_t n_rows_virtual = n_pairs * n_seg * M;
-        // store-all passes: one launch, every CTA inside one segment (uniform loop bounds per CTA)
-        const int pairs_per_cta = sv->NT / sv->T;
-        const int64_t seg_ctas = (n_pairs + pairs_per_cta - 1) / pairs_per_cta;
-        const int64_t grid_full = seg_ctas * n_seg;
-        const int64_t warps = grid_full * (sv->NT / 32);
-        const size_t x_bytes = size_t(warps) * size_t(seg_len) * sv->MT * 32 * sizeof(float);
-        const size_t s_bytes = size_t(warps) * size_t((seg_len + phb::kNorm - 1) / phb::kNorm) * 32 * sizeof(float);
-        if (storeall_scratch_fits(k, x_bytes, s_bytes)) {
-            int rc;
-            if ((rc = k->transfer_rows.reserve(size_t(n_rows_virtual) * M * sizeof(float))) != PHB_OK) return rc;
-            if ((rc = k->transfer_log.reserve(size_t(n_rows_virtual) * sizeof(double))) != PHB_OK) return rc;
-            if ((rc = k->bnd_alpha.reserve(size_t(n_pairs) * (n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
-            if ((rc = k->bnd_beta.reserve(size_t(n_pairs) * (n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
-            if ((rc = k->seg_dlog.reserve(size_t(n_pairs) * n_seg * 7 * M * sizeof(float))) != PHB_OK) return rc;
-            if ((rc = k->xall.reserve(x_bytes)) != PHB_OK) return rc;
-            if ((rc = k->sall.reserve(s_bytes)) != PHB_OK) return rc;
-            if ((rc = k->gacc.reserve(size_t(grid_full) * sv->NT * 6 * sv->MT * sizeof(double))) != PHB_OK) return rc;
-            for (const void *f : {tv->rows_func, sv->seg_func}) {
-                if (k->occupancy.find(f) == k->occupancy.end()) {
-                    PHB_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, int(f == tv->rows_func ? tv->smem : sv->smem)));
-                    k->occupancy.emplace(f, 1);
-                }
-            }
-            phb::TransferArgs ta{};
-            ta.k = a;
-            ta.k.err_flag = k->d_err;
-            ta.n_seg = n_seg;
-            ta.seg_len = seg_len;
-            ta.rows = static_cast<float *>(k->transfer_rows.ptr);
-            ta.row_log2 = static_cast<double *>(k->transfer_log.ptr);
-            void *bnd_a = k->bnd_alpha.ptr, *bnd_b = k->bnd_beta.ptr;
-            {
-                void *kargs[] = {&ta};
-                PHB_CUDA(cudaLaunchKernel(tv->rows_func, dim3(unsigned((n_rows_virtual + 127) / 128)), dim3(128), kargs, tv->smem, stream));
-                void *bargs[] = {&ta, &bnd_a, &bnd_b};
-                PHB_CUDA(cudaLaunchKernel(tv->boundaries_func, dim3(unsigned((n_pairs * M + 127) / 128)), dim3(128), bargs, 0, stream));
-            }
-            phb::KernelArgs sa = a;
-            sa.err_flag = k->d_err;
-            sa.xall = k->xall.ptr;
-            sa.sall = k->sall.ptr;
-            sa.gacc = static_cast<double *>(k->gacc.ptr);
-            sa.seg_count = n_seg;
-            sa.seg_len = seg_len;
-            sa.bnd_alpha = bnd_a;
-            sa.bnd_beta = bnd_b;
-            sa.seg_dlog = k->seg_dlog.ptr;
-            sa.seg_ctas = seg_ctas;
-            sa.n_groups = grid_full;
-            int n_launch = 3;
-            {
-                void *kargs[] = {&sa};
-                PHB_CUDA(cudaLaunchKernel(sv->seg_func, dim3(unsigned(grid_full)), dim3(sv->NT), kargs, sv->smem, stream));
-            }
-            {
-                const int64_t n_out = n_pairs * 7 * M;
-                phb::sum_segments_kernel<float><<<unsigned((n_out + 255) / 256), 256, 0, stream>>>(
-                    static_cast<const float *>(k->seg_dlog.ptr), n_pairs, n_seg, M, static_cast<float *>(a.dlog), a.out_mode);
-                PHB_CUDA(cudaGetLastError());
-                n_launch += 1;
-            }
-            k->launches += n_launch;
-            snprintf(k->last_name, sizeof k->last_name, "transfer_rows_kernel<float,M=%d> + storeall_kernel<SEG> x %lld segments",
-                     M, (long long)n_seg);
-            return PHB_OK;
+    const Variant *gv = segment_variant(k->M);  // segment passes: throughput kernel in SEG mode
+    if (!tv || !gv) return kNotTaken;
+    const int M = k->M;
+    const int64_t capacity = int64_t(k->num_sms) * 384;  // resident threads of the row kernel
+    if (pit_mode != 1 && n_pairs * M * 10 > capacity * 3) return kNotTaken;
+    int occ = 0;
+    {
+        auto it = k->occupancy.find(gv->func);
+        if (it == k->occupancy.end()) {
+            PHB_CUDA(cudaFuncSetAttribute(gv->func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gv->smem)));
+            PHB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gv->func, gv->NT, gv->smem));
+            k->occupancy.emplace(gv->func, occ);
+        } else {
+            occ = it->second;
         }
     }
-
-    return kNotTaken;
+    if (occ < 1) return kNotTaken;
+    const int64_t resident = int64_t(occ) * k->num_sms;
+    const int pairs_per_group = gv->NT / gv->T;
+    const int64_t seg_ctas = (n_pairs + pairs_per_group - 1) / pairs_per_group;  // groups per segment
+    const int64_t min_seg = pit_mode == 1 ? 64 : 1024;
+    // as many segments as keep every group of the segment passes resident at once
+    int64_t n_seg = std::min(resident / seg_ctas, a.L / min_seg);
+    if (pit_mode == 1) n_seg = std::max<int64_t>(n_seg, std::min<int64_t>(3, a.L / min_seg));
+    if (const char *g_env = getenv("PHB_PIT_SEGMENTS")) n_seg = std::min<int64_t>(atoi(g_env), a.L / 64);  // experiments
+    if (n_seg < 3) return kNotTaken;
+    const int64_t seg_len = ((a.L + n_seg - 1) / n_seg + 15) / 16 * 16;
+    n_seg = (a.L + seg_len - 1) / seg_len;
+    const int64_t n_rows_virtual = n_pairs * n_seg * M;
+    const int64_t n_groups = seg_ctas * n_seg;
+    const int64_t grid = std::min<int64_t>(n_groups, resident);
+    int rc;
+    if ((rc = k->transfer_rows.reserve(size_t(n_rows_virtual) * M * sizeof(float))) != PHB_OK) return rc;
+    if ((rc = k->transfer_log.reserve(size_t(n_rows_virtual) * sizeof(double))) != PHB_OK) return rc;
+    if ((rc = k->bnd_alpha.reserve(size_t(n_pairs) * (n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
+    if ((rc = k->bnd_beta.reserve(size_t(n_pairs) * (n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
+    if ((rc = k->seg_dlog.reserve(size_t(n_pairs) * n_seg * 7 * M * sizeof(float))) != PHB_OK) return rc;
+    if ((rc = k->ckpt.reserve(size_t(grid) * (gv->NT / 32) * size_t(gv->ckpt_bytes_per_warp(seg_len)))) != PHB_OK) return rc;
+    if ((rc = k->gacc.reserve(size_t(grid) * gv->NT * 6 * (gv->M / gv->T) * sizeof(double))) != PHB_OK) return rc;
+    if (k->occupancy.find(tv->rows_func) == k->occupancy.end()) {
+        PHB_CUDA(cudaFuncSetAttribute(tv->rows_func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tv->smem)));
+        k->occupancy.emplace(tv->rows_func, 1);
+    }
+    phb::TransferArgs ta{};
+    ta.k = a;
+    ta.k.err_flag = k->d_err;
+    ta.n_seg = n_seg;
+    ta.seg_len = seg_len;
+    ta.rows = static_cast<float *>(k->transfer_rows.ptr);
+    ta.row_log2 = static_cast<double *>(k->transfer_log.ptr);
+    void *bnd_a = k->bnd_alpha.ptr, *bnd_b = k->bnd_beta.ptr;
+    {
+        void *kargs[] = {&ta};
+        PHB_CUDA(cudaLaunchKernel(tv->rows_func, dim3(unsigned((n_rows_virtual + 127) / 128)), dim3(128), kargs, tv->smem, stream));
+        void *bargs[] = {&ta, &bnd_a, &bnd_b};
+        PHB_CUDA(cudaLaunchKernel(tv->boundaries_func, dim3(unsigned((n_pairs * M + 127) / 128)), dim3(128), bargs, 0, stream));
+    }
+    phb::KernelArgs sa = a;
+    sa.err_flag = k->d_err;
+    sa.ckpt = k->ckpt.ptr;
+    sa.gacc = static_cast<double *>(k->gacc.ptr);
+    sa.seg_count = n_seg;
+    sa.seg_len = seg_len;
+    sa.bnd_alpha = bnd_a;
+    sa.bnd_beta = bnd_b;
+    sa.seg_dlog = k->seg_dlog.ptr;
+    sa.seg_ctas = seg_ctas;
+    sa.n_groups = n_groups;
+    {
+        void *kargs[] = {&sa};
+        PHB_CUDA(cudaLaunchKernel(gv->func, dim3(unsigned(grid)), dim3(gv->NT), kargs, gv->smem, stream));
+    }
+    const int64_t n_out = n_pairs * 7 * M;
+    phb::sum_segments_kernel<float><<<unsigned((n_out + 255) / 256), 256, 0, stream>>>(
+        static_cast<const float *>(k->seg_dlog.ptr), n_pairs, n_seg, M, static_cast<float *>(a.dlog), a.out_mode);
+    PHB_CUDA(cudaGetLastError());
+    k->launches += 4;
+    snprintf(k->last_name, sizeof k->last_name, "transfer_rows_kernel<float,M=%d> + psmc_loglik_kernel<SEG,MT=%d,T=%d> x %lld segments", M,
+             gv->M / gv->T, gv->T, (long long)n_seg);
+    return PHB_OK;
 }
 
 // (1b) Gradient of a small minibatch with too many pairs for the operators (the reference's S = 5: 2 500

@@ -62,12 +62,12 @@ struct KernelArgs {
     // in device memory, so the split needs no host round trip.  nullptr = all S chunks.
     const int32_t *s_list;
     const int32_t *s_count;
-    // Segment mode of the store-all kernel (parallel-in-time gradient, see chain_boundaries_kernel): the
+    // Segment mode of the gradient kernel (parallel-in-time gradient, see chain_boundaries_kernel): the
     // launch scores the G segments of every chunk as independent short "pairs" (L = sites per chunk),
     // started from bnd_alpha and closed with bnd_beta; partial gradients go to seg_dlog.
     int64_t seg_count;      // G, segments per chunk
     int64_t seg_len;        // sites per segment (multiple of 16); the last one has L - (G - 1) seg_len
-    int64_t seg_ctas;       // CTAs per segment: CTA c scores segment c / seg_ctas, so that all warps of a CTA
+    int64_t seg_ctas;       // groups per segment: group g scores segment g / seg_ctas, so that all warps of a CTA
                             // share the segment length (the loop bounds stay uniform for the shuffles)
     const void *bnd_alpha;  // [B * S][G + 1][M] FLOAT: forward vector entering segment g (sum 1)
     const void *bnd_beta;   // [B * S][G + 1][M] FLOAT: adjoint vector behind segment g - 1 (any scale)
@@ -837,7 +837,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
 // adjoint pass streams them back with the loads of the next block issued one block ahead - two
 // passes instead of three, nothing recomputed.  One CTA handles exactly one group of pairs (the
 // host launches enough CTAs), so the scratch is indexed by the global warp index.
-template <typename F, int MT, int T, int NT, int MINB, bool SEG = false>
+template <typename F, int MT, int T, int NT, int MINB>
 __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_storeall_kernel(const KernelArgs a) {
     constexpr int M = MT * T;
     constexpr int PW = 32 / T;
@@ -865,12 +865,9 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_storeall_kernel(cons
     const int sub = lane % T;
     const int lp = lane / T;
     const int64_t s_eff = listed_chunks(a);
-    const int64_t n_pairs = SEG ? a.B * a.S : a.B * s_eff;
-    // SEG: CTA -> (segment, CTA within the segment); L = length of that segment
-    const int64_t seg = SEG ? int64_t(blockIdx.x) / a.seg_ctas : 0;
-    const int64_t cta = SEG ? int64_t(blockIdx.x) % a.seg_ctas : int64_t(blockIdx.x);
-    const int64_t L = SEG ? min(a.seg_len, a.L - seg * a.seg_len) : a.L;
-    const int64_t L_max = SEG ? a.seg_len : a.L;
+    const int64_t n_pairs = a.B * s_eff;
+    const int64_t cta = blockIdx.x;
+    const int64_t L = a.L;
     // the grid is sized for the whole minibatch; with a sub-list the surplus warps have nothing to do
     // (no block-level barrier follows, so whole warps may leave)
     if ((cta * kWarps + warp) * PW >= n_pairs) return;
@@ -878,23 +875,13 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_storeall_kernel(cons
     const int64_t warp_slot = int64_t(blockIdx.x) * kWarps + warp;
     const F *params6 = static_cast<const F *>(a.params6);
     const F *pi_g = static_cast<const F *>(a.pi);
-    V *xall = reinterpret_cast<V *>(a.xall) + warp_slot * L_max * QN * 32 + lane;                  // + (t * QN + q) * 32
-    F *sall = static_cast<F *>(a.sall) + warp_slot * ((L_max + kNorm - 1) / kNorm) * 32 + lane;   // + block * 32
+    V *xall = reinterpret_cast<V *>(a.xall) + warp_slot * L * QN * 32 + lane;  // + (t * QN + q) * 32
+    F *sall = static_cast<F *>(a.sall) + warp_slot * n_blocks * 32 + lane;     // + block * 32
 
     const int64_t pair_raw = (cta * kWarps + warp) * PW + lp;
     const bool writer = pair_raw < n_pairs;
-    int64_t pb, ps, pair, chunk_pair = 0;
-    if constexpr (SEG) {
-        chunk_pair = writer ? pair_raw : n_pairs - 1;   // (b, s) of the chunk
-        pb = chunk_pair / a.S;
-        ps = chunk_pair % a.S;
-        pair = chunk_pair * a.seg_count + seg;          // slot in seg_dlog
-    } else {
-        const PairIndex pidx = pair_index(a, writer ? pair_raw : n_pairs - 1, s_eff);
-        pb = pidx.b;
-        ps = pidx.s;
-        pair = pidx.out;
-    }
+    const PairIndex pidx = pair_index(a, writer ? pair_raw : n_pairs - 1, s_eff);
+    const int64_t pb = pidx.b, ps = pidx.s, pair = pidx.out;
     Params<F, MT> p;
     p.load(params6 + pb * a.pstride_b + ps * a.pstride_s + sub * MT, M);
     et.fill(params6 + pb * a.pstride_b + ps * a.pstride_s + sub * MT, M);
@@ -906,9 +893,8 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_storeall_kernel(cons
         if (sub == 0) atomicOr(a.err_flag, 1);
         row = 0;
     }
-    const int8_t *obs = a.data + row * a.pitch + (SEG ? seg * a.seg_len : 0);
-    const F *pi_p = SEG ? static_cast<const F *>(a.bnd_alpha) + (chunk_pair * (a.seg_count + 1) + seg) * M + sub * MT
-                        : pi_g + pb * a.pistride_b + ps * a.pistride_s + sub * MT;
+    const int8_t *obs = a.data + row * a.pitch;
+    const F *pi_p = pi_g + pb * a.pistride_b + ps * a.pistride_s + sub * MT;
 
     // ---------------------------------------------------------------- pass 1: forward, keep everything
     F x[MT];
@@ -948,28 +934,13 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_storeall_kernel(cons
         if (sub == 0) atomicOr(a.err_flag, 2);
     }
     if (bad_row) ll = __longlong_as_double(0x7ff8000000000000LL);
-    if constexpr (!SEG) {  // (the log-likelihood of a segmented chunk comes from chain_boundaries_kernel)
-        if (writer && sub == 0) a.ll[pair] = a.out_mode ? a.ll[pair] - ll : ll;
-    }
+    if (writer && sub == 0) a.ll[pair] = a.out_mode ? a.ll[pair] - ll : ll;
 
     // ---------------------------------------------------------------- pass 2: adjoint, streaming the vectors back
     Grad<F, MT, false> g;
     g.clear();
     F beta[MT];
-    if constexpr (SEG) {
-        // the adjoint vector behind this segment, scaled so that beta . x == 1
-        const F *bb = static_cast<const F *>(a.bnd_beta) + (chunk_pair * (a.seg_count + 1) + seg + 1) * M + sub * MT;
-        F dot = F(0);
-#pragma unroll
-        for (int k = 0; k < MT; ++k) {
-            beta[k] = bb[k];
-            dot = fma(beta[k], x[k], dot);
-        }
-        dot = F(1) / lanes_total<F, T>(dot);
-#pragma unroll
-        for (int k = 0; k < MT; ++k) beta[k] *= dot;
-        posterior_to_emission<F, MT, NT, false>(beta, x, int(obs[L - 1]), g, ea);
-    } else {
+    {
         const F tot = fast_rcp<F>(pair_sum<F, MT, T>(x));
 #pragma unroll
         for (int k = 0; k < MT; ++k) beta[k] = tot;
@@ -1053,7 +1024,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_storeall_kernel(cons
         }
     }
     if (writer) {
-        F *out = static_cast<F *>(SEG ? a.seg_dlog : a.dlog) + pair * 7 * M + sub * MT;
+        F *out = static_cast<F *>(a.dlog) + pair * 7 * M + sub * MT;
 #pragma unroll
         for (int k = 0; k < MT; ++k) {
             F val[7];
@@ -1065,7 +1036,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_storeall_kernel(cons
             val[5] = F(gacc_base[int64_t(5 * MT + k) * gacc_stride]);
             val[6] = beta[k] * pi_p[k];
 #pragma unroll
-            for (int r = 0; r < 7; ++r) out[r * M + k] = (!SEG && a.out_mode) ? out[r * M + k] - val[r] : val[r];
+            for (int r = 0; r < 7; ++r) out[r * M + k] = a.out_mode ? out[r * M + k] - val[r] : val[r];
         }
     }
 }
@@ -1211,8 +1182,8 @@ template <typename F, int M> __global__ void chain_transfer_kernel(const Transfe
 // for a single genome, mcmc.py:119-121: 500 pairs, 14 ms of dependent site steps): chained forwards
 // they give the forward vector entering every segment, chained backwards (beta_g = T_g beta_{g+1},
 // beta_G = 1) the adjoint vector behind it.  With both boundary vectors known the segments are
-// independent: the store-all kernel runs its two passes over every segment as if it were a short
-// chunk (SEG mode: started from alpha_g, closed with beta_{g+1} rescaled to beta . alpha == 1), and
+// independent: the gradient kernel runs over every segment as if it were a short chunk (SEG mode of
+// psmc_loglik_kernel: started from alpha_g, closed with beta_{g+1} rescaled to beta . alpha == 1), and
 // the partial gradients are added up.
 //
 // chain_boundaries_kernel: M lanes per pair (lane k owns component k); writes ll and the G + 1 boundary
@@ -1306,8 +1277,8 @@ __global__ void sum_segments_kernel(const F *__restrict__ seg_dlog, int64_t n_pa
 // side by side instead: even CTAs run the plain forward recursion and leave the forward vector at every
 // segment boundary (and the log-likelihood), odd CTAs run the adjoint recursion without any gradient
 // bookkeeping, beta <- A (emis .* beta), from the end of the chunk and leave the adjoint vectors.  Each
-// is one dependent pass of the cheap kind (~80 ns per site); the expensive gradient passes then run over
-// all segments at once (store-all kernel, SEG mode) as in the operator variant.
+// is one dependent pass of the cheap kind (~110 ns per site); the expensive gradient passes then run over
+// all segments at once (psmc_loglik_kernel, SEG mode) as in the operator variant.
 template <typename F, int MT, int T, int NT>
 __device__ __forceinline__ void adjoint_only_site(F (&beta)[MT], const Params<F, MT> &p, const EmisTable<F, MT, NT> &et, int ob, int sub) {
     F w[MT];

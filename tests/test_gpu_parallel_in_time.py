@@ -162,8 +162,12 @@ def test_gradient_dispatch_and_warmup_composition(golden):
     kern.set_parallel_in_time(0)
     ll_s, dlog_s = kern.evaluate_warmup(pps, inds, ov, True)
     np.testing.assert_allclose(ll, ll_s, rtol=1e-6)
+    # the result is a DIFFERENCE of two gradients (all bins - warm-up bins): fp32 round-off is relative to
+    # the un-cancelled size
+    _, full = kern.evaluate(pa, inds, True)
     scale = np.abs(dlog_s).max(axis=-1, keepdims=True)
-    assert (np.abs(dlog - dlog_s) <= GRAD_RTOL * (np.abs(dlog_s) + 1e-3 * scale)).all()
+    scale_full = np.abs(full).max(axis=-1, keepdims=True)
+    assert (np.abs(dlog - dlog_s) <= GRAD_RTOL * (np.abs(dlog_s) + 1e-3 * scale) + 2e-6 * scale_full).all()
 
 
 def test_per_pair_parameter_blocks_and_subtracting_launch():
