@@ -568,6 +568,8 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
     constexpr int W = Vec<F>::W;
     constexpr int QN = MT / W;
     static_assert(MT % 4 == 0 && K % 8 == 0 && K % kNorm == 0 && (kNorm == 4 || kNorm == 8) && T <= 32, "layout assumptions");
+    // one decision per block of kNorm sites instead of one per site (see pass 1)
+    constexpr bool kBlockBranch = T == 1 && !SEG;  // (the segment-mode build has no register to spare)
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -673,9 +675,22 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
             F acc = F(0);
             for (int kb = 0; kb < len; kb += kNorm) {
                 const uint64_t blk = ow.block(kb);
+                // one decision per block instead of one per site: the sites of a full block form one
+                // basic block (the scheduler can overlap neighbouring sites), the ragged tail of a
+                // chunk goes through a compact loop
+                // (thread-per-pair layouts only: measured +3 % at M = 16; the multi-lane layouts of M = 32 / 64
+                // run out of registers with the second code path and keep one predicated site per branch)
+                if (kBlockBranch && kb + kNorm <= len) {
 #pragma unroll
-                for (int j = 0; j < kNorm; ++j)
-                    if (kb + j < len) forward_site<F, MT, T, GRAD, NT>(x, p, pc, et, ObsWords<K>::byte_of(blk, j), sub);
+                    for (int j = 0; j < kNorm; ++j) forward_site<F, MT, T, GRAD, NT>(x, p, pc, et, ObsWords<K>::byte_of(blk, j), sub);
+                } else if constexpr (kBlockBranch) {
+#pragma unroll 1
+                    for (int j = 0; kb + j < len; ++j) forward_site<F, MT, T, GRAD, NT>(x, p, pc, et, ObsWords<K>::byte_of(blk, j), sub);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kNorm; ++j)
+                        if (kb + j < len) forward_site<F, MT, T, GRAD, NT>(x, p, pc, et, ObsWords<K>::byte_of(blk, j), sub);
+                }
                 const F tot = pair_sum<F, MT, T>(x);
                 const F inv = fast_rcp<F>(tot);
 #pragma unroll
@@ -747,12 +762,28 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                 }
                 for (int kb = 0; kb < len; kb += kNorm) {
                     const uint64_t blk = ow.block(kb);
+                    if (kBlockBranch && kb + kNorm <= len) {
 #pragma unroll
-                    for (int j = 0; j < kNorm; ++j) {
-                        if (kb + j < len) {
+                        for (int j = 0; j < kNorm; ++j) {
 #pragma unroll
                             for (int q = 0; q < QN; ++q) sts_word(seg_a + ((kb + j) * QN + q) * 32 * 16, &xs[q * W]);
                             forward_site<F, MT, T, GRAD, NT>(xs, p, pc, et, ObsWords<K>::byte_of(blk, j), sub);
+                        }
+                    } else if constexpr (kBlockBranch) {
+#pragma unroll 1
+                        for (int j = 0; kb + j < len; ++j) {
+#pragma unroll
+                            for (int q = 0; q < QN; ++q) sts_word(seg_a + ((kb + j) * QN + q) * 32 * 16, &xs[q * W]);
+                            forward_site<F, MT, T, GRAD, NT>(xs, p, pc, et, ObsWords<K>::byte_of(blk, j), sub);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < kNorm; ++j) {
+                            if (kb + j < len) {
+#pragma unroll
+                                for (int q = 0; q < QN; ++q) sts_word(seg_a + ((kb + j) * QN + q) * 32 * 16, &xs[q * W]);
+                                forward_site<F, MT, T, GRAD, NT>(xs, p, pc, et, ObsWords<K>::byte_of(blk, j), sub);
+                            }
                         }
                     }
                     const F inv = fast_rcp<F>(pair_sum<F, MT, T>(xs));
@@ -780,9 +811,29 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                     const F scale = lds_scalar_f(scale_a + (kb / kNorm) * 32 * uint32_t(sizeof(F)), F(0));
 #pragma unroll
                     for (int k = 0; k < MT; ++k) beta[k] *= scale;
+                    if (kBlockBranch && kb + kNorm <= len) {
 #pragma unroll
-                    for (int j = kNorm - 1; j >= 0; --j) {
-                        if (kb + j < len) {
+                        for (int j = kNorm - 1; j >= 0; --j) {
+                            F xin[MT];
+#pragma unroll
+                            for (int q = 0; q < QN; ++q) lds_word(seg_a + ((kb + j) * QN + q) * 32 * 16, &xin[q * W]);
+                            const int ob_prev = j > 0 ? ObsWords<K>::byte_of(blk, j - 1) : ob_before;
+                            backward_site<F, MT, T, NT, ESM>(beta, xin, ObsWords<K>::byte_of(blk, j), ob_prev, p, pc, et, sub, g, ea);
+                        }
+                    } else if constexpr (!kBlockBranch) {
+#pragma unroll
+                        for (int j = kNorm - 1; j >= 0; --j) {
+                            if (kb + j < len) {
+                                F xin[MT];
+#pragma unroll
+                                for (int q = 0; q < QN; ++q) lds_word(seg_a + ((kb + j) * QN + q) * 32 * 16, &xin[q * W]);
+                                const int ob_prev = j > 0 ? ObsWords<K>::byte_of(blk, j - 1) : ob_before;
+                                backward_site<F, MT, T, NT, ESM>(beta, xin, ObsWords<K>::byte_of(blk, j), ob_prev, p, pc, et, sub, g, ea);
+                            }
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int j = len - 1 - kb; j >= 0; --j) {
                             F xin[MT];
 #pragma unroll
                             for (int q = 0; q < QN; ++q) lds_word(seg_a + ((kb + j) * QN + q) * 32 * 16, &xin[q * W]);
@@ -910,6 +961,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_storeall_kernel(cons
         const uint32_t blk = blk_next;
         if (blk_i + 1 < n_blocks) blk_next = __ldg(reinterpret_cast<const unsigned int *>(obs + t0 + kNorm));
         const int len = int(min(int64_t(kNorm), L - t0));
+        // (a block-level decision instead of one per site was measured SLOWER here: 18.0 vs 17.0 ms at S = 16)
 #pragma unroll
         for (int j = 0; j < kNorm; ++j) {
             if (j < len) {
@@ -1115,9 +1167,13 @@ template <typename F, int M, int NT> __global__ void __maxnreg__(max_regs(NT, 3)
         F acc = F(0);
         for (int kb = 0; kb < n; kb += kNorm) {
             const uint64_t word = ow.block(kb);
+            if (kb + kNorm <= n) {
 #pragma unroll
-            for (int j = 0; j < kNorm; ++j)
-                if (kb + j < n) forward_site<F, MT, T, false, NT>(x, p, pc, et, ObsWords<K>::byte_of(word, j), 0);
+                for (int j = 0; j < kNorm; ++j) forward_site<F, MT, T, false, NT>(x, p, pc, et, ObsWords<K>::byte_of(word, j), 0);
+            } else {
+#pragma unroll 1
+                for (int j = 0; kb + j < n; ++j) forward_site<F, MT, T, false, NT>(x, p, pc, et, ObsWords<K>::byte_of(word, j), 0);
+            }
             const F tot = pair_sum<F, MT, T>(x);
             const F inv = fast_rcp<F>(tot);
 #pragma unroll
@@ -1375,10 +1431,13 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) boundary_sweep_kernel(const Kern
             const int64_t t0 = blk_i * kNorm;
             const uint32_t blk = blk_next;
             if (blk_i + 1 < n_blocks) blk_next = __ldg(reinterpret_cast<const unsigned int *>(obs + t0 + kNorm));
-            const int len = int(min(int64_t(kNorm), a.L - t0));
+            // (one decision per block, not per site: a lone warp pays ~10 cycles for every branch)
+            if (t0 + kNorm <= a.L) {
 #pragma unroll
-            for (int j = 0; j < kNorm; ++j)
-                if (j < len) forward_site<F, MT, T, false, NT>(x, p, pc, et, ObsWords<8>::byte_of(blk, j), sub);
+                for (int j = 0; j < kNorm; ++j) forward_site<F, MT, T, false, NT>(x, p, pc, et, ObsWords<8>::byte_of(blk, j), sub);
+            } else {
+                for (int j = 0; j < int(a.L - t0); ++j) forward_site<F, MT, T, false, NT>(x, p, pc, et, ObsWords<8>::byte_of(blk, j), sub);
+            }
             const F tot = pair_sum<F, MT, T>(x);
             const F inv = fast_rcp<F>(tot);
 #pragma unroll
@@ -1423,10 +1482,12 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) boundary_sweep_kernel(const Kern
             const int64_t t0 = blk_i * kNorm;
             const uint32_t blk = blk_next;
             if (blk_i > 0) blk_next = __ldg(reinterpret_cast<const unsigned int *>(obs + t0 - kNorm));
-            const int len = int(min(int64_t(kNorm), a.L - t0));
+            if (t0 + kNorm <= a.L) {
 #pragma unroll
-            for (int j = kNorm - 1; j >= 0; --j)
-                if (j < len) adjoint_only_site<F, MT, T, NT>(beta, p, et, ObsWords<8>::byte_of(blk, j), sub);
+                for (int j = kNorm - 1; j >= 0; --j) adjoint_only_site<F, MT, T, NT>(beta, p, et, ObsWords<8>::byte_of(blk, j), sub);
+            } else {
+                for (int j = int(a.L - t0) - 1; j >= 0; --j) adjoint_only_site<F, MT, T, NT>(beta, p, et, ObsWords<8>::byte_of(blk, j), sub);
+            }
             const F inv = fast_rcp<F>(pair_sum<F, MT, T>(beta));
 #pragma unroll
             for (int k = 0; k < MT; ++k) beta[k] *= inv;
