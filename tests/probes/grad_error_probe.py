@@ -1,7 +1,7 @@
 """Where does the fp32 gradient error at full chunk length come from?  (diagnostic)"""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import c_oracle, psmc_oracle as orc
 from phlash_b200.gpu import _PSMCKernelBase
 

@@ -2,7 +2,7 @@
 of a contig): ours vs the reference's own fp32 kernel, both against fp64 at the same inputs."""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import c_oracle, psmc_oracle as orc, ref_cuda
 from phlash_b200.gpu import _PSMCKernelBase
 

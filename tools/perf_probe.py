@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import psmc_oracle as orc  # inputs only (synthetic data generator)
+from benchdata import synth
 from phlash_b200.gpu import _PSMCKernelBase
 
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 16
@@ -20,12 +20,12 @@ TS = [int(t) for t in sys.argv[5].split(",")] if len(sys.argv) > 5 else [0]
 DBL = len(sys.argv) > 6 and sys.argv[6] == "dbl"
 
 rng = np.random.default_rng(0)
-het = orc.synth_het_matrix(1, 200_000, 0)
+het = synth.het_matrix(1, 200_000, 0)
 base = het[0]
 reps = -(-(NCH * L) // base.size)
 data = np.tile(base, reps)[: NCH * L].reshape(NCH, L).copy()
 data[:, 0] = np.where(data[:, 0] < 0, 0, data[:, 0])
-pps, _, _ = orc.synth_particles(M, B, 0)
+pps = synth.particles(M, B)  # committed fixtures: M = 16, 32, 64
 kern = _PSMCKernelBase(M, data, double_precision=DBL)
 dt = torch.float64 if DBL else torch.float32
 dev = torch.device("cuda:0")
