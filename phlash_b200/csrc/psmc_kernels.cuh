@@ -25,6 +25,19 @@
 // Per site and pair: ~9 M FMA-pipe instructions forward (twice with the recompute) and ~20 M for
 // the adjoint step, 1 B of observations, 2 * 4 * M / K B of checkpoint traffic,
 // 2 * 4 * (M + 1) B of shared-memory traffic.
+//
+// Kernels in this file:
+//   psmc_loglik_kernel            the throughput kernel described above (loglik, or loglik + gradient);
+//                                 SEG = true: the same passes over the segments of a chunk
+//   psmc_loglik_storeall_kernel   gradient of small minibatches: every forward vector kept in HBM
+//   transfer_rows_kernel,         parallel in time for FEW pairs: segment transfer operators, chained in
+//   chain_transfer_kernel,        float64 to the log-likelihood (forward only) or to the forward / adjoint
+//   chain_boundaries_kernel       vectors at the segment boundaries (gradient)
+//   boundary_sweep_kernel         the same boundary vectors from two sequential sweeps side by side
+//   sum_segments_kernel           adds the partial gradients of the segments
+//   flag_long_runs_kernel,        precision escalation: rows with long runs of identical observations
+//   split_minibatch_kernel        are scored in double
+//   chunk_het_kernel, validate_params_kernel   data chunking / input validation
 #pragma once
 
 #include <cuda_runtime.h>
