@@ -123,8 +123,8 @@ template <typename F, int MT, int T, int K, bool GRAD, int NT, int MINB, typenam
 
 // Every (precision, M, threads-per-pair) combination that is compiled.  Within one
 // (precision, M, grad) the entries are ordered by increasing T; the dispatcher takes the first
-// one that fills the GPU.  The gradient kernel keeps 6*MT parameters and 6*MT accumulators in
-// registers, so it is built for MT <= 8; the forward-only kernel also for MT = 16.
+// one that fills the GPU.  The gradient kernel keeps 4*MT parameters and 4*MT (MT = 16: the emission
+// rows live in shared memory) or 6*MT accumulators in registers: MT = 16 at 255 registers, MT = 8 at 168.
 const std::vector<Variant> &variants() {
     static const std::vector<Variant> table = [] {
         std::vector<Variant> t;
