@@ -405,3 +405,30 @@ def test_store_all_with_fused_warmup(golden):
     np.testing.assert_allclose(a[0], b[0], rtol=1e-6)
     scale = np.abs(b[1]).max(-1, keepdims=True)
     assert np.all(np.abs(a[1] - b[1]) <= 1e-4 * np.abs(b[1]) + 1e-5 * scale)
+
+
+def test_matrix_larger_than_2_gib_uses_64_bit_offsets():
+    """BASELINE configs 4 / 5 hold 1.3 - 50 GB of observations per GPU: row offsets must be 64-bit.
+    The last rows of a 2.3 GB matrix (46 000 x 50 000) score exactly like the same rows in a small one."""
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    L, reps = 50_000, 11_500
+    base = orc.synth_het_matrix(4, L, seed=3).astype(np.int8)
+    base[:, 0] = np.where(base[:, 0] < 0, 0, base[:, 0])
+    big = np.tile(base, (reps, 1))  # row i == base[i % 4]
+    assert big.nbytes > 2**31
+    pps, _, _ = orc.synth_particles(16, 3, seed=1)
+    small = _PSMCKernelBase(16, base)
+    large = _PSMCKernelBase(16, big)
+    inds_big = np.array([len(big) - 1, len(big) - 2, 0, len(big) // 2 + 1])
+    inds_small = inds_big % 4
+    pa = np.broadcast_to(pps[:, None], (3, 4, 7, 16)).copy()
+    for grad in (True, False):
+        got = large.evaluate(pa, inds_big, grad)
+        want = small.evaluate(pa, inds_small, grad)
+        if grad:
+            np.testing.assert_array_equal(got[0], want[0])
+            np.testing.assert_array_equal(got[1], want[1])
+        else:
+            np.testing.assert_array_equal(got, want)
+    assert large.num_escalated_rows == 0
