@@ -7,6 +7,7 @@ input need pysam / tskit and stay with the reference."""
 from __future__ import annotations
 
 import gzip
+from dataclasses import dataclass
 from typing import Iterator, List, NamedTuple, Optional, Sequence, Tuple
 
 import numpy as np
@@ -90,3 +91,63 @@ def psmc_inputs(psmcfa_files: Sequence[str], hold_out: bool = True) -> Tuple[Lis
     contigs = [het for f in psmcfa_files for _, het in read_psmcfa(f)]
     test = contigs.pop(0) if hold_out and len(contigs) > 1 else None
     return contigs, test
+
+
+@dataclass(frozen=True)
+class RawContig:
+    """A contig with a pre-computed het matrix and AFS: the reference's `RawContig` (data.py:114-170)
+    with the part of the `Contig` surface the hot path uses (`N`, `L`, `size`, `get_data`,
+    `to_chunked`, data.py:63-112).  The other Contig kinds of the reference (VCF, tree sequence) need
+    pysam / tskit and convert to this one with `Contig.to_raw`."""
+
+    het_matrix: Optional[np.ndarray]  # int8 [n_diploids, L / window_size]
+    afs: Optional[np.ndarray]
+    window_size: int
+
+    @classmethod
+    def from_psmcfa_iter(cls, psmcfa_path: str, window_size: int) -> Iterator["RawContig"]:
+        """data.py:122-149 (afs = ones(1) for a single diploid)."""
+        for _, het in read_psmcfa(psmcfa_path):
+            yield cls(het_matrix=het, afs=np.ones(1), window_size=window_size)
+
+    @property
+    def N(self) -> Optional[int]:
+        """number of ploids: twice the number of rows (data.py:150-156)"""
+        return None if self.het_matrix is None else 2 * self.het_matrix.shape[0]
+
+    @property
+    def L(self) -> Optional[int]:
+        """sequence length in base pairs (data.py:158-162)"""
+        return None if self.het_matrix is None else self.het_matrix.shape[1] * self.window_size
+
+    @property
+    def size(self) -> Optional[int]:
+        return None if self.L is None or self.N is None else self.L * self.N
+
+    def get_data(self, window_size: int) -> dict:
+        if window_size != self.window_size:
+            raise ValueError(
+                f"This contig was created with a window size of {self.window_size} but you requested {window_size}"
+            )
+        return {"het_matrix": self.het_matrix, "afs": self.afs, "window_size": self.window_size}
+
+    def to_chunked(self, overlap: int, chunk_size: int, window_size: int = 100) -> ChunkedContig:
+        d = self.get_data(window_size)
+        ch = None if d["het_matrix"] is None else _chunk_het_matrix(d["het_matrix"], overlap, chunk_size)
+        return ChunkedContig(chunks=ch, afs=d["afs"])
+
+
+def init_mcmc_data_from_contigs(data: Sequence[RawContig], window_size: int, overlap: int, chunk_size: Optional[int] = None):
+    """(summed AFS, stacked chunks) of a list of contigs - the reference's init_mcmc_data (data.py:506-558)
+    without the process pool: default chunk size ~1/5th of the shortest contig, every contig chunked with
+    the same geometry, AFS summed, chunks concatenated."""
+    if all(ds.L is None for ds in data):
+        raise ValueError("None of the contigs have a length")
+    if chunk_size is None:
+        chunk_size = default_chunk_size([ds.L for ds in data if ds.L], window_size)
+    parts = [ds.to_chunked(overlap=overlap, chunk_size=chunk_size, window_size=window_size) for ds in data]
+    afss = [p.afs for p in parts if p.afs is not None]
+    chunks = [p.chunks for p in parts if p.chunks is not None]
+    assert all(a.ndim == 1 for a in afss) and len({a.shape for a in afss}) <= 1
+    assert len({ch.shape[-1] for ch in chunks}) == 1 and all(ch.ndim == 2 for ch in chunks)
+    return (np.sum(afss, 0) if afss else None), np.concatenate(chunks, 0)

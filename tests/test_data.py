@@ -89,3 +89,30 @@ def test_read_psmcfa_rejects_headerless_input(tmp_path):
     path.write_text("TTTKTT\n")
     with pytest.raises(ValueError):
         list(read_psmcfa(str(path)))
+
+
+def test_raw_contig_surface_and_init_from_contigs(tmp_path):
+    """RawContig (data.py:114-170) and init_mcmc_data (data.py:506-558) on .psmcfa input: N, L, size,
+    get_data's window check, default chunk size ~1/5th of the shortest contig, stacked chunks."""
+    from phlash_b200.data import RawContig, _chunk_het_matrix, init_mcmc_data_from_contigs
+
+    rng = np.random.default_rng(1)
+    records = [(f"chr{i}", "".join(rng.choice(list("TTTTTTTKN"), size=n))) for i, n in enumerate([30_000, 12_345])]
+    path = str(tmp_path / "two.psmcfa")
+    _write_psmcfa(path, records)
+    contigs = list(RawContig.from_psmcfa_iter(path, window_size=100))
+    assert [c.N for c in contigs] == [2, 2]
+    assert [c.L for c in contigs] == [3_000_000, 1_234_500]
+    assert contigs[0].size == 6_000_000
+    with pytest.raises(ValueError):
+        contigs[0].get_data(50)
+    afs, chunks = init_mcmc_data_from_contigs(contigs, window_size=100, overlap=500)
+    cs = int(0.2 * 1_234_500 / 100)                       # data.py:520-521
+    want = np.concatenate([_chunk_het_matrix(c.het_matrix, 500, cs) for c in contigs], 0)
+    np.testing.assert_array_equal(chunks, want)
+    assert chunks.shape[1] == cs + 500
+    np.testing.assert_array_equal(afs, np.full(1, 2.0))
+    empty = RawContig(het_matrix=None, afs=None, window_size=100)
+    assert empty.N is None and empty.L is None and empty.size is None
+    with pytest.raises(ValueError):
+        init_mcmc_data_from_contigs([empty], 100, 500)
