@@ -63,3 +63,20 @@ def elpd_hmm_term(test_kern, x, pattern: str, theta: float):
     inds = torch.arange(test_kern._N, dtype=torch.int64, device=x.device)
     value, _ = test_kern.hmm_term(x, pattern, theta, inds, 1, 1.0, grad=False)
     return value.mean()
+
+
+def downsample_chunks(chunks, minibatch_size: int, niter: int, rng):
+    """Keep at most 5 * S * niter chunk rows, chosen without replacement (reference: mcmc.py:124-139:
+    "in expectation, we will sample at most S * niter rows of the data").  `rng` is a
+    numpy.random.Generator (the reference seeds one from its jax key, so the choice itself is not
+    reproducible across the two code bases - only the rule is)."""
+    limit = 5 * minibatch_size * niter
+    if len(chunks) > limit:
+        chunks = rng.choice(chunks, size=(limit,), replace=False)
+    return chunks
+
+
+def minibatch_weight(n_chunks: int, minibatch_size: int) -> float:
+    """N / S: the factor that makes the minibatch term an unbiased estimate of the sum over all chunks
+    (reference: mcmc.py:240-247, c = [1, N / S, 1])."""
+    return n_chunks / minibatch_size

@@ -52,3 +52,26 @@ def test_no_fallback_without_a_gpu():
     data = np.zeros((2, 64), dtype=np.int8)
     with pytest.raises((CudaError, RuntimeError)):
         get_kernel(M=16, data=data, double_precision=False)
+
+
+def test_fit_dispatch_rules():
+    """mcmc.py:116-139, 240-247: minibatch size, down-sampling bound, minibatch weight."""
+    import numpy as np
+
+    from phlash_b200 import model
+
+    assert model.default_minibatch_size(595, 1000) == 1       # BASELINE config 2: one genome
+    assert model.default_minibatch_size(5950, 1000) == 5      # config 3
+    assert model.default_minibatch_size(59_500, 1000) == 5    # config 4, before down-sampling
+    assert model.default_minibatch_size(10, 1000) == 1
+    rng = np.random.default_rng(0)
+    chunks = np.arange(59_500 * 3, dtype=np.int32).reshape(59_500, 3)
+    kept = model.downsample_chunks(chunks, 5, 1000, rng)       # 5 * S * niter = 25 000 rows (SURVEY 8a-1)
+    assert kept.shape == (25_000, 3)
+    assert len(np.unique(kept[:, 0])) == 25_000                # without replacement, whole rows
+    assert np.all(kept[:, 1] == kept[:, 0] + 1)
+    same = model.downsample_chunks(chunks[:20_000], 5, 1000, rng)
+    assert same.shape == (20_000, 3)
+    assert model.minibatch_weight(595, 1) == 595.0 and model.minibatch_weight(25_000, 5) == 5000.0
+    inds = model.sample_minibatch(np.random.default_rng(1), 595, 5)
+    assert inds.shape == (5,) and inds.min() >= 0 and inds.max() < 595
