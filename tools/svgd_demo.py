@@ -86,6 +86,7 @@ def run(n_iter=50, S=5, n_bins=3_000_000, device=0, seed=0):
     assert torch.isfinite(x).all()
     return {"svgd_iters_per_s": n_iter / dt, "ms_per_iter": 1e3 * dt / n_iter, "particles": int(x.shape[0]),
             "minibatch_chunks": S, "bins_per_chunk": int(chunks.shape[1]), "n_chunks": int(n_chunks),
+            "log_density_evaluations_per_iteration": 1,
             "mean_log_density_first": history[0], "mean_log_density_last": history[-1],
             "note": "plain-torch RBF SVGD + AMSGrad harness, not blackjax/optax; likelihood, warm-up, parameter "
                     "construction and their gradients run in this repository's CUDA kernels"}
