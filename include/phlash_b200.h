@@ -208,6 +208,13 @@ int phb_params_vjp(phb_kernel *k, const double *x, int64_t B, const int32_t *epo
 int phb_hmm_term_device(phb_kernel *k, const double *x, int64_t B, const int32_t *epoch_widths, int n_epochs,
                         double theta, const int64_t *inds, int64_t S, int64_t overlap, double weight,
                         double *value, double *grad_x, void *stream);
+/* The same with HOST buffers, blocking (x, value, grad_x are a few tens of kilobytes: this is the entry a
+ * jax.pure_callback binds when no FFI handler is built - the host round trip that costs the reference
+ * 2 x 1.1 MB per call, gpu.py:441-465, shrinks to B * (2 P + 1) doubles).  Checks 0 <= inds[s] < N and that
+ * x is finite. */
+int phb_hmm_term_host(phb_kernel *k, const double *x, int64_t B, const int32_t *epoch_widths, int n_epochs,
+                      double theta, const int64_t *inds, int64_t S, int64_t overlap, double weight,
+                      double *value, double *grad_x);
 int phb_hmm_term_sums_device(phb_kernel *k, const double *x, int64_t B, const int32_t *epoch_widths, int n_epochs,
                              double theta, const int64_t *inds, int64_t S, int64_t overlap, int want_grad,
                              double *sums, void *stream);

@@ -82,3 +82,42 @@ class PSMCKernel:
             return out
         value, dlog = out
         return value, PSMCParams(*dlog)
+
+
+def make_hmm_term(full_chunks, M: int, pattern: str, theta: float, overlap: int):
+    """The WHOLE HMM term of ``log_density`` (src/phlash/model.py:50-57) for all particles at once, as a
+    JAX function with a custom VJP, on top of ONE library call per evaluation (``phb_hmm_term_host``:
+    particles -> parameters -> fused warm-up likelihood + gradient -> VJP).
+
+        hmm_term(x, inds, weight) -> [B]       x [B, P] float64: flattened particles (params.py:58-66)
+
+    The host round trip is B * (2 P + 1) doubles (tens of kilobytes) instead of the reference's
+    [B, S, 7, M] blocks; ``full_chunks`` is the chunk matrix BEFORE the warm-up split of mcmc.py:203.
+    Use it in place of lines 50-57 of model.log_density with the vmap over particles lifted out."""
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    kern = _PSMCKernelBase(M, np.asarray(full_chunks))
+
+    def host_call(x, inds, weight, want_grad):
+        value, grad = kern.hmm_term_host(np.asarray(x), pattern, theta, np.asarray(inds), overlap, float(weight), want_grad)
+        return (value, grad) if want_grad else value
+
+    def call(x, inds, weight, want_grad):
+        value_t = jax.ShapeDtypeStruct(x.shape[:1], jnp.float64)
+        if not want_grad:
+            return jax.pure_callback(lambda *a: host_call(*a, False), value_t, x, inds, weight)
+        return jax.pure_callback(lambda *a: host_call(*a, True), (value_t, jax.ShapeDtypeStruct(x.shape, jnp.float64)), x, inds, weight)
+
+    @jax.custom_vjp
+    def hmm_term(x, inds, weight):
+        return call(x, inds, weight, False)
+
+    def forward(x, inds, weight):
+        value, grad = call(x, inds, weight, True)
+        return value, grad
+
+    def backward(grad, cotangent):
+        return cotangent[:, None] * grad, None, None
+
+    hmm_term.defvjp(forward, backward)
+    return hmm_term

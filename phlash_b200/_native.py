@@ -41,6 +41,7 @@ SIGNATURES = {
     "phb_params_from_particles": (_i, [_vp, _vp, _i64, _vp, _i, ctypes.c_double, _vp, _vp]),
     "phb_params_vjp": (_i, [_vp, _vp, _i64, _vp, _i, ctypes.c_double, _vp, _vp, _vp]),
     "phb_hmm_term_device": (_i, [_vp, _vp, _i64, _vp, _i, ctypes.c_double, _vp, _i64, _i64, ctypes.c_double, _vp, _vp, _vp]),
+    "phb_hmm_term_host": (_i, [_vp, _vp, _i64, _vp, _i, ctypes.c_double, _vp, _i64, _i64, ctypes.c_double, _vp, _vp]),
     "phb_hmm_term_sums_device": (_i, [_vp, _vp, _i64, _vp, _i, ctypes.c_double, _vp, _i64, _i64, _i, _vp, _vp]),
     "phb_hmm_term_finish_device": (_i, [_vp, _vp, _i64, _vp, _i, ctypes.c_double, _vp, ctypes.c_double, _vp, _vp, _vp]),
     "phb_stream": (_vp, [_vp]),

@@ -93,6 +93,7 @@ struct phb_kernel {
     std::unordered_map<const void *, int> occupancy;  // per kernel function: attribute set, CTAs per SM
     DeviceBuffer params, inds, ll, dlog, ckpt, gacc, xall, sall, split;
     DeviceBuffer term_params, term_ll, term_dlog, term_sums;  // scratch of the whole-term entries
+    DeviceBuffer term_io;                                     // device copies of the host entry's buffers
     DeviceBuffer transfer_rows, transfer_log;                 // parallel-in-time forward evaluation
     DeviceBuffer bnd_alpha, bnd_beta, seg_dlog;               // ... and gradient
     int parallel_in_time = -1;  // -1 auto, 0 never, 1 whenever possible
@@ -861,6 +862,7 @@ void phb_destroy(phb_kernel *k) {
     k->term_ll.release();
     k->term_dlog.release();
     k->term_sums.release();
+    k->term_io.release();
     k->transfer_rows.release();
     k->transfer_log.release();
     k->bnd_alpha.release();
@@ -1263,6 +1265,36 @@ int phb_hmm_term_device(phb_kernel *k, const double *x, int64_t B, const int32_t
     if (int rc = phb_hmm_term_sums_device(k, x, B, epoch_widths, n_epochs, theta, inds, S, overlap, grad_x != nullptr, sums, stream))
         return rc;
     return phb_hmm_term_finish_device(k, x, B, epoch_widths, n_epochs, theta, sums, weight, value, grad_x, stream);
+}
+
+int phb_hmm_term_host(phb_kernel *k, const double *x, int64_t B, const int32_t *epoch_widths, int n_epochs, double theta,
+                      const int64_t *inds, int64_t S, int64_t overlap, double weight, double *value, double *grad_x) {
+    if (int rc = check_handle(k)) return rc;
+    if (B < 0 || S < 0) return fail(PHB_E_INVALID, "negative batch shape");
+    if (B == 0) return PHB_OK;
+    if (!x || !value || (S > 0 && !inds)) return fail(PHB_E_INVALID, "NULL pointer");
+    for (int64_t s = 0; s < S; ++s)
+        if (inds[s] < 0 || inds[s] >= k->N)
+            return fail(PHB_E_INVALID, "0 <= inds[%lld]=%lld < N=%lld violated", (long long)s, (long long)inds[s], (long long)k->N);
+    const int64_t P = 2 + int64_t(n_epochs) + 1;
+    for (int64_t i = 0; i < B * P; ++i)
+        if (!std::isfinite(x[i])) return fail(PHB_E_INVALID, "not all particle coordinates finite");
+    PHB_CUDA(cudaSetDevice(k->device));
+    // device copies: x [B, P] | value [B] | grad_x [B, P] (doubles), then inds [S]
+    const size_t n_dbl = size_t(B) * P * 2 + size_t(B);
+    if (int rc = k->term_io.reserve(n_dbl * sizeof(double) + size_t(std::max<int64_t>(S, 1)) * sizeof(int64_t))) return rc;
+    double *d_x = static_cast<double *>(k->term_io.ptr);
+    double *d_value = d_x + B * P;
+    double *d_grad = d_value + B;
+    int64_t *d_inds = reinterpret_cast<int64_t *>(d_grad + B * P);
+    PHB_CUDA(cudaMemcpyAsync(d_x, x, size_t(B) * P * sizeof(double), cudaMemcpyHostToDevice, k->stream));
+    if (S > 0) PHB_CUDA(cudaMemcpyAsync(d_inds, inds, size_t(S) * sizeof(int64_t), cudaMemcpyHostToDevice, k->stream));
+    if (int rc = phb_hmm_term_device(k, d_x, B, epoch_widths, n_epochs, theta, d_inds, S, overlap, weight, d_value,
+                                     grad_x ? d_grad : nullptr, k->stream))
+        return rc;
+    PHB_CUDA(cudaMemcpyAsync(value, d_value, size_t(B) * sizeof(double), cudaMemcpyDeviceToHost, k->stream));
+    if (grad_x) PHB_CUDA(cudaMemcpyAsync(grad_x, d_grad, size_t(B) * P * sizeof(double), cudaMemcpyDeviceToHost, k->stream));
+    return phb_sync(k);
 }
 
 }  // extern "C"

@@ -331,6 +331,30 @@ class _PSMCKernelBase:
         )
         return value, grad_x
 
+    def hmm_term_host(self, x: np.ndarray, pattern: str, theta: float, inds: np.ndarray, overlap: int,
+                      weight: float = 1.0, grad: bool = True):
+        """`hmm_term` with NumPy buffers, blocking (phb_hmm_term_host): x float64 [B, P], inds int [S] ->
+        (weight * l2 [B], weight * d l2 / d x [B, P] or None).  No torch involved: the entry a
+        `jax.pure_callback` binds."""
+        from phlash_b200.params import parse_pattern
+
+        widths = np.ascontiguousarray(parse_pattern(pattern), dtype=np.int32)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        inds = np.ascontiguousarray(inds, dtype=np.int64)
+        B, P = x.shape
+        assert P == 2 + len(widths) + 1, "particle length does not match the pattern"
+        assert inds.ndim == 1 and (len(inds) == 0 or (inds.min() >= 0 and inds.max() < self._N))
+        assert np.isfinite(x).all(), "not all particle coordinates finite"
+        value = np.empty(B, dtype=np.float64)
+        grad_x = np.empty((B, P), dtype=np.float64) if grad else None
+        _check(
+            self._lib.phb_hmm_term_host(
+                self._handle, _ptr(x), B, _ptr(widths), len(widths), float(theta), _ptr(inds) if len(inds) else None,
+                len(inds), int(overlap), float(weight), _ptr(value), _ptr(grad_x) if grad else None,
+            )
+        )
+        return value, grad_x
+
     def params_vjp(self, x, pattern: str, theta: float, cotangent, stream=None):
         """cotangent [B, 7, M] = d l / d log(theta) (kernel float type).  Returns d l / d x [B, P]."""
         import torch

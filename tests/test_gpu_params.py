@@ -180,3 +180,28 @@ def test_whole_term_gradient_by_finite_differences(golden):
         fd = (kern.hmm_term(xp, PATTERN16, 1e-2, inds, 50, 2.0, grad=False)[0]
               - kern.hmm_term(xm, PATTERN16, 1e-2, inds, 50, 2.0, grad=False)[0]) / (2 * h)
         torch.testing.assert_close(grad[:, p], fd, rtol=2e-5, atol=1e-5)
+
+
+def test_whole_term_host_entry(golden):
+    """phb_hmm_term_host (NumPy buffers, blocking) equals the device entry; input checks raise."""
+    import torch
+
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    chunks, inds_np = golden["model_chunks"], golden["model_inds"]
+    kern = _PSMCKernelBase(16, chunks)
+    x_np = golden["part_x"][:5]
+    val_h, grad_h = kern.hmm_term_host(x_np, PATTERN16, 1e-2, inds_np, 50, weight=2.5)
+    dev = torch.device("cuda:0")
+    val_d, grad_d = kern.hmm_term(torch.tensor(x_np, device=dev), PATTERN16, 1e-2, torch.tensor(inds_np, device=dev), 50, weight=2.5)
+    np.testing.assert_array_equal(val_h, val_d.cpu().numpy())
+    np.testing.assert_array_equal(grad_h, grad_d.cpu().numpy())
+    val_f, none = kern.hmm_term_host(x_np, PATTERN16, 1e-2, inds_np, 50, weight=2.5, grad=False)
+    assert none is None
+    np.testing.assert_allclose(val_f, val_h, rtol=1e-6)
+    with pytest.raises(AssertionError):
+        kern.hmm_term_host(x_np, PATTERN16, 1e-2, np.array([len(chunks)]), 50)
+    bad = x_np.copy()
+    bad[0, 0] = np.nan
+    with pytest.raises(AssertionError):
+        kern.hmm_term_host(bad, PATTERN16, 1e-2, inds_np, 50)
