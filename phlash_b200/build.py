@@ -10,10 +10,11 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "_lib", "libphlash_b200.so")
 SOURCES = [os.path.join(_PKG, "csrc", "phlash_b200.cu")]
-DEPS = SOURCES + [
-    os.path.join(_PKG, "csrc", "psmc_kernels.cuh"),
-    os.path.join(os.path.dirname(_PKG), "include", "phlash_b200.h"),
-]
+import glob  # noqa: E402
+
+# every source / header the library is built from: editing any of them rebuilds
+DEPS = sorted(set(SOURCES + glob.glob(os.path.join(_PKG, "csrc", "*.cu*")) + glob.glob(os.path.join(_PKG, "csrc", "*.h"))
+                  + glob.glob(os.path.join(os.path.dirname(_PKG), "include", "*.h"))))
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -103,6 +103,9 @@ struct phb_kernel {
     uint8_t *d_rowflag = nullptr;  // [N]
     int64_t n_flagged = 0;
     int escalate = 1;
+    // experiment knobs, read from the environment ONCE when the object is created (never per call):
+    // PHB_NT, PHB_STORE_ALL, PHB_PARALLEL_IN_TIME, PHB_PIT_SEGMENTS
+    int env_nt = 0, env_store_all = -2, env_pit = -2, env_pit_segments = 0;
     size_t elem() const { return dbl ? sizeof(double) : sizeof(float); }
 };
 
@@ -279,8 +282,7 @@ const Variant *pick_variant(const phb_kernel *k, bool grad, int64_t n_pairs) {
     // help a little; above it the thread-per-pair layout is already the fastest.
     const int64_t fill = int64_t(k->num_sms) * 64;
     // tuning knob: PHB_NT=<threads per CTA> picks among variants that differ only in CTA size
-    const char *nt_env = getenv("PHB_NT");
-    const int want_nt = nt_env ? atoi(nt_env) : 0;
+    const int want_nt = k->env_nt;
     for (const Variant &v : variants()) {
         if (v.M != k->M || v.dbl != (k->dbl != 0) || v.grad != grad) continue;
         if (last && last->T == v.T && v.NT != want_nt) continue;  // same layout, other CTA size
@@ -341,7 +343,7 @@ int try_parallel_in_time_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaS
     // as many segments as keep every group of the segment passes resident at once
     int64_t n_seg = std::min(resident / seg_ctas, a.L / min_seg);
     if (pit_mode == 1) n_seg = std::max<int64_t>(n_seg, std::min<int64_t>(3, a.L / min_seg));
-    if (const char *g_env = getenv("PHB_PIT_SEGMENTS")) n_seg = std::min<int64_t>(atoi(g_env), a.L / 64);  // experiments
+    if (k->env_pit_segments > 0) n_seg = std::min<int64_t>(k->env_pit_segments, a.L / 64);  // experiments
     if (n_seg < 3) return kNotTaken;
     const int64_t seg_len = ((a.L + n_seg - 1) / n_seg + 15) / 16 * 16;
     n_seg = (a.L + seg_len - 1) / seg_len;
@@ -391,7 +393,7 @@ int try_parallel_in_time_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaS
     }
     const int64_t n_out = n_pairs * 7 * M;
     phb::sum_segments_kernel<float><<<unsigned((n_out + 255) / 256), 256, 0, stream>>>(
-        static_cast<const float *>(k->seg_dlog.ptr), n_pairs, n_seg, M, static_cast<float *>(a.dlog), a.out_mode);
+        static_cast<const float *>(k->seg_dlog.ptr), n_pairs, n_seg, M, static_cast<float *>(a.dlog), a.out_mode, a);
     PHB_CUDA(cudaGetLastError());
     k->launches += 4;
     snprintf(k->last_name, sizeof k->last_name, "transfer_rows_kernel<float,M=%d> + psmc_loglik_kernel<SEG,MT=%d,T=%d> x %lld segments", M,
@@ -430,7 +432,7 @@ int try_two_sweep_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t
     const int64_t seg_ctas = (n_pairs + pairs_per_group - 1) / pairs_per_group;  // groups per segment
     const int64_t min_seg = pit_mode == 2 ? 64 : 1024;
     int64_t n_seg = std::min(std::max<int64_t>(resident / seg_ctas, 2), a.L / min_seg);
-    if (const char *g_env = getenv("PHB_PIT_SEGMENTS")) n_seg = std::min<int64_t>(atoi(g_env), a.L / 64);  // experiments
+    if (k->env_pit_segments > 0) n_seg = std::min<int64_t>(k->env_pit_segments, a.L / 64);  // experiments
     // measured at B = 500, L = 50 000, M = 16 (profiles/r01_probe_parallel_in_time.log)
     if (n_seg < (pit_mode == 2 ? 2 : 6)) return kNotTaken;
     const int64_t seg_len = ((a.L + n_seg - 1) / n_seg + 15) / 16 * 16;
@@ -465,7 +467,7 @@ int try_two_sweep_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t
     PHB_CUDA(cudaLaunchKernel(tv->func, dim3(unsigned(grid)), dim3(tv->NT), kargs, tv->smem, stream));
     const int64_t n_out = n_pairs * 7 * M;
     phb::sum_segments_kernel<float><<<unsigned((n_out + 255) / 256), 256, 0, stream>>>(
-        static_cast<const float *>(k->seg_dlog.ptr), n_pairs, n_seg, M, static_cast<float *>(a.dlog), a.out_mode);
+        static_cast<const float *>(k->seg_dlog.ptr), n_pairs, n_seg, M, static_cast<float *>(a.dlog), a.out_mode, a);
     PHB_CUDA(cudaGetLastError());
     k->launches += 3;
     snprintf(k->last_name, sizeof k->last_name, "boundary_sweep_kernel<float,MT=%d,T=%d> + psmc_loglik_kernel<SEG,MT=%d,T=%d> x %lld segments",
@@ -600,19 +602,19 @@ int launch_throughput_kernel(phb_kernel *k, phb::KernelArgs a, bool grad, cudaSt
     return PHB_OK;
 }
 
-// One evaluation on `stream` over the whole minibatch or over the sub-list in `a`.
-int launch_one(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream, const Variant *fixed) {
-    // tuning knobs for experiments: PHB_STORE_ALL / PHB_PARALLEL_IN_TIME = 0 / 1 override the modes set through the API
-    const char *sa_env = getenv("PHB_STORE_ALL");
-    const int sa_mode = sa_env ? atoi(sa_env) : k->store_all_mode;
-    const char *pit_env = getenv("PHB_PARALLEL_IN_TIME");
-    const int pit_mode = pit_env ? atoi(pit_env) : k->parallel_in_time;
+// One evaluation on `stream` over the whole minibatch or over the sub-list in `a`.  pit_only: try the
+// parallel-in-time gradient paths only (they honour a.skip_flag) and report kNotTaken otherwise.
+int launch_one(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream, const Variant *fixed, bool pit_only = false) {
+    // experiment knobs PHB_STORE_ALL / PHB_PARALLEL_IN_TIME (read at creation) override the modes set through the API
+    const int sa_mode = k->env_store_all != -2 ? k->env_store_all : k->store_all_mode;
+    const int pit_mode = k->env_pit != -2 ? k->env_pit : k->parallel_in_time;
     const bool free_choice = !fixed && !k->dbl && k->force_T == 0;
     int rc = kNotTaken;
     if (free_choice && grad && pit_mode != 0 && pit_mode != 2 && sa_mode != 0 && a.s_list == nullptr)
         rc = try_parallel_in_time_gradient(k, a, stream, pit_mode);
     if (rc == kNotTaken && free_choice && grad && pit_mode != 0 && pit_mode != 1 && sa_mode != 0 && a.s_list == nullptr)
         rc = try_two_sweep_gradient(k, a, stream, pit_mode);
+    if (pit_only) return rc;
     if (rc == kNotTaken && free_choice && grad && sa_mode != 0) rc = try_store_all(k, a, stream, sa_mode);
     if (rc == kNotTaken && free_choice && !grad && pit_mode != 0 && a.s_list == nullptr)
         rc = try_parallel_in_time_forward(k, a, stream, pit_mode);
@@ -638,10 +640,16 @@ int launch(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream) {
         phb::split_minibatch_kernel<<<1, 1024, 0, stream>>>(a.inds, a.S, k->d_rowflag, k->N, lists, counts);
         PHB_CUDA(cudaGetLastError());
         k->launches += 1;
+        // The decision is per CALL, not per object: a small minibatch goes through the parallel-in-time paths
+        // whether or not it holds a marked row (they score everything and leave the outputs of marked rows
+        // to the double launch below); larger ones run the ordinary kernels over the un-marked sub-list.
+        phb::KernelArgs whole = a;
+        whole.skip_flag = k->d_rowflag;
+        rc = launch_one(k, whole, grad, stream, nullptr, /*pit_only=*/true);
         phb::KernelArgs part = a;
         part.s_list = lists;
         part.s_count = counts;
-        rc = launch_one(k, part, grad, stream, nullptr);
+        if (rc == kNotTaken) rc = launch_one(k, part, grad, stream, nullptr);
         if (rc == PHB_OK) {
             part.s_list = lists + a.S;
             part.s_count = counts + 1;
@@ -700,6 +708,10 @@ static int new_kernel(int M, int64_t N, int64_t L, int double_precision, int dev
     k->L = L;
     k->pitch = (L + 15) / 16 * 16;
     k->num_sms = prop.multiProcessorCount;
+    if (const char *v = getenv("PHB_NT")) k->env_nt = atoi(v);
+    if (const char *v = getenv("PHB_STORE_ALL")) k->env_store_all = atoi(v);
+    if (const char *v = getenv("PHB_PARALLEL_IN_TIME")) k->env_pit = atoi(v);
+    if (const char *v = getenv("PHB_PIT_SEGMENTS")) k->env_pit_segments = atoi(v);
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&k->d_data), size_t(N) * size_t(k->pitch));
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -993,6 +1005,8 @@ int phb_sync(phb_kernel *k) {
     PHB_CUDA(cudaMemcpy(&flag, k->d_err, sizeof flag, cudaMemcpyDeviceToHost));
     if (flag) PHB_CUDA(cudaMemset(k->d_err, 0, sizeof(int)));
     if (flag & 1) return fail(PHB_E_INVALID, "index out of range: need 0 <= inds < N=%lld", (long long)k->N);
+    // (reference: assert np.isfinite on the parameters, gpu.py:214; a non-finite parameter gives a non-finite ll)
+    if (flag & 2) return fail(PHB_E_INVALID, "not all parameters / results finite");
     return PHB_OK;
 }
 

@@ -75,6 +75,10 @@ struct KernelArgs {
     // in device memory, so the split needs no host round trip.  nullptr = all S chunks.
     const int32_t *s_list;
     const int32_t *s_count;
+    // Parallel-in-time paths score the WHOLE minibatch (their grids are sized on the host) but leave the
+    // outputs of pairs whose row is marked in skip_flag ([N], see flag_long_runs_kernel) untouched: those
+    // pairs belong to the double-arithmetic launch that follows.  nullptr = write everything.
+    const uint8_t *skip_flag;
     // Segment mode of the gradient kernel (parallel-in-time gradient, see chain_boundaries_kernel): the
     // launch scores the G segments of every chunk as independent short "pairs" (L = sites per chunk),
     // started from bnd_alpha and closed with bnd_beta; partial gradients go to seg_dlog.
@@ -92,6 +96,12 @@ struct PairIndex {
     int64_t b, s, out;  // particle, position in the full minibatch, index into ll / dlog ([B, S])
 };
 __device__ __forceinline__ int64_t listed_chunks(const KernelArgs &a) { return a.s_list ? int64_t(*a.s_count) : a.S; }
+// does another launch own the outputs of the pairs on chunk position ps?
+__device__ __forceinline__ bool outputs_skipped(const KernelArgs &a, int64_t ps) {
+    if (a.skip_flag == nullptr) return false;
+    const int64_t row = a.inds[ps];
+    return row >= 0 && row < a.n_rows && a.skip_flag[row] != 0;
+}
 __device__ __forceinline__ PairIndex pair_index(const KernelArgs &a, int64_t pair, int64_t s_eff) {
     PairIndex r;
     r.b = pair / s_eff;
@@ -1311,7 +1321,7 @@ template <typename F, int M> __global__ void chain_boundaries_kernel(const Trans
         v = next / group_max<M>(next);
         if (writer) be[g * M + k] = F(v);
     }
-    if (writer && k == 0) {
+    if (writer && k == 0 && !outputs_skipped(a, ps)) {
         double ll = ll2 * 0.69314718055994530942;
         const int64_t row = a.inds[ps];
         if (row < 0 || row >= a.n_rows) {
@@ -1328,12 +1338,13 @@ template <typename F, int M> __global__ void chain_boundaries_kernel(const Trans
 // one of the first segment.  One thread per output entry.
 template <typename F>
 __global__ void sum_segments_kernel(const F *__restrict__ seg_dlog, int64_t n_pairs, int64_t G, int M, F *__restrict__ dlog,
-                                    int out_mode) {
+                                    int out_mode, const KernelArgs a) {
     const int64_t n = n_pairs * 7 * M;
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t pair = i / (7 * M);
     const int64_t rm = i % (7 * M);
+    if (outputs_skipped(a, pair % a.S)) return;
     const F *src = seg_dlog + pair * G * 7 * M + rm;
     double acc = double(src[0]);
     if (rm < 6 * M)
@@ -1480,7 +1491,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) boundary_sweep_kernel(const Kern
             if (sub == 0) atomicOr(a.err_flag, 1);
             ll = __longlong_as_double(0x7ff8000000000000LL);
         }
-        if (writer && sub == 0) a.ll[pair] = a.out_mode ? a.ll[pair] - ll : ll;
+        if (writer && sub == 0 && !outputs_skipped(a, ps)) a.ll[pair] = a.out_mode ? a.ll[pair] - ll : ll;
     } else {
         F beta[MT];
 #pragma unroll

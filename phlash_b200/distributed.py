@@ -64,21 +64,22 @@ class ShardedPSMCKernel:
         live = dist.is_available() and dist.is_initialized()
         self.rank = rank if rank is not None else (dist.get_rank() if live else 0)
         self.world = world if world is not None else (dist.get_world_size() if live else 1)
-        self._packed = None
 
     def loglik_grad_sum(self, params6, pi, inds):
-        """params6 [B, 6, M], pi [B, M], inds [S] (global minibatch, identical on every rank), all
-        device tensors.  Returns (ll [B], dlog [B, 7, M]) summed over ALL S chunks, on every rank."""
+        """params6 [B, 6, M], pi [B, M] SHARED by the chunks of a particle, inds [S] (global minibatch,
+        identical on every rank), all device tensors.  Returns (ll [B], dlog [B, 7, M]) summed over ALL S
+        chunks, on every rank, in a fresh buffer per call (B (1 + 7 M) doubles) that the caller owns.
+        With a shared pi the terms are additive over chunks; for the reference's per-chunk warm-up pi
+        (model.py:52-55) use model.hmm_term_value_and_grad, whose fused warm-up keeps them additive."""
         import torch
 
         lo, hi = shard_bounds(int(inds.shape[0]), self.rank, self.world)
         B, M = int(params6.shape[0]), int(params6.shape[2])
-        if self._packed is None or self._packed.shape != (B, 1 + 7 * M):
-            self._packed = torch.empty((B, 1 + 7 * M), dtype=torch.float64, device=params6.device)
+        packed = torch.empty((B, 1 + 7 * M), dtype=torch.float64, device=params6.device)
         if hi > lo:
             ll, dlog = self.kern.evaluate_device(params6, pi, inds[lo:hi].contiguous(), True)
-            pack_per_particle(ll, dlog, out=self._packed)
+            pack_per_particle(ll, dlog, out=packed)
         else:
-            self._packed.zero_()
-        all_reduce_sum(self._packed)
-        return unpack_per_particle(self._packed, M)
+            packed.zero_()
+        all_reduce_sum(packed)
+        return unpack_per_particle(packed, M)

@@ -162,3 +162,37 @@ def test_bad_index_is_still_reported():
         kern.sync()
     ll = ll.cpu().numpy()
     assert np.isnan(ll[:, [1, 3]]).all() and np.isfinite(ll[:, [0, 2]]).all()
+
+
+def test_small_minibatch_keeps_parallel_in_time_with_marked_rows_in_the_data():
+    """The split is decided per call: real data always holds marked rows (the padded last chunk of every
+    contig), and a minibatch of ONE or FIVE chunks must still take the parallel-in-time gradient paths -
+    with marked chunks in the minibatch scored in double by the second launch."""
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    het = orc.synth_het_matrix(1, 420_000, seed=5)
+    data = orc.chunk_het_matrix(het, 500, 50_000)[:, 500:].copy()  # 9 chunks, the last one padded
+    pps, _, _ = orc.synth_particles(16, 40, seed=3)
+    kern = _PSMCKernelBase(16, data)
+    assert kern.num_escalated_rows == 1
+    for inds in (np.array([2]), np.array([8]), np.array([1, 8, 3, 8, 0])):
+        pa = np.broadcast_to(pps[:, None], (len(pps), len(inds), 7, 16)).copy()
+        ll, dlog = kern.evaluate(pa, inds, True)
+        assert "segments" in kern.last_kernel_name, kern.last_kernel_name
+        ref_ll, ref_dlog = oracle_eval(data, inds, pa)
+        np.testing.assert_allclose(ll, ref_ll, rtol=LL_RTOL)
+        grad_close(dlog, ref_dlog, GRAD_RTOL, f"inds={inds}")
+    # fused warm-up form (second launch subtracts): marked pairs must not be subtracted twice
+    full = orc.chunk_het_matrix(het, 500, 50_000)
+    kw = _PSMCKernelBase(16, full)
+    inds = np.array([8, 4])
+    p7 = pps[:12].astype(np.float32).astype(np.float64)
+    ll, dlog = kw.evaluate_warmup(p7, inds, 500, True)
+    assert "segments" in kw.last_kernel_name or "storeall" in kw.last_kernel_name
+    from test_warmup import oracle_warmup
+
+    want_ll, want_dlog, parts = oracle_warmup(full, inds, p7, 500, np.float32, with_parts=True)
+    np.testing.assert_allclose(ll, want_ll, rtol=LL_RTOL)
+    # (the difference of two evaluations: tolerance relative to the terms that were subtracted)
+    scale = np.abs(parts).max(-1, keepdims=True)
+    assert np.all(np.abs(dlog - want_dlog) <= GRAD_RTOL * parts + GRAD_RTOL * 1e-3 * scale)

@@ -298,6 +298,30 @@ def test_full_length_chunks_against_oracle(long_case):
     np.testing.assert_allclose(dlog64, ref_dlog64, rtol=1e-7, atol=1e-12)
 
 
+@pytest.mark.parametrize("M,T", [(16, 1), (32, 2)])
+def test_headline_throughput_kernel_full_length(long_case, M, T):
+    """THE kernel bench.py times - the thread-per-pair throughput kernel (MT = 16; non-segment mode,
+    checkpoints + recompute, 1024-site fp32 windows flushed into fp64 slots) - at the benchmark's chunk
+    length, against the fp64 oracle.  threads_per_pair forces the throughput path (no parallel-in-time /
+    store-all dispatch), so all 6 250 checkpoint segments and 48 window flushes of a 50 000-bin chunk run.
+    8 particles x all 9 chunks including the padded one (scored by the double build), and the same
+    layout with two lanes per pair at M = 32.  Mirrors tests/test_gpu.py:59-64 of the reference."""
+    data, pps16 = long_case
+    pps = pps16 if M == 16 else orc.synth_particles(M, 8, seed=M)[0]
+    kern = make_kernel(M, data, T=T).gpu_kernels[0]
+    inds = np.arange(data.shape[0])
+    pa = np.broadcast_to(pps[:8, None], (8, len(inds), 7, M)).copy()
+    ll, dlog = kern.evaluate(pa, inds, True)
+    assert f"psmc_loglik_kernel<float,MT=16,T={T},K=8,grad" in kern.last_kernel_name, kern.last_kernel_name
+    ref_ll, ref_dlog = oracle_eval(data, inds, pa)
+    np.testing.assert_allclose(ll, ref_ll, rtol=LL_RTOL)
+    grad_close(dlog, ref_dlog, GRAD_RTOL, f"throughput kernel M={M} T={T} L=50000")
+    # forward-only build of the same layout
+    ll_fwd = kern.evaluate(pa, inds, False)
+    assert f"T={T}" in kern.last_kernel_name and "fwd" in kern.last_kernel_name
+    np.testing.assert_allclose(ll_fwd, ref_ll, rtol=LL_RTOL)
+
+
 def test_full_length_invariants(long_case):
     """Properties that hold for any parameters, checked on every pair without the oracle:
     the posterior of each site sums to one, so  sum_m (dlog_e0 + dlog_e1)[m] = #non-missing sites,
