@@ -61,6 +61,15 @@ int phb_device_count(void);
 int phb_create(int M, const int8_t *data, int64_t N, int64_t L, int double_precision, int device,
                phb_kernel **out);
 
+/* The same for FULL chunks [N, W = overlap + L] as init_mcmc_data returns them (data.py:506-558), i.e. for
+ * the fused warm-up entries below.  The reference splits the warm-up columns off BEFORE it builds its kernel
+ * object (mcmc.py:203-209), so its "every row has an observation" check (gpu.py:111-113) sees the data part
+ * only; here the check covers columns [overlap, W) likewise.  All checks (values >= -1, clipping to <= 1,
+ * observed rows) run on the device after the copy, which is staged through pinned buffers by a few host
+ * threads: the host never walks the matrix (BASELINE config 5 is 50 GB). */
+int phb_create_chunks(int M, const int8_t *chunks, int64_t N, int64_t W, int64_t overlap, int double_precision,
+                      int device, phb_kernel **out);
+
 /* Create a kernel object from BINNED CONTIGS instead of ready-made chunks: het is host int8
  * [n_rows, length] (one row per diploid of one contig); the overlapping windows of
  * _chunk_het_matrix (data.py:37-61: ceil(length / W) windows of W = chunk_size + overlap bins per
@@ -143,6 +152,31 @@ int phb_loglik_host(phb_kernel *k, const void *params, const int64_t *inds, int6
 int phb_loglik_shared_host(phb_kernel *k, const void *params6, const void *pi, int pi_per_pair,
                            const int64_t *inds, int64_t B, int64_t S, int want_grad, double *ll,
                            void *dlog);
+
+/* ALLOCATION-FREE, CAPTURABLE STEPS.  phb_reserve sizes every scratch buffer and sets every kernel
+ * attribute that an evaluation with `B` particles and up to `S_max` chunks per minibatch can need (both the
+ * plain call and the fused warm-up / whole-term entries with this `overlap`), by running the dispatcher
+ * "dry" for each minibatch size.  Afterwards such calls neither allocate nor free device memory nor query
+ * the driver, so a caller may record them into a CUDA graph (cudaStreamBeginCapture on the stream it passes,
+ * or XLA's command buffers); phb_allocation_count reports how many device allocations the object's scratch
+ * buffers have made so far (tests: unchanged across calls after phb_reserve). */
+int phb_reserve(phb_kernel *k, int64_t B, int64_t S_max, int64_t overlap, int want_grad);
+int64_t phb_allocation_count(const phb_kernel *k);
+
+/* MINIBATCH SAMPLING ON THE DEVICE (replaces `inds = jax.random.choice(subkey, N, (S,))` and the host
+ * gather `warmup_chunks[inds]`, mcmc.py:277-278: the warm-up bins are resident with the chunks, so the
+ * indices are all an iteration needs).  inds[s] = phb_minibatch_indices(seed, it, N, S)[s], S draws WITH
+ * replacement from [0, N), where `it` is the object's iteration counter, which the call then advances -
+ * a captured graph therefore draws a new minibatch at every replay.  phb_minibatch_indices is the same
+ * counter-based generator on the host (pure function: reproducibility, tests). */
+int phb_sample_minibatch_device(phb_kernel *k, uint64_t seed, int64_t S, int64_t *inds, void *stream);
+int phb_set_iteration(phb_kernel *k, uint64_t iteration, void *stream);
+void phb_minibatch_indices(uint64_t seed, uint64_t iteration, int64_t N, int64_t S, int64_t *inds);
+
+/* FP32 FMA throughput of `device` measured now (TFLOP/s, best of 10): independent FFMA chains - the roofline
+ * denominator bench.py quotes - and, optionally, the accumulate pattern acc += x * y with three distinct
+ * register operands, which is what gradient sums look like to the register file. */
+int phb_measure_fp32_peak(int device, double *independent_tflops, double *accumulate_tflops);
 
 /* The kernel object's own (non-blocking) stream, as a cudaStream_t.  The host entries run on it. */
 void *phb_stream(const phb_kernel *k);

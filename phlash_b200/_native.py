@@ -20,6 +20,13 @@ SIGNATURES = {
     "phb_last_error": (ctypes.c_char_p, []),
     "phb_device_count": (_i, []),
     "phb_create": (_i, [_i, _vp, _i64, _i64, _i, _i, ctypes.POINTER(_vp)]),
+    "phb_create_chunks": (_i, [_i, _vp, _i64, _i64, _i64, _i, _i, ctypes.POINTER(_vp)]),
+    "phb_reserve": (_i, [_vp, _i64, _i64, _i64, _i]),
+    "phb_allocation_count": (_i64, [_vp]),
+    "phb_sample_minibatch_device": (_i, [_vp, ctypes.c_uint64, _i64, _vp, _vp]),
+    "phb_set_iteration": (_i, [_vp, ctypes.c_uint64, _vp]),
+    "phb_minibatch_indices": (None, [ctypes.c_uint64, ctypes.c_uint64, _i64, _i64, _vp]),
+    "phb_measure_fp32_peak": (_i, [_i, _dp, _dp]),
     "phb_create_from_contig": (_i, [_i, _vp, _i64, _i64, _i64, _i64, _i, _i, ctypes.POINTER(_vp)]),
     "phb_download_data": (_i, [_vp, _vp]),
     "phb_destroy": (None, [_vp]),

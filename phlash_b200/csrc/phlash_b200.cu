@@ -5,6 +5,7 @@
 #include "../../include/phlash_b200.h"
 #include "psmc_kernels.cuh"
 #include "psmc_params.cuh"
+#include "psmc_support.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -14,6 +15,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -42,8 +44,10 @@ int fail(int code, const char *fmt, ...) {
 struct DeviceBuffer {
     void *ptr = nullptr;
     size_t cap = 0;
+    int64_t *counter = nullptr;  // incremented on every (re)allocation
     int reserve(size_t bytes) {
         if (bytes <= cap) return PHB_OK;
+        if (counter) ++*counter;
         if (ptr) cudaFree(ptr);
         ptr = nullptr;
         cap = 0;
@@ -106,6 +110,11 @@ struct phb_kernel {
     // experiment knobs, read from the environment ONCE when the object is created (never per call):
     // PHB_NT, PHB_STORE_ALL, PHB_PARALLEL_IN_TIME, PHB_PIT_SEGMENTS
     int env_nt = 0, env_store_all = -2, env_pit = -2, env_pit_segments = 0;
+    // phb_reserve(): the dispatch runs with dry = true - every scratch buffer is sized and every kernel
+    // attribute set exactly as a real call would, but nothing is launched
+    bool dry = false;
+    unsigned long long *d_iteration = nullptr;  // minibatch counter of phb_sample_minibatch_device
+    int64_t allocations = 0;                    // device allocations made by the scratch buffers (tests: no growth after reserve)
     size_t elem() const { return dbl ? sizeof(double) : sizeof(float); }
 };
 
@@ -362,6 +371,7 @@ int try_parallel_in_time_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaS
         PHB_CUDA(cudaFuncSetAttribute(tv->rows_func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tv->smem)));
         k->occupancy.emplace(tv->rows_func, 1);
     }
+    if (k->dry) return PHB_OK;
     phb::TransferArgs ta{};
     ta.k = a;
     ta.k.err_flag = k->d_err;
@@ -451,6 +461,7 @@ int try_two_sweep_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t
         PHB_CUDA(cudaFuncSetAttribute(sv->sweep_func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sv->smem)));
         k->occupancy.emplace(sv->sweep_func, 1);
     }
+    if (k->dry) return PHB_OK;
     phb::KernelArgs sa = a;
     sa.err_flag = k->d_err;
     sa.ckpt = k->ckpt.ptr;
@@ -506,6 +517,7 @@ int try_store_all(phb_kernel *k, phb::KernelArgs a, cudaStream_t stream, int sa_
             PHB_CUDA(cudaFuncSetAttribute(sv.func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sv.smem)));
             k->occupancy.emplace(sv.func, 1);
         }
+        if (k->dry) return PHB_OK;
         void *kargs[] = {&a};
         PHB_CUDA(cudaLaunchKernel(sv.func, dim3(unsigned(grid)), dim3(sv.NT), kargs, sv.smem, stream));
         k->launches += 1;
@@ -547,6 +559,7 @@ int try_parallel_in_time_forward(phb_kernel *k, const phb::KernelArgs &a, cudaSt
                 PHB_CUDA(cudaFuncSetAttribute(tv->rows_func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tv->smem)));
                 k->occupancy.emplace(tv->rows_func, 1);
             }
+            if (k->dry) return PHB_OK;
             void *kargs[] = {&ta};
             PHB_CUDA(cudaLaunchKernel(tv->rows_func, dim3(unsigned((n_virtual + 127) / 128)), dim3(128), kargs, tv->smem, stream));
             PHB_CUDA(cudaLaunchKernel(tv->chain_func, dim3(unsigned((n_pairs + 63) / 64)), dim3(64), kargs, 0, stream));
@@ -593,6 +606,7 @@ int launch_throughput_kernel(phb_kernel *k, phb::KernelArgs a, bool grad, cudaSt
         a.gacc = static_cast<double *>(k->gacc.ptr);
     }
     a.err_flag = k->d_err;
+    if (k->dry) return PHB_OK;
     void *kargs[] = {&a};
     PHB_CUDA(cudaLaunchKernel(v->func, dim3(unsigned(grid)), dim3(v->NT), kargs, smem, stream));
     k->launches += 1;
@@ -627,7 +641,14 @@ int launch_one(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream,
 int launch(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream) {
     if (a.B * a.S == 0) return PHB_OK;
     const Variant *esc = (grad && !k->dbl && k->escalate && k->n_flagged > 0) ? escalation_variant(k->M) : nullptr;
-    PHB_CUDA(cudaEventRecord(k->ev0, stream));
+    // the timing events are skipped inside a stream capture (a captured event cannot be queried) and in a dry run
+    bool timing = !k->dry;
+    if (timing) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess) cudaGetLastError();
+        timing = cs == cudaStreamCaptureStatusNone;
+    }
+    if (timing) PHB_CUDA(cudaEventRecord(k->ev0, stream));
     int rc;
     if (!esc) {
         rc = launch_one(k, a, grad, stream, nullptr);
@@ -637,9 +658,11 @@ int launch(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream) {
         if ((rc = k->split.reserve((size_t(2) * a.S + 2) * sizeof(int32_t))) != PHB_OK) return rc;
         int32_t *lists = static_cast<int32_t *>(k->split.ptr);
         int32_t *counts = lists + 2 * a.S;
-        phb::split_minibatch_kernel<<<1, 1024, 0, stream>>>(a.inds, a.S, k->d_rowflag, k->N, lists, counts);
-        PHB_CUDA(cudaGetLastError());
-        k->launches += 1;
+        if (!k->dry) {
+            phb::split_minibatch_kernel<<<1, 1024, 0, stream>>>(a.inds, a.S, k->d_rowflag, k->N, lists, counts);
+            PHB_CUDA(cudaGetLastError());
+            k->launches += 1;
+        }
         // The decision is per CALL, not per object: a small minibatch goes through the parallel-in-time paths
         // whether or not it holds a marked row (they score everything and leave the outputs of marked rows
         // to the double launch below); larger ones run the ordinary kernels over the un-marked sub-list.
@@ -657,8 +680,12 @@ int launch(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream) {
         }
     }
     if (rc != PHB_OK) return rc;
-    PHB_CUDA(cudaEventRecord(k->ev1, stream));
-    k->timed = true;
+    if (timing) {
+        PHB_CUDA(cudaEventRecord(k->ev1, stream));
+        k->timed = true;
+    } else if (!k->dry) {
+        k->timed = false;
+    }
     return PHB_OK;
 }
 
@@ -672,7 +699,7 @@ template <typename F> bool all_finite(const F *p, size_t n) {
 
 extern "C" {
 
-int phb_abi_version(void) { return 2; }
+int phb_abi_version(void) { return 3; }
 
 const char *phb_last_error(void) { return g_err.c_str(); }
 
@@ -718,7 +745,13 @@ static int new_kernel(int M, int64_t N, int64_t L, int double_precision, int dev
         phb_destroy(k);
         return fail(PHB_E_NOMEM, "While trying to allocate %lld bytes on GPU: %s", (long long)(N * k->pitch), cudaGetErrorString(e));
     }
+    for (DeviceBuffer *b : {&k->params, &k->inds, &k->ll, &k->dlog, &k->ckpt, &k->gacc, &k->xall, &k->sall, &k->split, &k->term_params,
+                            &k->term_ll, &k->term_dlog, &k->term_sums, &k->term_io, &k->transfer_rows, &k->transfer_log, &k->bnd_alpha,
+                            &k->bnd_beta, &k->seg_dlog})
+        b->counter = &k->allocations;
     if ((e = cudaStreamCreateWithFlags(&k->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void **>(&k->d_iteration), sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMemset(k->d_iteration, 0, sizeof(unsigned long long))) != cudaSuccess ||
         (e = cudaEventCreate(&k->ev0)) != cudaSuccess || (e = cudaEventCreate(&k->ev1)) != cudaSuccess ||
         (e = cudaMalloc(reinterpret_cast<void **>(&k->d_err), sizeof(int))) != cudaSuccess ||
         (e = cudaMalloc(reinterpret_cast<void **>(&k->d_flags), sizeof(int))) != cudaSuccess ||
@@ -753,52 +786,147 @@ static int flag_rows(phb_kernel *k) {
     return PHB_OK;
 }
 
-int phb_create(int M, const int8_t *data, int64_t N, int64_t L, int double_precision, int device,
-               phb_kernel **out) {
+}  // extern "C" (the helpers below are C++: a template and lambdas)
+
+// Host rows [n_rows, row_bytes] (contiguous) -> device rows of `dst_pitch` bytes, through two pinned
+// staging buffers filled by a few host threads while the previous slab is on the wire, so that neither a
+// second host copy of a 50 GB matrix nor a single-threaded pass over it is needed.  after_slab(first_row,
+// n_rows) is called once the slab's copy has been enqueued on k->stream.
+template <typename AfterSlab>
+static int staged_upload(phb_kernel *k, const int8_t *src, int64_t n_rows, int64_t row_bytes, int8_t *dst, int64_t dst_pitch,
+                         AfterSlab after_slab) {
+    constexpr size_t kSlabBytes = size_t(128) << 20;
+    const int64_t slab_rows = std::max<int64_t>(1, std::min<int64_t>(n_rows, int64_t(kSlabBytes / size_t(dst_pitch))));
+    const size_t slab_bytes = size_t(slab_rows) * size_t(dst_pitch);
+    int8_t *pinned[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    int rc = PHB_OK;
+    for (int i = 0; i < 2 && rc == PHB_OK; ++i) {
+        if (cudaMallocHost(reinterpret_cast<void **>(&pinned[i]), slab_bytes) != cudaSuccess ||
+            cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            rc = fail(PHB_E_NOMEM, "pinned staging buffer of %zu bytes", slab_bytes);
+        }
+    }
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int n_threads = int(std::min<unsigned>(8u, hw));
+    int64_t slab = 0;
+    for (int64_t r0 = 0; r0 < n_rows && rc == PHB_OK; r0 += slab_rows, ++slab) {
+        const int64_t nr = std::min(slab_rows, n_rows - r0);
+        const int b = int(slab & 1);
+        if (slab >= 2 && cudaEventSynchronize(done[b]) != cudaSuccess) {
+            rc = fail(PHB_E_CUDA, "staging: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        auto fill = [&](int t) {
+            const int64_t lo = nr * t / n_threads, hi = nr * (t + 1) / n_threads;
+            if (dst_pitch == row_bytes) {
+                memcpy(pinned[b] + lo * dst_pitch, src + (r0 + lo) * row_bytes, size_t(hi - lo) * size_t(row_bytes));
+            } else {
+                for (int64_t i = lo; i < hi; ++i) memcpy(pinned[b] + i * dst_pitch, src + (r0 + i) * row_bytes, size_t(row_bytes));
+            }
+        };
+        if (n_threads > 1 && size_t(nr) * size_t(row_bytes) >= (size_t(8) << 20)) {
+            std::vector<std::thread> pool;
+            for (int t = 1; t < n_threads; ++t) pool.emplace_back(fill, t);
+            fill(0);
+            for (std::thread &th : pool) th.join();
+        } else {
+            for (int t = 0; t < n_threads; ++t) fill(t);
+        }
+        cudaError_t e = cudaMemcpyAsync(dst + r0 * dst_pitch, pinned[b], size_t(nr) * size_t(dst_pitch), cudaMemcpyHostToDevice, k->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(done[b], k->stream);
+        if (e != cudaSuccess) {
+            rc = fail(PHB_E_CUDA, "cudaMemcpyAsync(data): %s", cudaGetErrorString(e));
+            break;
+        }
+        rc = after_slab(r0, nr);
+    }
+    if (cudaStreamSynchronize(k->stream) != cudaSuccess && rc == PHB_OK)
+        rc = fail(PHB_E_CUDA, "upload: %s", cudaGetErrorString(cudaGetLastError()));
+    for (int i = 0; i < 2; ++i) {
+        if (pinned[i]) cudaFreeHost(pinned[i]);
+        if (done[i]) cudaEventDestroy(done[i]);
+    }
+    return rc;
+}
+
+// The reference's constructor checks (gpu.py:106-113), evaluated on the DEVICE over the resident rows
+// [first_row, first_row + n_rows): clip to <= 1, pad the pitch with -1, note values < -1 and rows whose
+// columns [check_from, L) hold no observation.  check_state = {first bad linear index, row flags}.
+struct CheckState {
+    unsigned long long *d_first_bad = nullptr;  // [2]: smallest linear index of a value < -1; first row without an observation
+    uint8_t *d_row_observed = nullptr;          // [N]
+};
+static int check_alloc(phb_kernel *k, CheckState &cs) {
+    PHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&cs.d_first_bad), 2 * sizeof(unsigned long long)));
+    PHB_CUDA(cudaMemsetAsync(cs.d_first_bad, 0xff, 2 * sizeof(unsigned long long), k->stream));
+    PHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&cs.d_row_observed), size_t(k->N)));
+    return PHB_OK;
+}
+static void check_free(CheckState &cs) {
+    if (cs.d_first_bad) cudaFree(cs.d_first_bad);
+    if (cs.d_row_observed) cudaFree(cs.d_row_observed);
+    cs = CheckState{};
+}
+static int check_rows(phb_kernel *k, CheckState &cs, int64_t first_row, int64_t n_rows, int64_t check_from) {
+    const unsigned grid = unsigned(std::min<int64_t>(n_rows, int64_t(k->num_sms) * 8));
+    phb::fixup_rows_kernel<<<grid, 256, 0, k->stream>>>(k->d_data + first_row * k->pitch, n_rows, k->L, k->pitch, check_from, first_row,
+                                                         cs.d_first_bad, cs.d_row_observed);
+    PHB_CUDA(cudaGetLastError());
+    k->launches += 1;
+    return PHB_OK;
+}
+static int check_verdict(phb_kernel *k, CheckState &cs, const char *what) {
+    phb::first_zero_kernel<<<unsigned(std::min<int64_t>((k->N + 255) / 256, int64_t(k->num_sms) * 8)), 256, 0, k->stream>>>(
+        cs.d_row_observed, k->N, cs.d_first_bad + 1);
+    PHB_CUDA(cudaGetLastError());
+    k->launches += 1;
+    unsigned long long res[2];
+    PHB_CUDA(cudaMemcpyAsync(res, cs.d_first_bad, sizeof res, cudaMemcpyDeviceToHost, k->stream));
+    PHB_CUDA(cudaStreamSynchronize(k->stream));
+    if (res[0] != ~0ull)
+        return fail(PHB_E_DATA, "%s[%lld, %lld] < -1", what, (long long)(res[0] / (unsigned long long)k->L), (long long)(res[0] % (unsigned long long)k->L));
+    if (res[1] != ~0ull) return fail(PHB_E_DATA, "data contains observations with all missing values (row %lld)", (long long)res[1]);
+    return PHB_OK;
+}
+
+static int create_from_rows(int M, const int8_t *data, int64_t N, int64_t L, int64_t check_from, int double_precision, int device,
+                            phb_kernel **out) {
     if (!out) return fail(PHB_E_INVALID, "out is NULL");
     *out = nullptr;
     if (!(M == 4 || M == 8 || M == 16 || M == 32 || M == 64))
         return fail(PHB_E_INVALID, "M=%d is not supported (4, 8, 16, 32 or 64)", M);
     if (!data || N <= 0 || L <= 0) return fail(PHB_E_INVALID, "data must be a non-empty [N, L] int8 matrix");
-    // the reference's constructor checks (gpu.py:106-113)
-    for (int64_t i = 0; i < N; ++i) {
-        const int8_t *row = data + i * L;
-        bool any = false;
-        for (int64_t j = 0; j < L; ++j) {
-            if (row[j] < -1) return fail(PHB_E_DATA, "data[%lld, %lld] = %d < -1", (long long)i, (long long)j, row[j]);
-            any |= row[j] > -1;
-        }
-        if (!any) return fail(PHB_E_DATA, "data contains observations with all missing values (row %lld)", (long long)i);
-    }
+    if (check_from < 0 || check_from >= L) return fail(PHB_E_INVALID, "overlap %lld not in [0, row length %lld)", (long long)check_from, (long long)L);
     phb_kernel *k = nullptr;
     if (int rc = new_kernel(M, N, L, double_precision, device, &k)) return rc;
-    // clip to [-1, 1] on the way in (gpu.py:108-110); padding columns are never read as sites.
-    // Staged in slabs of rows so that a 50 GB matrix (BASELINE config 5) does not need a second
-    // 50 GB host copy.
-    {
-        const int64_t slab_rows = std::max<int64_t>(1, (int64_t(64) << 20) / k->pitch);
-        std::vector<int8_t> staged(size_t(std::min(slab_rows, N)) * size_t(k->pitch));
-        for (int64_t r0 = 0; r0 < N; r0 += slab_rows) {
-            const int64_t nr = std::min(slab_rows, N - r0);
-            std::fill(staged.begin(), staged.begin() + size_t(nr) * size_t(k->pitch), int8_t(-1));
-            for (int64_t i = 0; i < nr; ++i) {
-                const int8_t *src = data + (r0 + i) * L;
-                int8_t *dst = staged.data() + i * k->pitch;
-                for (int64_t j = 0; j < L; ++j) dst[j] = src[j] > 1 ? int8_t(1) : src[j];
-            }
-            cudaError_t e = cudaMemcpy(k->d_data + r0 * k->pitch, staged.data(), size_t(nr) * size_t(k->pitch), cudaMemcpyHostToDevice);
-            if (e != cudaSuccess) {
-                phb_destroy(k);
-                return fail(PHB_E_CUDA, "cudaMemcpy(data): %s", cudaGetErrorString(e));
-            }
-        }
-    }
-    if (int rc = flag_rows(k)) {
+    CheckState cs;
+    int rc = check_alloc(k, cs);
+    if (rc == PHB_OK)
+        rc = staged_upload(k, data, N, L, k->d_data, k->pitch, [&](int64_t r0, int64_t nr) { return check_rows(k, cs, r0, nr, check_from); });
+    if (rc == PHB_OK) rc = check_verdict(k, cs, "data");
+    check_free(cs);
+    if (rc == PHB_OK) rc = flag_rows(k);
+    if (rc != PHB_OK) {
+        const std::string msg = g_err;  // phb_destroy must not clobber the message
         phb_destroy(k);
+        g_err = msg;
         return rc;
     }
     *out = k;
     return PHB_OK;
+}
+
+extern "C" {
+
+int phb_create(int M, const int8_t *data, int64_t N, int64_t L, int double_precision, int device, phb_kernel **out) {
+    return create_from_rows(M, data, N, L, 0, double_precision, device, out);
+}
+
+int phb_create_chunks(int M, const int8_t *chunks, int64_t N, int64_t W, int64_t overlap, int double_precision, int device,
+                      phb_kernel **out) {
+    return create_from_rows(M, chunks, N, W, overlap, double_precision, device, out);
 }
 
 int phb_create_from_contig(int M, const int8_t *het, int64_t n_rows, int64_t length, int64_t overlap,
@@ -809,40 +937,43 @@ int phb_create_from_contig(int M, const int8_t *het, int64_t n_rows, int64_t len
     if (overlap < 0 || chunk_size <= 0) return fail(PHB_E_INVALID, "need overlap >= 0 and chunk_size > 0");
     const int64_t width = chunk_size + overlap;
     const int64_t n_chunks = (length + width - 1) / width;
-    // host-side checks of the reference on the windows (values >= -1; every window has an observation)
-    for (int64_t n = 0; n < n_rows; ++n) {
-        const int8_t *row = het + n * length;
-        for (int64_t j = 0; j < length; ++j)
-            if (row[j] < -1) return fail(PHB_E_DATA, "het[%lld, %lld] = %d < -1", (long long)n, (long long)j, row[j]);
-        for (int64_t kk = 0; kk < n_chunks; ++kk) {
-            bool any = false;
-            const int64_t lo = kk * chunk_size, hi = std::min(length, lo + width);
-            for (int64_t j = lo; j < hi && !any; ++j) any = row[j] > -1;
-            if (!any) return fail(PHB_E_DATA, "data contains observations with all missing values (row %lld, chunk %lld)", (long long)n, (long long)kk);
-        }
-    }
     phb_kernel *k = nullptr;
     if (int rc = new_kernel(M, n_rows * n_chunks, width, double_precision, device, &k)) return rc;
     int8_t *d_het = nullptr;
-    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&d_het), size_t(n_rows) * size_t(length));
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_het, het, size_t(n_rows) * size_t(length), cudaMemcpyHostToDevice, k->stream);
-    if (e == cudaSuccess) {
+    CheckState cs;
+    int rc = check_alloc(k, cs);
+    if (rc == PHB_OK && cudaMalloc(reinterpret_cast<void **>(&d_het), size_t(n_rows) * size_t(length)) != cudaSuccess) {
+        cudaGetLastError();
+        rc = fail(PHB_E_NOMEM, "While trying to allocate %lld bytes on GPU for the binned contig", (long long)(n_rows * length));
+    }
+    // the contig as ONE row of n_rows * length bytes cut into slabs (any slab boundary will do)
+    if (rc == PHB_OK) {
+        const int64_t total = n_rows * length, piece = int64_t(1) << 20;
+        const int64_t whole = total / piece;
+        if (whole > 0) rc = staged_upload(k, het, whole, piece, d_het, piece, [](int64_t, int64_t) { return PHB_OK; });
+        if (rc == PHB_OK && total > whole * piece)
+            rc = staged_upload(k, het + whole * piece, 1, total - whole * piece, d_het + whole * piece, total - whole * piece,
+                               [](int64_t, int64_t) { return PHB_OK; });
+    }
+    if (rc == PHB_OK) {
         const int64_t total = k->N * k->pitch;
         const int threads = 256;
         const int blocks = int(std::min<int64_t>((total + threads - 1) / threads, int64_t(k->num_sms) * 16));
         phb::chunk_het_kernel<<<blocks, threads, 0, k->stream>>>(d_het, n_rows, length, chunk_size, width, n_chunks, k->d_data, k->pitch);
-        e = cudaGetLastError();
         k->launches += 1;
+        if (cudaGetLastError() != cudaSuccess) rc = fail(PHB_E_CUDA, "chunking on the device failed");
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(k->stream);
+    // the reference's checks on the chunk matrix (values >= -1; the data part of every chunk holds an
+    // observation: mcmc.py:203 splits the warm-up columns off before gpu.py:111-113 looks)
+    if (rc == PHB_OK) rc = check_rows(k, cs, 0, k->N, overlap);
+    if (rc == PHB_OK) rc = check_verdict(k, cs, "chunks");
     if (d_het) cudaFree(d_het);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
+    check_free(cs);
+    if (rc == PHB_OK) rc = flag_rows(k);
+    if (rc != PHB_OK) {
+        const std::string msg = g_err;
         phb_destroy(k);
-        return fail(e == cudaErrorMemoryAllocation ? PHB_E_NOMEM : PHB_E_CUDA, "chunking on the device: %s", cudaGetErrorString(e));
-    }
-    if (int rc = flag_rows(k)) {
-        phb_destroy(k);
+        g_err = msg;
         return rc;
     }
     *out = k;
@@ -884,6 +1015,7 @@ void phb_destroy(phb_kernel *k) {
     if (k->d_data) cudaFree(k->d_data);
     if (k->d_err) cudaFree(k->d_err);
     if (k->d_flags) cudaFree(k->d_flags);
+    if (k->d_iteration) cudaFree(k->d_iteration);
     if (k->ev0) cudaEventDestroy(k->ev0);
     if (k->ev1) cudaEventDestroy(k->ev1);
     if (k->stream) cudaStreamDestroy(k->stream);
@@ -992,6 +1124,108 @@ int phb_loglik_warmup_device(phb_kernel *k, const void *params7, const int64_t *
     if (rc != PHB_OK || overlap == 0) return rc;
     // ... minus LL over the warm-up bins alone (same stream: ordered after the first launch)
     return device_eval(k, params7, 7 * M, 0, pi, 7 * M, 0, inds, B, S, want_grad, ll, dlog, st, overlap, 1);
+}
+
+int phb_reserve(phb_kernel *k, int64_t B, int64_t S_max, int64_t overlap, int want_grad) {
+    if (int rc = check_handle(k)) return rc;
+    if (B <= 0 || S_max <= 0) return fail(PHB_E_INVALID, "need B > 0 and S_max > 0");
+    if (overlap < 0 || overlap >= k->L) return fail(PHB_E_INVALID, "overlap %lld not in [0, row length %lld)", (long long)overlap, (long long)k->L);
+    PHB_CUDA(cudaSetDevice(k->device));
+    // Dry run of the dispatcher for every minibatch size a caller may use: the path (and with it the scratch)
+    // depends on S, not monotonically.  Small sizes are walked one by one, then powers of two up to S_max.
+    std::vector<int64_t> sizes;
+    for (int64_t S = 1; S <= std::min<int64_t>(S_max, 64); ++S) sizes.push_back(S);
+    for (int64_t S = 128; S < S_max; S *= 2) sizes.push_back(S);
+    sizes.push_back(S_max);
+    std::vector<int32_t> widths(size_t(k->M), 1);
+    void *dummy = k->d_err;  // any non-NULL device address: nothing is dereferenced in a dry run
+    int rc = PHB_OK;
+    k->dry = true;
+    for (int64_t S : sizes) {
+        // the one-call term (particles -> parameters -> fused warm-up evaluation -> sums -> VJP) ...
+        rc = phb_hmm_term_device(k, static_cast<const double *>(dummy), B, widths.data(), k->M, 1.0, static_cast<const int64_t *>(dummy), S,
+                                 overlap, 1.0, static_cast<double *>(dummy), want_grad ? static_cast<double *>(dummy) : nullptr, k->stream);
+        // ... and the plain kernel call the reference's interface makes (gpu.py:182-325)
+        if (rc == PHB_OK)
+            rc = phb_loglik_device(k, dummy, 6 * k->M, 0, dummy, k->M, 0, static_cast<const int64_t *>(dummy), B, S, want_grad,
+                                   static_cast<double *>(dummy), dummy, k->stream);
+        if (rc != PHB_OK) break;
+    }
+    // host-entry staging of the term
+    if (rc == PHB_OK) {
+        const int64_t P = 2 + int64_t(k->M) + 1;
+        rc = k->term_io.reserve((size_t(B) * P * 2 + size_t(B)) * sizeof(double) + size_t(S_max) * sizeof(int64_t));
+    }
+    k->dry = false;
+    return rc;
+}
+
+int64_t phb_allocation_count(const phb_kernel *k) { return k ? k->allocations : 0; }
+
+void phb_minibatch_indices(uint64_t seed, uint64_t iteration, int64_t N, int64_t S, int64_t *inds) {
+    for (int64_t s = 0; s < S; ++s) inds[s] = phb::minibatch_index(seed, iteration, uint64_t(s), N);
+}
+
+int phb_set_iteration(phb_kernel *k, uint64_t iteration, void *stream) {
+    if (int rc = check_handle(k)) return rc;
+    PHB_CUDA(cudaSetDevice(k->device));
+    // (a kernel-argument store, not a memcpy from pageable host memory: legal inside a stream capture)
+    phb::set_counter_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(k->d_iteration, (unsigned long long)iteration);
+    PHB_CUDA(cudaGetLastError());
+    k->launches += 1;
+    return PHB_OK;
+}
+
+int phb_sample_minibatch_device(phb_kernel *k, uint64_t seed, int64_t S, int64_t *inds, void *stream) {
+    if (int rc = check_handle(k)) return rc;
+    if (S < 0 || (S > 0 && !inds)) return fail(PHB_E_INVALID, "bad minibatch buffer");
+    if (S == 0) return PHB_OK;
+    PHB_CUDA(cudaSetDevice(k->device));
+    phb::sample_minibatch_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(seed, k->d_iteration, k->N, S, inds);
+    PHB_CUDA(cudaGetLastError());
+    k->launches += 1;
+    return PHB_OK;
+}
+
+int phb_measure_fp32_peak(int device, double *independent_tflops, double *accumulate_tflops) {
+    if (!independent_tflops) return fail(PHB_E_INVALID, "NULL pointer");
+    PHB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PHB_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int threads = 256, ctas = prop.multiProcessorCount * 8;
+    float *out = nullptr, *in = nullptr;
+    PHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&out), sizeof(float) * threads * ctas));
+    PHB_CUDA(cudaMalloc(reinterpret_cast<void **>(&in), sizeof(float) * 64));
+    float h[64];
+    for (int i = 0; i < 64; ++i) h[i] = 0.5f + 1e-3f * i;
+    PHB_CUDA(cudaMemcpy(in, h, sizeof h, cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1;
+    PHB_CUDA(cudaEventCreate(&e0));
+    PHB_CUDA(cudaEventCreate(&e1));
+    const double flop = 2.0 * double(threads) * ctas * phb::kPeakIters * phb::kPeakChains;
+    double best[2] = {0.0, 0.0};
+    for (int which = 0; which < 2; ++which) {
+        for (int rep = 0; rep < 13; ++rep) {  // 3 warm-ups, best of 10
+            cudaEventRecord(e0, nullptr);
+            if (which == 0)
+                phb::ffma_peak_kernel<<<ctas, threads>>>(out, 0.999f, 1e-3f);
+            else
+                phb::ffma_accumulate_kernel<<<ctas, threads>>>(out, in);
+            cudaEventRecord(e1, nullptr);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep >= 3 && ms > 0.f) best[which] = std::max(best[which], flop / (double(ms) * 1e-3) / 1e12);
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    cudaFree(in);
+    PHB_CUDA(cudaGetLastError());
+    *independent_tflops = best[0];
+    if (accumulate_tflops) *accumulate_tflops = best[1];
+    return PHB_OK;
 }
 
 void *phb_stream(const phb_kernel *k) { return k ? static_cast<void *>(k->stream) : nullptr; }
@@ -1186,6 +1420,7 @@ int phb_params_from_particles(phb_kernel *k, const double *x, int64_t B, const i
     if (B == 0) return PHB_OK;
     PHB_CUDA(cudaSetDevice(k->device));
     a.params7 = params7;
+    if (k->dry) return PHB_OK;
     const int threads = 64;
     phb::psmc_params_forward_kernel<<<unsigned((B + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(a);
     PHB_CUDA(cudaGetLastError());
@@ -1202,6 +1437,7 @@ int phb_params_vjp(phb_kernel *k, const double *x, int64_t B, const int32_t *epo
     PHB_CUDA(cudaSetDevice(k->device));
     a.cotangent = cotangent;
     a.grad_x = grad_x;
+    if (k->dry) return PHB_OK;
     const int threads = 64;
     const int64_t n = B * a.P;
     phb::psmc_params_vjp_kernel<<<unsigned((n + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(a);
@@ -1231,6 +1467,7 @@ int phb_hmm_term_sums_device(phb_kernel *k, const double *x, int64_t B, const in
                                            want_grad ? k->term_dlog.ptr : nullptr, stream)) != PHB_OK)
             return rc;
     }
+    if (k->dry) return PHB_OK;
     const int threads = 128;
     if (k->dbl)
         phb::sum_over_chunks_kernel<double><<<unsigned(B), threads, 0, st>>>(static_cast<const double *>(k->term_ll.ptr),
@@ -1252,6 +1489,7 @@ int phb_hmm_term_finish_device(phb_kernel *k, const double *x, int64_t B, const 
     PHB_CUDA(cudaSetDevice(k->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t stride = 1 + 7 * k->M;
+    if (k->dry) return PHB_OK;
     const int threads = 64;
     phb::scaled_first_column_kernel<<<unsigned((B + threads - 1) / threads), threads, 0, st>>>(sums, B, stride, weight, value);
     PHB_CUDA(cudaGetLastError());

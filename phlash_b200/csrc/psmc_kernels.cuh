@@ -1593,7 +1593,7 @@ __global__ void chunk_het_kernel(const int8_t *__restrict__ het, int64_t n_rows,
         int8_t v = -1;
         if (j < width && src < length) {
             v = het[n * length + src];
-            v = v > 1 ? int8_t(1) : (v < -1 ? int8_t(-1) : v);
+            v = v > 1 ? int8_t(1) : v;  // (values < -1 are left for fixup_rows_kernel to report)
         }
         out[i] = v;
     }

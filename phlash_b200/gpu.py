@@ -46,23 +46,26 @@ def _ptr(a: np.ndarray) -> ctypes.c_void_p:
 class _PSMCKernelBase:
     "PSMC kernel running on a single GPU (reference: gpu.py:101-325)"
 
-    def __init__(self, M: int, data: np.ndarray, double_precision: bool = False, device: int = 0):
+    def __init__(self, M: int, data: np.ndarray, double_precision: bool = False, device: int = 0, overlap: int = 0):
+        """``overlap`` > 0: ``data`` are FULL chunks [N, overlap + L] (for the fused warm-up entries); the
+        "every row has an observation" check then covers the data part [overlap:], which is what the
+        reference's constructor sees after mcmc.py:203 has split the warm-up columns off."""
         data = np.asarray(data)
         assert data.ndim == 2
         assert data.dtype == np.int8
-        assert data.min() >= -1
-        # values > 1 are clipped to 1 by phb_create while it stages the upload (gpu.py:108-110);
-        # no clipped host copy is made here (the matrix can be tens of GB)
+        # The reference's checks (min >= -1, clip to <= 1, every row observed; gpu.py:106-113) run on the
+        # DEVICE inside phb_create_chunks, after the copy: the host never walks a matrix that can be tens
+        # of GB (BASELINE config 5), and no clipped host copy is made.
         data = np.ascontiguousarray(data)
-        assert np.all(data.max(axis=1) > -1), "data contains observations with all missing values"
         self.double_precision = bool(double_precision)
         self._N, self._L = data.shape
         self._M = int(M)
         self._lib = _native.lib()
         handle = ctypes.c_void_p()
         _check(
-            self._lib.phb_create(
-                self._M, _ptr(data), self._N, self._L, int(self.double_precision), int(device), ctypes.byref(handle)
+            self._lib.phb_create_chunks(
+                self._M, _ptr(data), self._N, self._L, int(overlap), int(self.double_precision), int(device),
+                ctypes.byref(handle)
             )
         )
         self._handle = handle
@@ -76,8 +79,10 @@ class _PSMCKernelBase:
         use evaluate_warmup(..., overlap=overlap)."""
         het = np.asarray(het_matrix)
         assert het.ndim == 2
-        assert het.min() >= -1
-        het = np.ascontiguousarray(het.clip(-1, 1).astype(np.int8))
+        if het.dtype != np.int8:  # counts of any integer type: bring them to int8 without wrapping
+            assert het.min() >= -1
+            het = het.clip(-1, 1).astype(np.int8)
+        het = np.ascontiguousarray(het)  # (int8 input is validated and clipped on the device)
         self = cls.__new__(cls)
         self.double_precision = bool(double_precision)
         self._M = int(M)
@@ -420,6 +425,50 @@ class _PSMCKernelBase:
 
     def sync(self) -> None:
         _check(self._lib.phb_sync(self._handle))
+
+    # ---- allocation-free, capturable steps; minibatch sampling on the device (mcmc.py:277-278)
+    def reserve(self, B: int, S_max: int, overlap: int = 0, grad: bool = True) -> None:
+        """Size every scratch buffer a call with B particles and up to S_max chunks can need, so that later
+        calls neither allocate nor free (phb_reserve): a whole step can then be recorded into a CUDA graph."""
+        _check(self._lib.phb_reserve(self._handle, int(B), int(S_max), int(overlap), int(grad)))
+
+    @property
+    def allocation_count(self) -> int:
+        return int(self._lib.phb_allocation_count(self._handle))
+
+    def set_iteration(self, iteration: int, stream=None) -> None:
+        import torch
+
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        _check(self._lib.phb_set_iteration(self._handle, int(iteration), ctypes.c_void_p(stream)))
+
+    def sample_minibatch(self, seed: int, S: int, out=None, stream=None):
+        """inds ~ choice(N, (S,)) with replacement, drawn ON THE DEVICE for the object's current iteration
+        counter (which advances): torch int64 CUDA tensor [S]."""
+        import torch
+
+        if out is None:
+            out = torch.empty((int(S),), dtype=torch.int64, device=torch.device("cuda", self.device))
+        assert out.is_cuda and out.dtype == torch.int64 and out.is_contiguous() and out.shape == (int(S),)
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        _check(self._lib.phb_sample_minibatch_device(self._handle, int(seed), int(S), out.data_ptr(), ctypes.c_void_p(stream)))
+        return out
+
+
+def minibatch_indices(seed: int, iteration: int, n_chunks: int, S: int) -> np.ndarray:
+    """The generator of ``sample_minibatch`` on the host (pure function of (seed, iteration))."""
+    out = np.empty(int(S), dtype=np.int64)
+    _native.lib().phb_minibatch_indices(int(seed), int(iteration), int(n_chunks), int(S), _ptr(out))
+    return out
+
+
+def measure_fp32_peak(device: int = 0):
+    """(independent-FFMA TFLOP/s, accumulate-pattern TFLOP/s) measured now on ``device``."""
+    a, b = ctypes.c_double(), ctypes.c_double()
+    _check(_native.lib().phb_measure_fp32_peak(int(device), ctypes.byref(a), ctypes.byref(b)))
+    return a.value, b.value
 
 
 def _normalise_call(pp: PSMCParams, index, M: int):

@@ -47,7 +47,7 @@ def test_no_torch_or_python_types_in_the_abi():
 
 
 def test_abi_version(lib):
-    assert lib.phb_abi_version() == 2
+    assert lib.phb_abi_version() == 3
 
 
 def test_create_rejects_bad_arguments_before_touching_cuda(lib):
@@ -57,15 +57,29 @@ def test_create_rejects_bad_arguments_before_touching_cuda(lib):
     assert rc == _native.PHB_E_INVALID and "M=7" in _native.last_error()
     rc = lib.phb_create(16, None, 2, 32, 0, 0, ctypes.byref(h))
     assert rc == _native.PHB_E_INVALID
-    bad = data.copy()
-    bad[1, 3] = -2
-    rc = lib.phb_create(16, bad.ctypes.data, 2, 32, 0, 0, ctypes.byref(h))
-    assert rc == _native.PHB_E_DATA and "< -1" in _native.last_error()
-    allmiss = data.copy()
-    allmiss[1] = -1
-    rc = lib.phb_create(16, allmiss.ctypes.data, 2, 32, 0, 0, ctypes.byref(h))
-    assert rc == _native.PHB_E_DATA and "all missing" in _native.last_error()
+    rc = lib.phb_create_chunks(16, data.ctypes.data, 2, 32, 32, 0, 0, ctypes.byref(h))
+    assert rc == _native.PHB_E_INVALID and "overlap" in _native.last_error()
     assert not h.value
+    # (the checks of the matrix itself - values >= -1, every row observed - run on the device:
+    # tests/test_gpu_step_plumbing.py)
+
+
+def test_minibatch_generator_on_the_host(lib):
+    """phb_minibatch_indices is a pure function of (seed, iteration): with replacement, in range, and
+    different across iterations / seeds (reference: jax.random.choice(subkey, N, (S,)), mcmc.py:277)."""
+    from phlash_b200.gpu import minibatch_indices
+
+    a = minibatch_indices(7, 3, 595, 5)
+    assert a.shape == (5,) and a.dtype == np.int64 and (a >= 0).all() and (a < 595).all()
+    np.testing.assert_array_equal(a, minibatch_indices(7, 3, 595, 5))
+    assert not np.array_equal(a, minibatch_indices(7, 4, 595, 5))
+    assert not np.array_equal(a, minibatch_indices(8, 3, 595, 5))
+    # a prefix property: the first draws do not depend on S
+    np.testing.assert_array_equal(minibatch_indices(7, 3, 595, 64)[:5], a)
+    # uniform over the rows, with replacement
+    big = np.concatenate([minibatch_indices(1, it, 10, 1000) for it in range(20)])
+    counts = np.bincount(big, minlength=10)
+    assert counts.min() > 1800 and counts.max() < 2200
 
 
 def test_null_handle_is_an_error_not_a_crash(lib):

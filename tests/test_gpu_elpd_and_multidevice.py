@@ -78,7 +78,7 @@ def test_chunking_on_the_device_is_bit_exact(golden, tag):
     ov, cs = (int(v) for v in golden[f"chunk_{tag}_geom"])
     het = golden[f"chunk_{tag}_in"]
     want = golden[f"chunk_{tag}_out"]
-    if not np.all(want.max(axis=1) > -1):
+    if not np.all(want[:, ov:].max(axis=1) > -1):  # the reference checks the data part (mcmc.py:203, gpu.py:111-113)
         with pytest.raises(AssertionError):
             _PSMCKernelBase.from_contig(16, het, ov, cs)
         return
