@@ -256,6 +256,12 @@ int phb_hmm_term_finish_device(phb_kernel *k, const double *x, int64_t B, const 
                                int n_epochs, double theta, const double *sums, double weight, double *value,
                                double *grad_x, void *stream);
 
+/* Per-particle sums over the chunk axis of an evaluation's outputs: ll [B, S] and dlog [B, S, 7, M] (or NULL)
+ * -> sums [B, 1 + 7 M] doubles, the buffer one process per GPU all-reduces per step (the summing stage of
+ * phb_hmm_term_sums_device on its own; the reference sums in XLA, model.py:57).  Device pointers. */
+int phb_sum_over_chunks_device(phb_kernel *k, const double *ll, const void *dlog, int64_t B, int64_t S, double *sums,
+                               void *stream);
+
 /* Wait for the kernel object's own stream AND for the stream of the most recent
  * phb_loglik_device call, then report deferred device-side errors. */
 int phb_sync(phb_kernel *k);

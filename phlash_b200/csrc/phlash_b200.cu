@@ -1480,6 +1480,23 @@ int phb_hmm_term_sums_device(phb_kernel *k, const double *x, int64_t B, const in
     return PHB_OK;
 }
 
+int phb_sum_over_chunks_device(phb_kernel *k, const double *ll, const void *dlog, int64_t B, int64_t S, double *sums, void *stream) {
+    if (int rc = check_handle(k)) return rc;
+    if (B < 0 || S < 0) return fail(PHB_E_INVALID, "negative batch shape");
+    if (!sums || (S > 0 && !ll)) return fail(PHB_E_INVALID, "NULL pointer");
+    if (B == 0) return PHB_OK;
+    PHB_CUDA(cudaSetDevice(k->device));
+    const int C = 7 * k->M;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (k->dbl)
+        phb::sum_over_chunks_kernel<double><<<unsigned(B), 128, 0, st>>>(ll, static_cast<const double *>(dlog), S, C, sums);
+    else
+        phb::sum_over_chunks_kernel<float><<<unsigned(B), 128, 0, st>>>(ll, static_cast<const float *>(dlog), S, C, sums);
+    PHB_CUDA(cudaGetLastError());
+    k->launches += 1;
+    return PHB_OK;
+}
+
 int phb_hmm_term_finish_device(phb_kernel *k, const double *x, int64_t B, const int32_t *epoch_widths, int n_epochs,
                                double theta, const double *sums, double weight, double *value, double *grad_x, void *stream) {
     phb::ParamsArgs pa{};

@@ -423,6 +423,27 @@ class _PSMCKernelBase:
         )
         return ll, (dlog if grad else None)
 
+    def sum_over_chunks(self, ll, dlog, out=None, stream=None):
+        """ll [B, S] float64, dlog [B, S, 7, M] (torch CUDA) -> per-particle sums [B, 1 + 7 M] float64: what one
+        process per GPU contributes to the all-reduce of a step (phb_sum_over_chunks_device)."""
+        import torch
+
+        B, S = int(ll.shape[0]), int(ll.shape[1])
+        assert ll.is_cuda and ll.dtype == torch.float64 and ll.is_contiguous()
+        assert dlog is None or (dlog.is_contiguous() and dlog.shape == (B, S, 7, self._M))
+        if out is None:
+            out = torch.empty((B, 1 + 7 * self._M), dtype=torch.float64, device=ll.device)
+        assert out.shape == (B, 1 + 7 * self._M) and out.dtype == torch.float64 and out.is_contiguous()
+        if stream is None:
+            stream = torch.cuda.current_stream(ll.device).cuda_stream
+        _check(
+            self._lib.phb_sum_over_chunks_device(
+                self._handle, ll.data_ptr(), dlog.data_ptr() if dlog is not None else None, B, S, out.data_ptr(),
+                ctypes.c_void_p(stream),
+            )
+        )
+        return out
+
     def sync(self) -> None:
         _check(self._lib.phb_sync(self._handle))
 

@@ -133,3 +133,57 @@ def test_fp32_peak_measurement():
 
     ind, acc = measure_fp32_peak(0)
     assert 40.0 < ind < 80.0 and 25.0 < acc <= ind * 1.02, (ind, acc)
+
+
+def test_fit_loop_follows_the_reference_schedule():
+    """phlash_b200.mcmc.fit_loop: S rule, device-side sampling (reproducible from the seed), N / S weight, ELPD
+    every 10th iteration with the early stop (mcmc.py:116-140, 275-304); one CUDA-graph replay per iteration
+    gives exactly the particles of the eager loop."""
+    import os
+    import sys
+
+    import torch
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import svgd_torch
+
+    from phlash_b200 import mcmc, model
+    from phlash_b200.gpu import _PSMCKernelBase, minibatch_indices
+
+    chunks = _chunks(310_000, seed=7)[:6]  # 6 full chunks
+    _, xs, pattern = orc.synth_particles(16, 48, seed=2)
+    test_het = orc.synth_het_matrix(1, 20_000, seed=9)
+    assert model.default_minibatch_size(len(chunks), 1000) == 1 and model.default_minibatch_size(6000, 1000) == 5
+    out = []
+    for use_graph in (True, False):
+        x0 = torch.tensor(xs, dtype=torch.float64, device="cuda:0")
+        opt = svgd_torch.SvgdAmsgrad(x0)
+        res = mcmc.fit_loop(chunks, x0, pattern, 1e-2, opt, niter=24, overlap=500, minibatch_size=2, test_het=test_het,
+                            log_prior_grad=svgd_torch.log_prior_grad, seed=11, use_graph=use_graph)
+        assert res.iterations == 24 and res.minibatch_size == 2 and res.n_chunks == 6 and not res.stopped_early
+        assert len(res.elpd_trace) == 3  # iterations 0, 10, 20 (mcmc.py:287)
+        assert res.graph_replays == (24 - 3 if use_graph else 0)
+        out.append(res.particles.cpu().numpy())
+    np.testing.assert_array_equal(out[0], out[1])
+    assert np.abs(out[0] - xs).max() > 1e-3  # the particles moved
+    # the first iteration, by hand: the sampler's indices, the weighted HMM term, the prior, one update
+    x = torch.tensor(xs, dtype=torch.float64, device="cuda:0")
+    kern = _PSMCKernelBase(16, chunks, overlap=500)
+    inds = torch.tensor(minibatch_indices(11, 0, 6, 2), device="cuda:0")
+    _, g = kern.hmm_term(x, pattern, 1e-2, inds, 500, weight=6 / 2)
+    opt = svgd_torch.SvgdAmsgrad(x)
+    x1 = x.clone()
+    opt(x1, g + svgd_torch.log_prior_grad(x))
+    x0 = torch.tensor(xs, dtype=torch.float64, device="cuda:0")
+    res = mcmc.fit_loop(chunks, x0, pattern, 1e-2, svgd_torch.SvgdAmsgrad(x0), niter=1, overlap=500, minibatch_size=2,
+                        log_prior_grad=svgd_torch.log_prior_grad, seed=11, use_graph=False)
+    np.testing.assert_array_equal(res.particles.cpu().numpy(), x1.cpu().numpy())
+    # early stop: an update that makes the particles worse every time trips the ELPD cut-off
+    x0 = torch.tensor(xs, dtype=torch.float64, device="cuda:0")
+
+    def worsen(x, score):
+        x[:, 2:-1] += 0.5  # population sizes drift away
+
+    res = mcmc.fit_loop(chunks, x0, pattern, 1e-2, worsen, niter=200, overlap=500, minibatch_size=1, test_het=test_het,
+                        elpd_cutoff=15, seed=1, use_graph=False)
+    assert res.stopped_early and res.iterations < 60
