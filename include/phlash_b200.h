@@ -256,6 +256,28 @@ int phb_hmm_term_finish_device(phb_kernel *k, const double *x, int64_t B, const 
                                int n_epochs, double theta, const double *sums, double weight, double *value,
                                double *grad_x, void *stream);
 
+/* TIME-AXIS SHARDING of the whole HMM term over `world` processes (one per GPU) for SMALL minibatches: with
+ * S < world chunks the chunk axis cannot occupy every GPU (the reference splits its S <= 5 indices over the
+ * devices, gpu.py:398-400, and leaves the rest idle).  The parallel-in-time gradient cuts every chunk into
+ * segments that are independent once the boundary vectors are known, so the SEGMENTS are sharded instead:
+ *   _plan   n_segments / slot_bytes for this call shape; n_segments == 0 means "does not apply" (double
+ *           precision, M > 16, or too many pairs for the operators to pay) - shard the chunks instead;
+ *   _begin  particles -> parameters, then this process's slice of the segment transfer operators, written
+ *           into ITS slot (rank * slot_bytes) of `gather` (world * slot_bytes bytes of device memory);
+ *   -- the caller all-gathers `gather` in place (one NCCL call) --
+ *   _end    chains all operators (float64) to the boundary vectors, runs the gradient passes over this
+ *           process's segments and leaves its PARTIAL per-particle sums [B, 1 + 7 M] in `sums`; process 0 adds
+ *           the log-likelihood, the pairs on marked rows (precision escalation) and subtracts the warm-up term;
+ *   -- the caller all-reduces `sums` and calls phb_hmm_term_finish_device, as in the chunk-sharded form.
+ * The result equals phb_hmm_term_sums_device on one process up to floating-point summation order. */
+int phb_hmm_term_sharded_plan(phb_kernel *k, int64_t B, int64_t S, int64_t overlap, int world, int64_t *n_segments,
+                              int64_t *slot_bytes);
+int phb_hmm_term_sharded_begin(phb_kernel *k, const double *x, int64_t B, const int32_t *epoch_widths, int n_epochs,
+                               double theta, const int64_t *inds, int64_t S, int64_t overlap, int rank, int world,
+                               void *gather, void *stream);
+int phb_hmm_term_sharded_end(phb_kernel *k, const int64_t *inds, int64_t B, int64_t S, int64_t overlap, int rank, int world,
+                             const void *gather, double *sums, void *stream);
+
 /* Per-particle sums over the chunk axis of an evaluation's outputs: ll [B, S] and dlog [B, S, 7, M] (or NULL)
  * -> sums [B, 1 + 7 M] doubles, the buffer one process per GPU all-reduces per step (the summing stage of
  * phb_hmm_term_sums_device on its own; the reference sums in XLA, model.py:57).  Device pointers. */

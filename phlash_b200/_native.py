@@ -51,6 +51,9 @@ SIGNATURES = {
     "phb_hmm_term_host": (_i, [_vp, _vp, _i64, _vp, _i, ctypes.c_double, _vp, _i64, _i64, ctypes.c_double, _vp, _vp]),
     "phb_hmm_term_sums_device": (_i, [_vp, _vp, _i64, _vp, _i, ctypes.c_double, _vp, _i64, _i64, _i, _vp, _vp]),
     "phb_hmm_term_finish_device": (_i, [_vp, _vp, _i64, _vp, _i, ctypes.c_double, _vp, ctypes.c_double, _vp, _vp, _vp]),
+    "phb_hmm_term_sharded_plan": (_i, [_vp, _i64, _i64, _i64, _i, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
+    "phb_hmm_term_sharded_begin": (_i, [_vp, _vp, _i64, _vp, _i, ctypes.c_double, _vp, _i64, _i64, _i, _i, _vp, _vp]),
+    "phb_hmm_term_sharded_end": (_i, [_vp, _vp, _i64, _i64, _i64, _i, _i, _vp, _vp, _vp]),
     "phb_sum_over_chunks_device": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "phb_stream": (_vp, [_vp]),
     "phb_sync": (_i, [_vp]),

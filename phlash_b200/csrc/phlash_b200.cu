@@ -379,6 +379,8 @@ int try_parallel_in_time_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaS
     ta.seg_len = seg_len;
     ta.rows = static_cast<float *>(k->transfer_rows.ptr);
     ta.row_log2 = static_cast<double *>(k->transfer_log.ptr);
+    ta.segs_per_slot = n_seg;  // one process: a single slot with all segments
+    ta.n_seg_local = n_seg;
     void *bnd_a = k->bnd_alpha.ptr, *bnd_b = k->bnd_beta.ptr;
     {
         void *kargs[] = {&ta};
@@ -555,6 +557,8 @@ int try_parallel_in_time_forward(phb_kernel *k, const phb::KernelArgs &a, cudaSt
             ta.seg_len = seg_len;
             ta.rows = static_cast<float *>(k->transfer_rows.ptr);
             ta.row_log2 = static_cast<double *>(k->transfer_log.ptr);
+            ta.segs_per_slot = n_seg;
+            ta.n_seg_local = n_seg;
             if (k->occupancy.find(tv->rows_func) == k->occupancy.end()) {
                 PHB_CUDA(cudaFuncSetAttribute(tv->rows_func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tv->smem)));
                 k->occupancy.emplace(tv->rows_func, 1);
@@ -571,6 +575,56 @@ int try_parallel_in_time_forward(phb_kernel *k, const phb::KernelArgs &a, cudaSt
     }
 
     return kNotTaken;
+}
+
+// ---- time-axis sharding of a SMALL minibatch over several processes (one per GPU) ------------------------
+// With S < world chunks there is nothing to shard on the chunk axis (the reference splits S <= 5 indices over
+// its devices and leaves the others idle, gpu.py:398-400).  The segments of the parallel-in-time gradient ARE
+// independent once the boundary vectors exist: every process computes the transfer operators of its own
+// slice of the segments, one all-gather makes all operators visible everywhere, every process chains them
+// (cheap, float64) and then runs the gradient passes over its own slice only; the partial per-particle sums
+// join the all-reduce that the chunk-sharded path uses as well.
+struct ShardPlan {
+    int64_t n_seg = 0, seg_len = 0, seg_ctas = 0, per_rank = 0;
+    size_t rows_bytes = 0, slot_bytes = 0;  // per process
+};
+bool shard_plan(phb_kernel *k, int64_t B, int64_t S, int64_t L, int world, ShardPlan &p) {
+    p = ShardPlan{};
+    const TransferVariant *tv = transfer_variant(k->M);
+    const Variant *gv = segment_variant(k->M);
+    if (!tv || !gv || k->dbl || world < 2) return false;
+    const int64_t n_pairs = B * S;
+    const int M = k->M;
+    const int64_t capacity = int64_t(k->num_sms) * 384 * world;  // resident threads of the row kernel, all GPUs
+    if (n_pairs * M * 10 > capacity * 3) return false;           // the single-GPU rule, scaled
+    int occ = 0;
+    auto it = k->occupancy.find(gv->func);
+    if (it == k->occupancy.end()) {
+        if (cudaFuncSetAttribute(gv->func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gv->smem)) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gv->func, gv->NT, gv->smem) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        k->occupancy.emplace(gv->func, occ);
+    } else {
+        occ = it->second;
+    }
+    if (occ < 1) return false;
+    const int pairs_per_group = gv->NT / gv->T;
+    p.seg_ctas = (n_pairs + pairs_per_group - 1) / pairs_per_group;
+    // as many segments per process as keep its gradient groups resident at once; segments >= 512 sites
+    int64_t per_rank = std::min<int64_t>(int64_t(occ) * k->num_sms / p.seg_ctas, (L / 512) / world);
+    if (k->env_pit_segments > 0) per_rank = std::max<int64_t>(1, k->env_pit_segments / world);
+    if (per_rank < 1) return false;
+    int64_t n_seg = per_rank * world;
+    p.seg_len = ((L + n_seg - 1) / n_seg + 15) / 16 * 16;
+    n_seg = (L + p.seg_len - 1) / p.seg_len;
+    p.per_rank = (n_seg + world - 1) / world;  // the last process may hold fewer
+    p.n_seg = n_seg;
+    if (n_seg < 2 * world && n_seg < 3) return false;
+    p.rows_bytes = size_t(p.per_rank) * size_t(n_pairs) * M * M * sizeof(float);
+    p.slot_bytes = p.rows_bytes + size_t(p.per_rank) * size_t(n_pairs) * M * sizeof(double);
+    return true;
 }
 
 // (4) The throughput kernel: persistent grid, checkpoints + recompute for the gradient.  `fixed` pins the
@@ -1475,6 +1529,208 @@ int phb_hmm_term_sums_device(phb_kernel *k, const double *x, int64_t B, const in
     else
         phb::sum_over_chunks_kernel<float><<<unsigned(B), threads, 0, st>>>(static_cast<const double *>(k->term_ll.ptr),
                                                                            want_grad ? static_cast<const float *>(k->term_dlog.ptr) : nullptr, S, C, sums);
+    PHB_CUDA(cudaGetLastError());
+    k->launches += 1;
+    return PHB_OK;
+}
+
+int phb_hmm_term_sharded_plan(phb_kernel *k, int64_t B, int64_t S, int64_t overlap, int world, int64_t *n_segments, int64_t *slot_bytes) {
+    if (int rc = check_handle(k)) return rc;
+    if (!n_segments || !slot_bytes) return fail(PHB_E_INVALID, "NULL pointer");
+    (void)overlap;
+    *n_segments = 0;
+    *slot_bytes = 0;
+    if (B <= 0 || S <= 0 || world < 1) return fail(PHB_E_INVALID, "need B, S > 0 and world >= 1");
+    PHB_CUDA(cudaSetDevice(k->device));
+    ShardPlan p;
+    if (shard_plan(k, B, S, k->L, world, p)) {
+        *n_segments = p.n_seg;
+        *slot_bytes = int64_t(p.slot_bytes);
+    }
+    return PHB_OK;
+}
+
+int phb_hmm_term_sharded_begin(phb_kernel *k, const double *x, int64_t B, const int32_t *epoch_widths, int n_epochs, double theta,
+                               const int64_t *inds, int64_t S, int64_t overlap, int rank, int world, void *gather, void *stream) {
+    phb::ParamsArgs pa{};
+    if (int rc = fill_params_args(k, x, B, epoch_widths, n_epochs, theta, pa)) return rc;
+    if (!inds || !gather || S <= 0 || rank < 0 || rank >= world) return fail(PHB_E_INVALID, "bad argument");
+    if (overlap < 0 || overlap >= k->L) return fail(PHB_E_INVALID, "overlap %lld not in [0, row length %lld)", (long long)overlap, (long long)k->L);
+    PHB_CUDA(cudaSetDevice(k->device));
+    ShardPlan p;
+    if (!shard_plan(k, B, S, k->L, world, p)) return fail(PHB_E_INVALID, "time-axis sharding does not apply to this call (see phb_hmm_term_sharded_plan)");
+    const TransferVariant *tv = transfer_variant(k->M);
+    const int M = k->M, C = 7 * M;
+    int rc;
+    if ((rc = k->term_params.reserve(size_t(B) * C * k->elem())) != PHB_OK) return rc;
+    if ((rc = phb_params_from_particles(k, x, B, epoch_widths, n_epochs, theta, k->term_params.ptr, stream)) != PHB_OK) return rc;
+    const int64_t seg_lo = std::min<int64_t>(p.n_seg, int64_t(rank) * p.per_rank);
+    const int64_t seg_hi = std::min<int64_t>(p.n_seg, seg_lo + p.per_rank);
+    if (k->occupancy.find(tv->rows_func) == k->occupancy.end()) {
+        PHB_CUDA(cudaFuncSetAttribute(tv->rows_func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tv->smem)));
+        k->occupancy.emplace(tv->rows_func, 1);
+    }
+    if (seg_hi <= seg_lo || k->dry) return PHB_OK;
+    phb::TransferArgs ta{};
+    phb::KernelArgs &a = ta.k;
+    a.data = k->d_data;
+    a.pitch = k->pitch;
+    a.n_rows = k->N;
+    a.L = k->L;
+    a.inds = inds;
+    a.B = B;
+    a.S = S;
+    a.params6 = k->term_params.ptr;
+    a.pstride_b = C;
+    a.pi = static_cast<const char *>(k->term_params.ptr) + size_t(6) * M * k->elem();
+    a.pistride_b = C;
+    a.err_flag = k->d_err;
+    ta.n_seg = p.n_seg;
+    ta.seg_len = p.seg_len;
+    char *base = static_cast<char *>(gather);
+    ta.rows = reinterpret_cast<float *>(base);
+    ta.row_log2 = reinterpret_cast<double *>(base + p.rows_bytes);
+    ta.segs_per_slot = p.per_rank;
+    ta.slot_stride_rows = int64_t(p.slot_bytes / sizeof(float));
+    ta.slot_stride_log = int64_t(p.slot_bytes / sizeof(double));
+    ta.seg_first = seg_lo;
+    ta.n_seg_local = seg_hi - seg_lo;
+    const int64_t n_virtual = B * S * ta.n_seg_local * M;
+    void *kargs[] = {&ta};
+    PHB_CUDA(cudaLaunchKernel(tv->rows_func, dim3(unsigned((n_virtual + 127) / 128)), dim3(128), kargs, tv->smem, static_cast<cudaStream_t>(stream)));
+    k->launches += 1;
+    return PHB_OK;
+}
+
+int phb_hmm_term_sharded_end(phb_kernel *k, const int64_t *inds, int64_t B, int64_t S, int64_t overlap, int rank, int world,
+                             const void *gather, double *sums, void *stream) {
+    if (int rc = check_handle(k)) return rc;
+    if (!inds || !gather || !sums || B <= 0 || S <= 0 || rank < 0 || rank >= world) return fail(PHB_E_INVALID, "bad argument");
+    if (overlap < 0 || overlap >= k->L) return fail(PHB_E_INVALID, "overlap %lld not in [0, row length %lld)", (long long)overlap, (long long)k->L);
+    PHB_CUDA(cudaSetDevice(k->device));
+    ShardPlan p;
+    if (!shard_plan(k, B, S, k->L, world, p)) return fail(PHB_E_INVALID, "time-axis sharding does not apply to this call");
+    const TransferVariant *tv = transfer_variant(k->M);
+    const Variant *gv = segment_variant(k->M);
+    const int M = k->M, C = 7 * M;
+    const int64_t n_pairs = B * S;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t seg_lo = std::min<int64_t>(p.n_seg, int64_t(rank) * p.per_rank);
+    const int64_t seg_hi = std::min<int64_t>(p.n_seg, seg_lo + p.per_rank);
+    const int64_t n_local = seg_hi - seg_lo;
+    const int64_t n_groups = p.seg_ctas * n_local;
+    const int64_t occ = k->occupancy[gv->func];
+    const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(n_groups, occ * k->num_sms));
+    int rc;
+    if ((rc = k->term_ll.reserve(size_t(n_pairs) * sizeof(double))) != PHB_OK) return rc;
+    if ((rc = k->term_dlog.reserve(size_t(n_pairs) * C * k->elem())) != PHB_OK) return rc;
+    if ((rc = k->bnd_alpha.reserve(size_t(n_pairs) * (p.n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
+    if ((rc = k->bnd_beta.reserve(size_t(n_pairs) * (p.n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
+    if ((rc = k->seg_dlog.reserve(size_t(n_pairs) * std::max<int64_t>(n_local, 1) * C * sizeof(float))) != PHB_OK) return rc;
+    if ((rc = k->ckpt.reserve(size_t(grid) * (gv->NT / 32) * size_t(gv->ckpt_bytes_per_warp(p.seg_len)))) != PHB_OK) return rc;
+    if ((rc = k->gacc.reserve(size_t(grid) * gv->NT * 6 * (gv->M / gv->T) * sizeof(double))) != PHB_OK) return rc;
+    const bool marked = !k->dbl && k->escalate && k->n_flagged > 0;
+    if (marked && (rc = k->split.reserve((size_t(2) * S + 2) * sizeof(int32_t))) != PHB_OK) return rc;
+    if (!k->dry) {
+        // every process contributes zero where it has nothing to say (ll: process 0 only; marked rows: process 0's
+        // double launch only)
+        PHB_CUDA(cudaMemsetAsync(k->term_ll.ptr, 0, size_t(n_pairs) * sizeof(double), st));
+        PHB_CUDA(cudaMemsetAsync(k->term_dlog.ptr, 0, size_t(n_pairs) * C * k->elem(), st));
+        phb::TransferArgs ta{};
+        phb::KernelArgs &a = ta.k;
+        a.data = k->d_data;
+        a.pitch = k->pitch;
+        a.n_rows = k->N;
+        a.L = k->L;
+        a.inds = inds;
+        a.B = B;
+        a.S = S;
+        a.params6 = k->term_params.ptr;
+        a.pstride_b = C;
+        a.pi = static_cast<const char *>(k->term_params.ptr) + size_t(6) * M * k->elem();
+        a.pistride_b = C;
+        a.ll = static_cast<double *>(k->term_ll.ptr);
+        a.dlog = k->term_dlog.ptr;
+        a.err_flag = k->d_err;
+        a.skip_flag = marked ? k->d_rowflag : nullptr;
+        ta.n_seg = p.n_seg;
+        ta.seg_len = p.seg_len;
+        const char *base = static_cast<const char *>(gather);
+        ta.rows = reinterpret_cast<float *>(const_cast<char *>(base));
+        ta.row_log2 = reinterpret_cast<double *>(const_cast<char *>(base) + p.rows_bytes);
+        ta.segs_per_slot = p.per_rank;
+        ta.slot_stride_rows = int64_t(p.slot_bytes / sizeof(float));
+        ta.slot_stride_log = int64_t(p.slot_bytes / sizeof(double));
+        void *bnd_a = k->bnd_alpha.ptr, *bnd_b = k->bnd_beta.ptr;
+        void *bargs[] = {&ta, &bnd_a, &bnd_b};
+        PHB_CUDA(cudaLaunchKernel(tv->boundaries_func, dim3(unsigned((n_pairs * M + 127) / 128)), dim3(128), bargs, 0, st));
+        k->launches += 1;
+        if (n_local > 0) {
+            phb::KernelArgs sa = a;
+            sa.ckpt = k->ckpt.ptr;
+            sa.gacc = static_cast<double *>(k->gacc.ptr);
+            sa.seg_count = p.n_seg;
+            sa.seg_len = p.seg_len;
+            sa.seg_first = seg_lo;
+            sa.seg_local = n_local;
+            sa.bnd_alpha = bnd_a;
+            sa.bnd_beta = bnd_b;
+            sa.seg_dlog = k->seg_dlog.ptr;
+            sa.seg_ctas = p.seg_ctas;
+            sa.n_groups = n_groups;
+            void *kargs[] = {&sa};
+            PHB_CUDA(cudaLaunchKernel(gv->func, dim3(unsigned(grid)), dim3(gv->NT), kargs, gv->smem, st));
+            const int64_t n_out = n_pairs * C;
+            phb::sum_segments_kernel<float><<<unsigned((n_out + 255) / 256), 256, 0, st>>>(
+                static_cast<const float *>(k->seg_dlog.ptr), n_pairs, n_local, M, static_cast<float *>(k->term_dlog.ptr), 0, sa);
+            PHB_CUDA(cudaGetLastError());
+            k->launches += 2;
+        }
+        snprintf(k->last_name, sizeof k->last_name, "time-sharded %d/%d: transfer_rows_kernel<float,M=%d> + psmc_loglik_kernel<SEG> x %lld of %lld segments",
+                 rank, world, M, (long long)n_local, (long long)p.n_seg);
+    }
+    if (rank == 0) {
+        // process 0 owns: the log-likelihood (chain_boundaries_kernel wrote it everywhere: the others drop theirs below),
+        // the pairs on marked rows (double arithmetic over the whole chunk) and the warm-up term that is subtracted
+        phb::KernelArgs a{};
+        a.data = k->d_data;
+        a.pitch = k->pitch;
+        a.n_rows = k->N;
+        a.inds = inds;
+        a.B = B;
+        a.S = S;
+        a.params6 = k->term_params.ptr;
+        a.pstride_b = C;
+        a.pi = static_cast<const char *>(k->term_params.ptr) + size_t(6) * M * k->elem();
+        a.pistride_b = C;
+        a.ll = static_cast<double *>(k->term_ll.ptr);
+        a.dlog = k->term_dlog.ptr;
+        if (marked) {
+            const Variant *esc = escalation_variant(M);
+            int32_t *lists = static_cast<int32_t *>(k->split.ptr);
+            int32_t *counts = lists + 2 * S;
+            if (!k->dry) {
+                phb::split_minibatch_kernel<<<1, 1024, 0, st>>>(inds, S, k->d_rowflag, k->N, lists, counts);
+                PHB_CUDA(cudaGetLastError());
+                k->launches += 1;
+            }
+            phb::KernelArgs part = a;
+            part.L = k->L;
+            part.s_list = lists + S;
+            part.s_count = counts + 1;
+            if ((rc = launch_one(k, part, true, st, esc)) != PHB_OK) return rc;
+        }
+        if (overlap > 0) {
+            a.L = overlap;
+            a.out_mode = 1;
+            if ((rc = launch(k, a, true, st)) != PHB_OK) return rc;
+        }
+    }
+    if (k->dry) return PHB_OK;
+    // per-particle sums; the log-likelihood column comes from process 0 alone
+    if (rank != 0) PHB_CUDA(cudaMemsetAsync(k->term_ll.ptr, 0, size_t(n_pairs) * sizeof(double), st));
+    phb::sum_over_chunks_kernel<float><<<unsigned(B), 128, 0, st>>>(static_cast<const double *>(k->term_ll.ptr),
+                                                                      static_cast<const float *>(k->term_dlog.ptr), S, C, sums);
     PHB_CUDA(cudaGetLastError());
     k->launches += 1;
     return PHB_OK;

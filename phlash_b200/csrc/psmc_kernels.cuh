@@ -83,12 +83,14 @@ struct KernelArgs {
     // launch scores the G segments of every chunk as independent short "pairs" (L = sites per chunk),
     // started from bnd_alpha and closed with bnd_beta; partial gradients go to seg_dlog.
     int64_t seg_count;      // G, segments per chunk
+    int64_t seg_first;      // this launch scores segments [seg_first, seg_first + seg_local) only (time-axis
+    int64_t seg_local;      // sharding over processes; seg_local == 0 means all G)
     int64_t seg_len;        // sites per segment (multiple of 16); the last one has L - (G - 1) seg_len
     int64_t seg_ctas;       // groups per segment: group g scores segment g / seg_ctas, so that all warps of a CTA
                             // share the segment length (the loop bounds stay uniform for the shuffles)
     const void *bnd_alpha;  // [B * S][G + 1][M] FLOAT: forward vector entering segment g (sum 1)
     const void *bnd_beta;   // [B * S][G + 1][M] FLOAT: adjoint vector behind segment g - 1 (any scale)
-    void *seg_dlog;         // [B * S][G][7][M] FLOAT
+    void *seg_dlog;         // [B * S][segments of this launch][7][M] FLOAT
 };
 
 // Pair enumeration shared by the kernels: b major, position in the (sub-)list minor.
@@ -648,7 +650,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
     // uniform and the shuffles need no reconvergence guards
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         // SEG: group -> (segment of the chunk, group within the segment); L = sites of that segment
-        const int64_t pseg = SEG ? grp / a.seg_ctas : 0;
+        const int64_t pseg = SEG ? a.seg_first + grp / a.seg_ctas : 0;
         const int64_t L = SEG ? min(a.seg_len, a.L - pseg * a.seg_len) : a.L;
         const int64_t n_seg = (L + K - 1) / K;
         const int64_t pair_raw = ((SEG ? grp % a.seg_ctas : grp) * kWarps + warp) * PW + lp;
@@ -658,7 +660,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
             chunk_pair = writer ? pair_raw : n_pairs - 1;
             pb = chunk_pair / a.S;
             ps = chunk_pair % a.S;
-            pair = chunk_pair * a.seg_count + pseg;  // slot in seg_dlog
+            pair = chunk_pair * (a.seg_local ? a.seg_local : a.seg_count) + (pseg - a.seg_first);  // slot in seg_dlog
         } else {
             const PairIndex pidx = pair_index(a, writer ? pair_raw : n_pairs - 1, s_eff);  // idle lanes shadow the last pair
             pb = pidx.b;
@@ -1137,9 +1139,32 @@ struct TransferArgs {
     KernelArgs k;          // data, inds, B, S, params / pi layout, ll, err_flag, out_mode of the evaluation
     int64_t n_seg;         // G
     int64_t seg_len;       // sites per segment (multiple of 16; the last segment takes the rest)
-    float *rows;           // [pair][segment][M rows][M]
-    double *row_log2;      // [pair][segment][M rows]
+    // Operator blocks are stored SEGMENT-MAJOR in slots of segs_per_slot segments: block (pair, g) lives in slot
+    // g / segs_per_slot at [g % segs_per_slot][pair][M rows][M].  One process: a single slot holding all G
+    // segments.  Time-axis sharding: every process fills its own slot and an all-gather makes all of them
+    // visible everywhere (slot = rows then row_log2 of that process, so ONE collective moves both).
+    float *rows;
+    double *row_log2;      // same addressing, [M rows] per block
+    int64_t segs_per_slot;
+    int64_t slot_stride_rows;  // floats between consecutive slots of `rows`
+    int64_t slot_stride_log;   // doubles between consecutive slots of `row_log2`
+    int64_t seg_first;     // transfer_rows_kernel computes segments [seg_first, seg_first + n_seg_local)
+    int64_t n_seg_local;
 };
+__device__ __forceinline__ int64_t op_block(const TransferArgs &ta, int64_t pair, int64_t g, int64_t n_pairs, int64_t *slot) {
+    *slot = g / ta.segs_per_slot;
+    return (g - *slot * ta.segs_per_slot) * n_pairs + pair;
+}
+__device__ __forceinline__ const float *op_rows(const TransferArgs &ta, int64_t pair, int64_t g, int64_t n_pairs, int M) {
+    int64_t slot;
+    const int64_t blk = op_block(ta, pair, g, n_pairs, &slot);
+    return ta.rows + slot * ta.slot_stride_rows + blk * M * M;
+}
+__device__ __forceinline__ const double *op_log2(const TransferArgs &ta, int64_t pair, int64_t g, int64_t n_pairs, int M) {
+    int64_t slot;
+    const int64_t blk = op_block(ta, pair, g, n_pairs, &slot);
+    return ta.row_log2 + slot * ta.slot_stride_log + blk * M;
+}
 
 template <typename F, int M, int NT> __global__ void __maxnreg__(max_regs(NT, 3)) transfer_rows_kernel(const TransferArgs ta) {
     constexpr int MT = M, T = 1, K = 8;
@@ -1157,13 +1182,13 @@ template <typename F, int M, int NT> __global__ void __maxnreg__(max_regs(NT, 3)
         }
         __syncthreads();
     }
-    const int64_t n_virtual = a.B * a.S * ta.n_seg * M;
+    const int64_t n_virtual = a.B * a.S * ta.n_seg_local * M;
     const int64_t vraw = int64_t(blockIdx.x) * NT + threadIdx.x;
     const bool writer = vraw < n_virtual;
     const int64_t v = writer ? vraw : n_virtual - 1;
     const int unit = int(v % M);
-    const int64_t seg = (v / M) % ta.n_seg;
-    const int64_t pair = v / (M * ta.n_seg);
+    const int64_t seg = ta.seg_first + (v / M) % ta.n_seg_local;
+    const int64_t pair = v / (M * ta.n_seg_local);
     const int64_t pb = pair / a.S, ps = pair % a.S;
     const F *par = static_cast<const F *>(a.params6) + pb * a.pstride_b + ps * a.pstride_s;
     Params<F, MT> p;
@@ -1208,10 +1233,10 @@ template <typename F, int M, int NT> __global__ void __maxnreg__(max_regs(NT, 3)
     if (writer) {
         // exact normalisation of what is handed on (the reciprocal above is approximate)
         const F tot = pair_sum<F, MT, T>(x);
-        float *out = ta.rows + v * M;
+        float *out = const_cast<float *>(op_rows(ta, pair, seg, a.B * a.S, M)) + unit * M;
 #pragma unroll
         for (int k = 0; k < MT; ++k) out[k] = float(x[k] / tot);
-        ta.row_log2[v] = log2_scale + double(log2_of<F>(tot));
+        const_cast<double *>(op_log2(ta, pair, seg, a.B * a.S, M))[unit] = log2_scale + double(log2_of<F>(tot));
     }
 }
 
@@ -1229,8 +1254,8 @@ template <typename F, int M> __global__ void chain_transfer_kernel(const Transfe
     double ll2 = log2(tot);  // log2 of everything divided out so far
     for (int k = 0; k < M; ++k) alpha[k] /= tot;
     for (int64_t g = 0; g < ta.n_seg; ++g) {
-        const float *rows = ta.rows + (pair * ta.n_seg + g) * M * M;
-        const double *lg = ta.row_log2 + (pair * ta.n_seg + g) * M;
+        const float *rows = op_rows(ta, pair, g, a.B * a.S, M);
+        const double *lg = op_log2(ta, pair, g, a.B * a.S, M);
         double top = -1e300;
         for (int i = 0; i < M; ++i)
             if (alpha[i] > 0.0 && lg[i] > top) top = lg[i];
@@ -1295,8 +1320,8 @@ template <typename F, int M> __global__ void chain_boundaries_kernel(const Trans
     v /= tot;
     if (writer) al[k] = F(v);
     for (int64_t g = 0; g < G; ++g) {
-        const float *rows = ta.rows + (pair * G + g) * M * M;
-        const double lg = ta.row_log2[(pair * G + g) * M + k];
+        const float *rows = op_rows(ta, pair, g, n_pairs, M);
+        const double lg = op_log2(ta, pair, g, n_pairs, M)[k];
         const double top = group_max<M>(v > 0.0 ? lg : -1e300);
         const double w = v > 0.0 ? v * exp2(lg - top) : 0.0;
         double next = 0.0;
@@ -1311,8 +1336,8 @@ template <typename F, int M> __global__ void chain_boundaries_kernel(const Trans
     v = 1.0;
     if (writer) be[G * M + k] = F(1);
     for (int64_t g = G - 1; g >= 0; --g) {
-        const float *rows = ta.rows + (pair * G + g) * M * M;
-        const double lg = ta.row_log2[(pair * G + g) * M + k];
+        const float *rows = op_rows(ta, pair, g, n_pairs, M);
+        const double lg = op_log2(ta, pair, g, n_pairs, M)[k];
         const double top = group_max<M>(lg);
         double acc = 0.0;
 #pragma unroll
@@ -1346,7 +1371,9 @@ __global__ void sum_segments_kernel(const F *__restrict__ seg_dlog, int64_t n_pa
     const int64_t rm = i % (7 * M);
     if (outputs_skipped(a, pair % a.S)) return;
     const F *src = seg_dlog + pair * G * 7 * M + rm;
-    double acc = double(src[0]);
+    // (G = segments of this launch; the pi row belongs to the chunk's first segment: zero from a launch that
+    // does not hold it, i.e. under time-axis sharding)
+    double acc = (rm < 6 * M || a.seg_first == 0) ? double(src[0]) : 0.0;
     if (rm < 6 * M)
         for (int64_t g = 1; g < G; ++g) acc += double(src[g * 7 * M]);
     dlog[i] = out_mode ? F(double(dlog[i]) - acc) : F(acc);

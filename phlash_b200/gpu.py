@@ -423,6 +423,44 @@ class _PSMCKernelBase:
         )
         return ll, (dlog if grad else None)
 
+    # ---- time-axis sharding of a small minibatch over several processes (include/phlash_b200.h)
+    def sharded_plan(self, B: int, S: int, overlap: int, world: int):
+        """(segments, bytes per process of the all-gather buffer); segments == 0: does not apply"""
+        n_seg, slot = ctypes.c_int64(), ctypes.c_int64()
+        _check(self._lib.phb_hmm_term_sharded_plan(self._handle, int(B), int(S), int(overlap), int(world),
+                                                   ctypes.byref(n_seg), ctypes.byref(slot)))
+        return n_seg.value, slot.value
+
+    def sharded_begin(self, x, pattern: str, theta: float, inds, overlap: int, rank: int, world: int, gather, stream=None):
+        import torch
+
+        widths, B, _ = self._term_args(x, pattern)
+        assert inds.is_cuda and inds.dtype == torch.int64 and inds.is_contiguous()
+        assert gather.is_cuda and gather.dtype == torch.uint8 and gather.is_contiguous()
+        if stream is None:
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+        _check(
+            self._lib.phb_hmm_term_sharded_begin(
+                self._handle, x.data_ptr(), B, _ptr(widths), len(widths), float(theta), inds.data_ptr(), int(inds.shape[0]),
+                int(overlap), int(rank), int(world), gather.data_ptr(), ctypes.c_void_p(stream),
+            )
+        )
+
+    def sharded_end(self, inds, B: int, overlap: int, rank: int, world: int, gather, stream=None):
+        """this process's partial per-particle sums [B, 1 + 7 M] (to be all-reduced)"""
+        import torch
+
+        sums = torch.empty((int(B), 1 + 7 * self._M), dtype=torch.float64, device=inds.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(inds.device).cuda_stream
+        _check(
+            self._lib.phb_hmm_term_sharded_end(
+                self._handle, inds.data_ptr(), int(B), int(inds.shape[0]), int(overlap), int(rank), int(world),
+                gather.data_ptr(), sums.data_ptr(), ctypes.c_void_p(stream),
+            )
+        )
+        return sums
+
     def sum_over_chunks(self, ll, dlog, out=None, stream=None):
         """ll [B, S] float64, dlog [B, S, 7, M] (torch CUDA) -> per-particle sums [B, 1 + 7 M] float64: what one
         process per GPU contributes to the all-reduce of a step (phb_sum_over_chunks_device)."""

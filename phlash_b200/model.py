@@ -17,6 +17,20 @@ from __future__ import annotations
 from phlash_b200.distributed import all_reduce_sum, shard_bounds
 
 
+_GATHER = {}
+
+
+def _gather_buffer(kern, n_bytes: int, device):
+    """the all-gather buffer of the time-sharded path, kept per kernel object (stable address: CUDA graphs)"""
+    import torch
+
+    buf = _GATHER.get(id(kern))
+    if buf is None or buf.numel() < n_bytes or buf.device != device:
+        buf = torch.empty(n_bytes, dtype=torch.uint8, device=device)
+        _GATHER[id(kern)] = buf
+    return buf[:n_bytes]
+
+
 def sample_minibatch(rng, n_chunks: int, minibatch_size: int):
     """inds ~ choice(N, (S,)) WITH replacement (reference: mcmc.py:277)."""
     return rng.integers(0, n_chunks, size=minibatch_size)
@@ -36,7 +50,22 @@ def hmm_term_value_and_grad(kern, x, pattern: str, theta: float, inds, overlap: 
     all-reduce joins the per-particle sums [B, 1 + 7 M], and every rank finishes on the total."""
     if world == 1:
         return kern.hmm_term(x, pattern, theta, inds, overlap, weight, grad)
-    lo, hi = shard_bounds(int(inds.shape[0]), rank, world)
+    S = int(inds.shape[0])
+    if grad and S < world:
+        # fewer chunks than GPUs (the reference's default S <= 5): shard the SEGMENTS of the parallel-in-time
+        # gradient instead of the chunks - one all-gather of the segment operators, then the usual all-reduce
+        n_seg, slot = kern.sharded_plan(int(x.shape[0]), S, overlap, world)
+        if n_seg > 0:
+            import torch
+            import torch.distributed as dist
+
+            gather = _gather_buffer(kern, world * slot, x.device)
+            kern.sharded_begin(x, pattern, theta, inds, overlap, rank, world, gather)
+            dist.all_gather_into_tensor(gather, gather[rank * slot:(rank + 1) * slot])
+            sums = kern.sharded_end(inds, int(x.shape[0]), overlap, rank, world, gather)
+            all_reduce_sum(sums)
+            return kern.hmm_term_finish(x, pattern, theta, sums, weight, grad)
+    lo, hi = shard_bounds(S, rank, world)
     sums = kern.hmm_term_sums(x, pattern, theta, inds[lo:hi].contiguous(), overlap, grad)
     all_reduce_sum(sums)
     return kern.hmm_term_finish(x, pattern, theta, sums, weight, grad)

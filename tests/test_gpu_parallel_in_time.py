@@ -242,3 +242,41 @@ def test_two_sweep_is_chosen_between_operators_and_store_all():
         pa = np.broadcast_to(pps[:1, None], (1, n_chunks, 7, 16)).copy()
         kern.evaluate(pa, np.zeros(n_chunks, dtype=np.int64), True)
         assert expect in kern.last_kernel_name, (n_chunks, kern.last_kernel_name)
+
+
+@pytest.mark.parametrize("S,world", [(1, 2), (1, 8), (3, 4), (5, 8)])
+def test_time_axis_sharding_equals_the_single_process_term(S, world):
+    """phb_hmm_term_sharded_*: the segments of the parallel-in-time gradient sharded over `world` processes.
+    Emulated on ONE GPU: every "process" fills its slot of the gather buffer (what the all-gather would
+    deliver), then every one of them finishes its share; the partial per-particle sums add up to the sums of
+    the single-process call (different segmentation: agreement to fp32 round-off, not bit for bit).  The
+    data hold a marked row (padded last chunk), which process 0 scores in double."""
+    import torch
+
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    het = orc.synth_het_matrix(1, 420_000, seed=11)
+    chunks = orc.chunk_het_matrix(het, 500, 50_000)
+    _, xs, pattern = orc.synth_particles(16, 40, seed=6)
+    dev = torch.device("cuda:0")
+    x = torch.tensor(xs, dtype=torch.float64, device=dev)
+    kern = _PSMCKernelBase(16, chunks, overlap=500)
+    assert kern.num_escalated_rows == 1
+    inds = torch.tensor([8, 2, 5, 0, 7][:S], device=dev)  # chunk 8 is the marked one
+    want = kern.hmm_term_sums(x, pattern, 1e-2, inds, 500, True)
+    n_seg, slot = kern.sharded_plan(40, S, 500, world)
+    assert n_seg >= world and slot > 0
+    gather = torch.zeros(world * slot, dtype=torch.uint8, device=dev)
+    for rank in range(world):
+        kern.sharded_begin(x, pattern, 1e-2, inds, 500, rank, world, gather)
+    total = torch.zeros_like(want)
+    for rank in range(world):
+        total += kern.sharded_end(inds, 40, 500, rank, world, gather)
+        assert "time-sharded" in kern.last_kernel_name or rank == 0
+    kern.sync()
+    want, total = want.cpu().numpy(), total.cpu().numpy()
+    np.testing.assert_allclose(total[:, 0], want[:, 0], rtol=1e-6)
+    g_want, g_got = want[:, 1:].reshape(40, 7, 16), total[:, 1:].reshape(40, 7, 16)
+    scale = np.abs(g_want).max(-1, keepdims=True)
+    # (the sums are differences LL(all) - LL(warm-up): pi row entries are small remainders of O(1) terms)
+    assert np.all(np.abs(g_got - g_want) <= 2e-4 * np.abs(g_want) + 2e-6 * np.maximum(scale, 1.0))
