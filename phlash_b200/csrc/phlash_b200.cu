@@ -109,7 +109,7 @@ struct phb_kernel {
     int escalate = 1;
     // experiment knobs, read from the environment ONCE when the object is created (never per call):
     // PHB_NT, PHB_STORE_ALL, PHB_PARALLEL_IN_TIME, PHB_PIT_SEGMENTS
-    int env_nt = 0, env_store_all = -2, env_pit = -2, env_pit_segments = 0;
+    int env_nt = 0, env_store_all = -2, env_pit = -2, env_pit_segments = 0, env_sweep_T = 0;
     // phb_reserve(): the dispatch runs with dry = true - every scratch buffer is sized and every kernel
     // attribute set exactly as a real call would, but nothing is launched
     bool dry = false;
@@ -249,6 +249,29 @@ const std::vector<StoreAllVariant> &storeall_variants() {
         make_storeall<4, 16, 128, 4>(),  // M = 64
     };
     return table;
+}
+
+// Lane layouts of the boundary sweeps (latency regime: one warp per scheduler, what counts is the length of
+// the dependency chain per site, not the instruction count).  PHB_SWEEP_T picks one for experiments.
+struct SweepVariant {
+    int M, T, MT, NT;
+    const void *func;
+    size_t smem;
+};
+template <int MT, int T, int NT, int MINB> SweepVariant make_sweep() {
+    return SweepVariant{MT * T, T, MT, NT, reinterpret_cast<const void *>(&phb::boundary_sweep_kernel<float, MT, T, NT, MINB>),
+                        phb::smem_bytes<float, MT, 8, NT, false>()};
+}
+const SweepVariant *sweep_variant(int M, int want_T) {
+    static const std::vector<SweepVariant> table = {
+        make_sweep<8, 2, 64, 4>(),    // M = 16, two lanes per pair
+        make_sweep<16, 1, 32, 4>(),   // M = 16, thread per pair
+        make_sweep<16, 2, 64, 4>(),   // M = 32
+        make_sweep<16, 4, 128, 2>(),  // M = 64
+    };
+    for (const SweepVariant &v : table)
+        if (v.M == M && v.T == want_T) return &v;
+    return nullptr;
 }
 
 // Parallel-in-time forward evaluation (few, long pairs; see transfer_rows_kernel): float, M <= 16.
@@ -452,16 +475,27 @@ int try_two_sweep_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t
     if (n_seg < 2) return kNotTaken;
     const int64_t n_groups = seg_ctas * n_seg;
     const int64_t grid = std::min<int64_t>(n_groups, resident);
-    const int64_t sweep_ctas = (n_pairs + sv->NT / sv->T - 1) / (sv->NT / sv->T);
+    // lane layout of the sweeps: the store-all table's, unless PHB_SWEEP_T names another one
+    const void *sweep_func = sv->sweep_func;
+    size_t sweep_smem = sv->smem;
+    int sweep_NT = sv->NT, sweep_T = sv->T, sweep_MT = sv->MT;
+    if (const SweepVariant *alt = sweep_variant(M, k->env_sweep_T)) {
+        sweep_func = alt->func;
+        sweep_smem = alt->smem;
+        sweep_NT = alt->NT;
+        sweep_T = alt->T;
+        sweep_MT = alt->MT;
+    }
+    const int64_t sweep_ctas = (n_pairs + sweep_NT / sweep_T - 1) / (sweep_NT / sweep_T);
     int rc;
     if ((rc = k->bnd_alpha.reserve(size_t(n_pairs) * (n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
     if ((rc = k->bnd_beta.reserve(size_t(n_pairs) * (n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
     if ((rc = k->seg_dlog.reserve(size_t(n_pairs) * n_seg * 7 * M * sizeof(float))) != PHB_OK) return rc;
     if ((rc = k->ckpt.reserve(size_t(grid) * (tv->NT / 32) * size_t(tv->ckpt_bytes_per_warp(seg_len)))) != PHB_OK) return rc;
     if ((rc = k->gacc.reserve(size_t(grid) * tv->NT * 6 * (tv->M / tv->T) * sizeof(double))) != PHB_OK) return rc;
-    if (k->occupancy.find(sv->sweep_func) == k->occupancy.end()) {
-        PHB_CUDA(cudaFuncSetAttribute(sv->sweep_func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sv->smem)));
-        k->occupancy.emplace(sv->sweep_func, 1);
+    if (k->occupancy.find(sweep_func) == k->occupancy.end()) {
+        PHB_CUDA(cudaFuncSetAttribute(sweep_func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sweep_smem)));
+        k->occupancy.emplace(sweep_func, 1);
     }
     if (k->dry) return PHB_OK;
     phb::KernelArgs sa = a;
@@ -476,7 +510,7 @@ int try_two_sweep_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t
     sa.seg_ctas = seg_ctas;
     sa.n_groups = n_groups;
     void *kargs[] = {&sa};
-    PHB_CUDA(cudaLaunchKernel(sv->sweep_func, dim3(unsigned(2 * sweep_ctas)), dim3(sv->NT), kargs, sv->smem, stream));
+    PHB_CUDA(cudaLaunchKernel(sweep_func, dim3(unsigned(2 * sweep_ctas)), dim3(sweep_NT), kargs, sweep_smem, stream));
     PHB_CUDA(cudaLaunchKernel(tv->func, dim3(unsigned(grid)), dim3(tv->NT), kargs, tv->smem, stream));
     const int64_t n_out = n_pairs * 7 * M;
     phb::sum_segments_kernel<float><<<unsigned((n_out + 255) / 256), 256, 0, stream>>>(
@@ -484,7 +518,7 @@ int try_two_sweep_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t
     PHB_CUDA(cudaGetLastError());
     k->launches += 3;
     snprintf(k->last_name, sizeof k->last_name, "boundary_sweep_kernel<float,MT=%d,T=%d> + psmc_loglik_kernel<SEG,MT=%d,T=%d> x %lld segments",
-             sv->MT, sv->T, tv->M / tv->T, tv->T, (long long)n_seg);
+             sweep_MT, sweep_T, tv->M / tv->T, tv->T, (long long)n_seg);
     return PHB_OK;
 }
 
@@ -793,6 +827,7 @@ static int new_kernel(int M, int64_t N, int64_t L, int double_precision, int dev
     if (const char *v = getenv("PHB_STORE_ALL")) k->env_store_all = atoi(v);
     if (const char *v = getenv("PHB_PARALLEL_IN_TIME")) k->env_pit = atoi(v);
     if (const char *v = getenv("PHB_PIT_SEGMENTS")) k->env_pit_segments = atoi(v);
+    if (const char *v = getenv("PHB_SWEEP_T")) k->env_sweep_T = atoi(v);
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&k->d_data), size_t(N) * size_t(k->pitch));
     if (e != cudaSuccess) {
         cudaGetLastError();

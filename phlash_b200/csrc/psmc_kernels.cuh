@@ -379,11 +379,14 @@ template <typename F, int MT> struct Grad<F, MT, false> {
         for (int k = 0; k < MT; ++k) b[k] = d[k] = u[k] = v[k] = e0[k] = e1[k] = F(0);
     }
 };
+// (no accumulator for d: every posterior sums the three ways of arriving in a state, so
+//     d ll / d log d_k = sum_t posterior_t(k) - d ll / d log b_k - d ll / d log v_k,
+// and the posterior sums are accumulated anyway for the emission rows - 16 FMAs per site and 16 registers less)
 template <typename F, int MT> struct Grad<F, MT, true> {
-    F b[MT], d[MT], u[MT], v[MT];
+    F b[MT], u[MT], v[MT];
     __device__ __forceinline__ void clear() {
 #pragma unroll
-        for (int k = 0; k < MT; ++k) b[k] = d[k] = u[k] = v[k] = F(0);
+        for (int k = 0; k < MT; ++k) b[k] = u[k] = v[k] = F(0);
     }
 };
 
@@ -423,16 +426,19 @@ template <typename F, int MT, int NT> struct EmisAcc {
             sts_word(base + (row * QN + q) * NT * 16, a);
         }
     }
+    // rows emis0 / emis1 go to slots 4 / 5; the posterior mass of MISSING observations (row 2) goes to
+    // slot 1, which has no accumulator of its own (see Grad<F, MT, true>)
     __device__ __forceinline__ void flush(double *acc, int64_t stride) {
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < 3; ++r) {
+            const int slot = r < 2 ? 4 + r : 1;
 #pragma unroll
             for (int q = 0; q < QN; ++q) {
                 F a[W], z[W];
                 lds_word(base + (r * QN + q) * NT * 16, a);
 #pragma unroll
                 for (int i = 0; i < W; ++i) {
-                    atomicAdd(acc + int64_t((4 + r) * MT + q * W + i) * stride, double(a[i]));
+                    atomicAdd(acc + int64_t(slot * MT + q * W + i) * stride, double(a[i]));
                     z[i] = F(0);
                 }
                 sts_word(base + (r * QN + q) * NT * 16, z);
@@ -515,7 +521,7 @@ __device__ __forceinline__ void backward_site(F (&beta)[MT], const F (&x)[MT], i
     for (int i = 0; i < MT; ++i) {
         const int k = i, j = MT - 1 - i;
         beta[k] = fma(p.d[k], w[k], b_run);
-        g.d[k] = fma(x[k], w[k], g.d[k]);
+        if constexpr (!ESM) g.d[k] = fma(x[k], w[k], g.d[k]);
         g.v[k] = fma(x_run, w[k], g.v[k]);
         b_run = fma(p.b[k], w[k], b_run);
         x_run = fma(p.u[k], x[k], x_run);
@@ -871,7 +877,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                     double *acc = PHB_GACC_BASE;
                     const int64_t stride = PHB_GACC_STRIDE;
                     flush_row<F, MT>(g.b, 0, acc, stride);
-                    flush_row<F, MT>(g.d, 1, acc, stride);
+                    if constexpr (!ESM) flush_row<F, MT>(g.d, 1, acc, stride);
                     flush_row<F, MT>(g.u, 2, acc, stride);
                     flush_row<F, MT>(g.v, 3, acc, stride);
                     if constexpr (ESM) {
@@ -889,13 +895,23 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
 #pragma unroll
                 for (int k = 0; k < MT; ++k) {
                     F val[7];
-                    val[0] = F(gacc[int64_t(0 * MT + k) * gacc_stride] * double(p.b[k]));
-                    val[1] = F(gacc[int64_t(1 * MT + k) * gacc_stride] * double(p.d[k]));
+                    const double gb = gacc[int64_t(0 * MT + k) * gacc_stride] * double(p.b[k]);
+                    const double gv = gacc[int64_t(3 * MT + k) * gacc_stride] * double(p.v[k]);
+                    const double ge0 = gacc[int64_t(4 * MT + k) * gacc_stride], ge1 = gacc[int64_t(5 * MT + k) * gacc_stride];
+                    val[0] = F(gb);
                     val[2] = F(gacc[int64_t(2 * MT + k) * gacc_stride] * double(p.u[k]));
-                    val[3] = F(gacc[int64_t(3 * MT + k) * gacc_stride] * double(p.v[k]));
-                    val[4] = F(gacc[int64_t(4 * MT + k) * gacc_stride]);
-                    val[5] = F(gacc[int64_t(5 * MT + k) * gacc_stride]);
+                    val[3] = F(gv);
+                    val[4] = F(ge0);
+                    val[5] = F(ge1);
                     val[6] = beta[k] * F(pi_p[k]);
+                    if constexpr (ESM) {
+                        // slot 1 holds the posterior mass of the missing observations plus the posterior of the
+                        // START vector (the first adjoint step books it under "no observation"), which is val[6]
+                        const double arrivals = ge0 + ge1 + gacc[int64_t(1 * MT + k) * gacc_stride] - double(val[6]);
+                        val[1] = p.d[k] == F(0) ? F(0) : F(arrivals - gb - gv);
+                    } else {
+                        val[1] = F(gacc[int64_t(1 * MT + k) * gacc_stride] * double(p.d[k]));
+                    }
 #pragma unroll
                     for (int r = 0; r < 7; ++r) out[r * M + k] = IO((!SEG && a.out_mode) ? F(out[r * M + k]) - val[r] : val[r]);
                 }
