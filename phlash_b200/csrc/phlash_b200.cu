@@ -306,6 +306,12 @@ bool storeall_scratch_fits(const phb_kernel *k, size_t x_bytes, size_t s_bytes) 
     return x_bytes + s_bytes <= (free_b + k->xall.cap + k->sall.cap) / 2;
 }
 
+// Groups (CTAs' worth of pairs) of psmc_loglik_kernel
+int64_t chunk_major_groups(const Variant *v, int64_t B, int64_t S) {
+    const int64_t pairs_per_cta = v->NT / v->T;
+    return (B * S + pairs_per_cta - 1) / pairs_per_cta;
+}
+
 const Variant *pick_variant(const phb_kernel *k, bool grad, int64_t n_pairs) {
     const Variant *last = nullptr, *forced = nullptr, *first_fill = nullptr;
     // Lane layouts are ordered by increasing T (fewer lanes per pair = fewer instructions per pair).
@@ -369,8 +375,7 @@ int try_parallel_in_time_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaS
     }
     if (occ < 1) return kNotTaken;
     const int64_t resident = int64_t(occ) * k->num_sms;
-    const int pairs_per_group = gv->NT / gv->T;
-    const int64_t seg_ctas = (n_pairs + pairs_per_group - 1) / pairs_per_group;  // groups per segment
+    const int64_t seg_ctas = chunk_major_groups(gv, a.B, a.S);  // groups per segment
     const int64_t min_seg = pit_mode == 1 ? 64 : 1024;
     // as many segments as keep every group of the segment passes resident at once
     int64_t n_seg = std::min(resident / seg_ctas, a.L / min_seg);
@@ -463,8 +468,7 @@ int try_two_sweep_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t
     }
     if (occ < 1) return kNotTaken;
     const int64_t resident = int64_t(occ) * k->num_sms;
-    const int pairs_per_group = tv->NT / tv->T;
-    const int64_t seg_ctas = (n_pairs + pairs_per_group - 1) / pairs_per_group;  // groups per segment
+    const int64_t seg_ctas = chunk_major_groups(tv, a.B, a.S);  // groups per segment
     const int64_t min_seg = pit_mode == 2 ? 64 : 1024;
     int64_t n_seg = std::min(std::max<int64_t>(resident / seg_ctas, 2), a.L / min_seg);
     if (k->env_pit_segments > 0) n_seg = std::min<int64_t>(k->env_pit_segments, a.L / 64);  // experiments
@@ -644,8 +648,7 @@ bool shard_plan(phb_kernel *k, int64_t B, int64_t S, int64_t L, int world, Shard
         occ = it->second;
     }
     if (occ < 1) return false;
-    const int pairs_per_group = gv->NT / gv->T;
-    p.seg_ctas = (n_pairs + pairs_per_group - 1) / pairs_per_group;
+    p.seg_ctas = chunk_major_groups(gv, B, S);
     // as many segments per process as keep its gradient groups resident at once; segments >= 512 sites
     int64_t per_rank = std::min<int64_t>(int64_t(occ) * k->num_sms / p.seg_ctas, (L / 512) / world);
     if (k->env_pit_segments > 0) per_rank = std::max<int64_t>(1, k->env_pit_segments / world);
@@ -667,8 +670,7 @@ int launch_throughput_kernel(phb_kernel *k, phb::KernelArgs a, bool grad, cudaSt
     const int64_t n_pairs = a.B * a.S;  // upper bound when a sub-list is given
     const Variant *v = fixed ? fixed : pick_variant(k, grad, n_pairs);
     if (!v) return fail(PHB_E_INVALID, "no kernel variant for M=%d, threads_per_pair=%d", k->M, k->force_T);
-    const int pairs_per_cta = v->NT / v->T;
-    a.n_groups = (n_pairs + pairs_per_cta - 1) / pairs_per_cta;
+    a.n_groups = chunk_major_groups(v, a.B, a.S);
     const size_t smem = v->smem;
     int occ = 0;
     {

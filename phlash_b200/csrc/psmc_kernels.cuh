@@ -93,7 +93,8 @@ struct KernelArgs {
     void *seg_dlog;         // [B * S][segments of this launch][7][M] FLOAT
 };
 
-// Pair enumeration shared by the kernels: b major, position in the (sub-)list minor.
+// Pair enumeration of the store-all kernel: b major, position in the (sub-)list minor.  (psmc_loglik_kernel
+// enumerates chunk major, see there.)
 struct PairIndex {
     int64_t b, s, out;  // particle, position in the full minibatch, index into ll / dlog ([B, S])
 };
@@ -636,8 +637,14 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
     const int sub = lane % T;
     const int lp = lane / T;
     static_assert(!SEG || (GRAD && sizeof(IO) == sizeof(F)), "segment mode: gradient kernel, plain buffers");
+    // Work enumeration: CHUNK major, particle minor (pair p -> chunk p / B, particle p % B), so that the lanes of
+    // a warp score consecutive particles of the SAME chunk (a warp straddles two chunks only where 32 / T does
+    // not divide B): their observation requests carry one address and are served as one transaction, and all
+    // warps that score a chunk share its lines in L1 / L2.  (Rounding B up to whole warps per chunk would make
+    // the observations provably warp-uniform, but costs padding lanes and, at the benchmark shape, a ninth round
+    // of groups on the persistent grid: measured 7 % slower.)
     const int64_t s_eff = listed_chunks(a);
-    const int64_t n_pairs = SEG ? a.B * a.S : a.B * s_eff;
+    const int64_t n_pairs = (SEG ? a.S : s_eff) * a.B;
     const int64_t n_groups = (!SEG && a.s_list) ? (n_pairs + kWarps * PW - 1) / (kWarps * PW) : a.n_groups;
     const int64_t L_max = SEG ? a.seg_len : a.L;
     const int64_t warp_slot = int64_t(blockIdx.x) * kWarps + warp;
@@ -661,18 +668,13 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
         const int64_t n_seg = (L + K - 1) / K;
         const int64_t pair_raw = ((SEG ? grp % a.seg_ctas : grp) * kWarps + warp) * PW + lp;
         const bool writer = pair_raw < n_pairs;
-        int64_t pb, ps, pair, chunk_pair = 0;
-        if constexpr (SEG) {
-            chunk_pair = writer ? pair_raw : n_pairs - 1;
-            pb = chunk_pair / a.S;
-            ps = chunk_pair % a.S;
-            pair = chunk_pair * (a.seg_local ? a.seg_local : a.seg_count) + (pseg - a.seg_first);  // slot in seg_dlog
-        } else {
-            const PairIndex pidx = pair_index(a, writer ? pair_raw : n_pairs - 1, s_eff);  // idle lanes shadow the last pair
-            pb = pidx.b;
-            ps = pidx.s;
-            pair = pidx.out;
-        }
+        const int64_t pair_idx = writer ? pair_raw : n_pairs - 1;  // idle lanes shadow the last pair
+        const int64_t slot = pair_idx / a.B;                        // position in the (sub-)list of chunks
+        const int64_t pb = pair_idx - slot * a.B;
+        const int64_t ps = (!SEG && a.s_list) ? int64_t(a.s_list[slot]) : slot;
+        const int64_t chunk_pair = pb * a.S + ps;  // index into ll / dlog ([B, S]) and the boundary vectors
+        int64_t pair = chunk_pair;
+        if constexpr (SEG) pair = chunk_pair * (a.seg_local ? a.seg_local : a.seg_count) + (pseg - a.seg_first);  // slot in seg_dlog
         Params<F, MT> p;
         p.load(params6 + pb * a.pstride_b + ps * a.pstride_s + sub * MT, M);
         et.fill(params6 + pb * a.pstride_b + ps * a.pstride_s + sub * MT, M);
