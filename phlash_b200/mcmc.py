@@ -23,7 +23,6 @@ from typing import Callable, List, Optional
 import numpy as np
 
 from phlash_b200 import model
-from phlash_b200.distributed import all_reduce_sum, shard_bounds
 
 
 @dataclass
@@ -80,7 +79,6 @@ def fit_loop(chunks: np.ndarray, x0, pattern: str, theta: float, update: Callabl
             test = test[:max_samples]  # mcmc.py:208-210
         test_kern = model.elpd_kernel(M, test, device=device)
     weight = model.minibatch_weight(N, S)  # mcmc.py:240-247: c = [1, N / S, 1]
-    lo, hi = shard_bounds(S, rank, world)
     kern.reserve(B, S, overlap)
     inds = torch.empty(S, dtype=torch.int64, device=dev)
     kern.set_iteration(0)
@@ -88,12 +86,9 @@ def fit_loop(chunks: np.ndarray, x0, pattern: str, theta: float, update: Callabl
     def one_iteration():
         # mcmc.py:277-279
         kern.sample_minibatch(seed, S, out=inds)
-        if world == 1:
-            _, g = kern.hmm_term(x, pattern, theta, inds, overlap, weight, True)
-        else:
-            sums = kern.hmm_term_sums(x, pattern, theta, inds[lo:hi], overlap, True)
-            all_reduce_sum(sums)
-            _, g = kern.hmm_term_finish(x, pattern, theta, sums, weight, True)
+        # one library call on one GPU; with several processes the chunks - or, for fewer chunks than processes,
+        # the segments of the parallel-in-time gradient - are sharded and joined by one all-reduce
+        _, g = model.hmm_term_value_and_grad(kern, x, pattern, theta, inds, overlap, weight, rank=rank, world=world)
         if log_prior_grad is not None:
             g = g + log_prior_grad(x)
         update(x, g)

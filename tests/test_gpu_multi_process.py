@@ -30,7 +30,7 @@ def _worker(rank, world, port, chunks, xs, pattern, cases, out_dir):
         inds_d = torch.tensor(inds, device=dev)
         value, grad = model.hmm_term_value_and_grad(kern, x, pattern, 1e-2, inds_d, 500, weight=2.5, rank=rank, world=world)
         torch.cuda.synchronize()
-        if rank == 0:
+        if rank == world - 1:  # (process 0's last launch is the warm-up term it subtracts)
             np.savez(os.path.join(out_dir, f"{name}.npz"), value=value.cpu().numpy(), grad=grad.cpu().numpy(),
                      kernel=np.array(kern.last_kernel_name))
     dist.destroy_process_group()
