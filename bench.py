@@ -468,7 +468,7 @@ def main():
                        "pinned_h2d_gbs_measured": rate, "pcie_copy_seconds_at_that_rate": chunks_full.nbytes / (rate * 1e9),
                        "create_over_pcie_copy": t_create / (chunks_full.nbytes / (rate * 1e9)),
                        "host_tiling_seconds": t_host,
-                       "what": "phb_create_chunks: pageable host matrix -> 2 pinned slabs filled by 8 host threads -> H2D, "
+                       "what": "phb_create_chunks: pageable host matrix -> 2 pinned slabs filled by up to 16 host threads -> H2D, "
                                "validated / clipped / padded on the device per slab, rows with long constant runs marked"}
         kern_full = kern
         S = cfg["minibatch"]

@@ -6,6 +6,7 @@
 #include "psmc_kernels.cuh"
 #include "psmc_params.cuh"
 #include "psmc_support.cuh"
+#include "psmc_uniform.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -100,6 +101,7 @@ struct phb_kernel {
     DeviceBuffer term_io;                                     // device copies of the host entry's buffers
     DeviceBuffer transfer_rows, transfer_log;                 // parallel-in-time forward evaluation
     DeviceBuffer bnd_alpha, bnd_beta, seg_dlog;               // ... and gradient
+    DeviceBuffer uniform_stage;                               // parameter rows packed for the constant bank (psmc_uniform.cuh)
     int parallel_in_time = -1;  // -1 auto, 0 never, 1 whenever possible
     int store_all_mode = -1;  // -1 auto, 0 never, 1 whenever a store-all variant exists
     // precision escalation (float objects): rows holding a long run of identical observations are
@@ -109,7 +111,7 @@ struct phb_kernel {
     int escalate = 1;
     // experiment knobs, read from the environment ONCE when the object is created (never per call):
     // PHB_NT, PHB_STORE_ALL, PHB_PARALLEL_IN_TIME, PHB_PIT_SEGMENTS
-    int env_nt = 0, env_store_all = -2, env_pit = -2, env_pit_segments = 0, env_sweep_T = 0;
+    int env_nt = 0, env_store_all = -2, env_pit = -2, env_pit_segments = 0, env_sweep_T = 0, env_uniform = 1;
     // phb_reserve(): the dispatch runs with dry = true - every scratch buffer is sized and every kernel
     // attribute set exactly as a real call would, but nothing is launched
     bool dry = false;
@@ -664,10 +666,79 @@ bool shard_plan(phb_kernel *k, int64_t B, int64_t S, int64_t L, int world, Shard
     return true;
 }
 
+// (4a) FORWARD-ONLY evaluation of large minibatches at M = 16 whose parameter rows are shared by the chunks of a
+// particle: the same recursion with the parameters in uniform registers (psmc_uniform.cuh; +28 % measured),
+// scored in batches of kUniformSlots particles (the constant bank holds that many).
+int try_uniform_throughput(phb_kernel *k, const phb::KernelArgs &a, bool grad, cudaStream_t stream) {
+    if (grad || k->dbl || k->M != phb::kUniformM || !k->env_uniform || a.pstride_s != 0 || a.S < 64 || a.alpha_out != nullptr) return kNotTaken;
+    // The constant bank is ONE per device: evaluations of different kernel objects / streams that use it are
+    // ordered through a per-device event.  Not inside a stream capture (an event recorded outside the capture
+    // cannot be waited on there): captured calls take the register-parameter kernel.
+    static cudaEvent_t bank_free[64] = {};
+    if (k->device >= 64) return kNotTaken;
+    {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess) cudaGetLastError();
+        if (cs != cudaStreamCaptureStatusNone) return kNotTaken;
+    }
+    constexpr int K = 8;
+    const void *func = reinterpret_cast<const void *>(&phb::psmc_uniform_forward_kernel<K>);
+    const size_t smem = phb::uniform_smem_bytes();
+    int occ = 0;
+    {
+        auto it = k->occupancy.find(func);
+        if (it == k->occupancy.end()) {
+            PHB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, func, 32, smem));
+            k->occupancy.emplace(func, occ);
+        } else {
+            occ = it->second;
+        }
+    }
+    if (occ < 1) return kNotTaken;
+    const int64_t resident = int64_t(occ) * k->num_sms;
+    const int64_t wpp = (a.S + 31) / 32;  // warp tasks per particle (upper bound with a sub-list)
+    int rc;
+    if ((rc = k->uniform_stage.reserve(size_t(a.B) * sizeof(phb::UniformParams))) != PHB_OK) return rc;
+    if (k->dry) return PHB_OK;
+    phb::UniformParams *stage = static_cast<phb::UniformParams *>(k->uniform_stage.ptr);
+    {
+        const int64_t n = a.B * 6 * phb::kUniformM;
+        phb::pack_uniform_params_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(static_cast<const float *>(a.params6), a.pstride_b, a.B, stage);
+        PHB_CUDA(cudaGetLastError());
+        k->launches += 1;
+    }
+    if (bank_free[k->device] == nullptr)
+        PHB_CUDA(cudaEventCreateWithFlags(&bank_free[k->device], cudaEventDisableTiming));
+    else
+        PHB_CUDA(cudaStreamWaitEvent(stream, bank_free[k->device], 0));
+    phb::UniformArgs ua{};
+    ua.k = a;
+    ua.k.err_flag = k->d_err;
+    for (int64_t first = 0; first < a.B; first += phb::kUniformSlots) {
+        const int64_t nb = std::min<int64_t>(phb::kUniformSlots, a.B - first);
+        PHB_CUDA(cudaMemcpyToSymbolAsync(phb::c_uniform_params, stage + first, size_t(nb) * sizeof(phb::UniformParams), 0,
+                                         cudaMemcpyDeviceToDevice, stream));
+        ua.first_b = first;
+        ua.n_b = nb;
+        ua.n_tasks = nb * wpp;
+        const int64_t grid = std::min<int64_t>(ua.n_tasks, resident);
+        void *kargs[] = {&ua};
+        PHB_CUDA(cudaLaunchKernel(func, dim3(unsigned(grid)), dim3(32), kargs, smem, stream));
+        k->launches += 1;
+    }
+    PHB_CUDA(cudaEventRecord(bank_free[k->device], stream));
+    snprintf(k->last_name, sizeof k->last_name, "psmc_uniform_forward_kernel<float,M=16,K=%d,fwd> (parameters in uniform registers)", K);
+    return PHB_OK;
+}
+
 // (4) The throughput kernel: persistent grid, checkpoints + recompute for the gradient.  `fixed` pins the
 // kernel variant (precision escalation), nullptr lets pick_variant choose.
 int launch_throughput_kernel(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream, const Variant *fixed) {
     const int64_t n_pairs = a.B * a.S;  // upper bound when a sub-list is given
+    if (!fixed && k->force_T == 0) {
+        const int rc = try_uniform_throughput(k, a, grad, stream);
+        if (rc != kNotTaken) return rc;
+    }
     const Variant *v = fixed ? fixed : pick_variant(k, grad, n_pairs);
     if (!v) return fail(PHB_E_INVALID, "no kernel variant for M=%d, threads_per_pair=%d", k->M, k->force_T);
     a.n_groups = chunk_major_groups(v, a.B, a.S);
@@ -830,6 +901,7 @@ static int new_kernel(int M, int64_t N, int64_t L, int double_precision, int dev
     if (const char *v = getenv("PHB_PARALLEL_IN_TIME")) k->env_pit = atoi(v);
     if (const char *v = getenv("PHB_PIT_SEGMENTS")) k->env_pit_segments = atoi(v);
     if (const char *v = getenv("PHB_SWEEP_T")) k->env_sweep_T = atoi(v);
+    if (const char *v = getenv("PHB_UNIFORM")) k->env_uniform = atoi(v);
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&k->d_data), size_t(N) * size_t(k->pitch));
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -838,7 +910,7 @@ static int new_kernel(int M, int64_t N, int64_t L, int double_precision, int dev
     }
     for (DeviceBuffer *b : {&k->params, &k->inds, &k->ll, &k->dlog, &k->ckpt, &k->gacc, &k->xall, &k->sall, &k->split, &k->term_params,
                             &k->term_ll, &k->term_dlog, &k->term_sums, &k->term_io, &k->transfer_rows, &k->transfer_log, &k->bnd_alpha,
-                            &k->bnd_beta, &k->seg_dlog})
+                            &k->bnd_beta, &k->seg_dlog, &k->uniform_stage})
         b->counter = &k->allocations;
     if ((e = cudaStreamCreateWithFlags(&k->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaMalloc(reinterpret_cast<void **>(&k->d_iteration), sizeof(unsigned long long))) != cudaSuccess ||
@@ -900,7 +972,7 @@ static int staged_upload(phb_kernel *k, const int8_t *src, int64_t n_rows, int64
         }
     }
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const int n_threads = int(std::min<unsigned>(8u, hw));
+    const int n_threads = int(std::min<unsigned>(16u, hw));  // (8 threads staged 25 GB/s on the 16-core box: half the PCIe rate)
     int64_t slab = 0;
     for (int64_t r0 = 0; r0 < n_rows && rc == PHB_OK; r0 += slab_rows, ++slab) {
         const int64_t nr = std::min(slab_rows, n_rows - r0);
@@ -1102,6 +1174,7 @@ void phb_destroy(phb_kernel *k) {
     k->bnd_alpha.release();
     k->bnd_beta.release();
     k->seg_dlog.release();
+    k->uniform_stage.release();
     if (k->d_rowflag) cudaFree(k->d_rowflag);
     if (k->d_data) cudaFree(k->d_data);
     if (k->d_err) cudaFree(k->d_err);

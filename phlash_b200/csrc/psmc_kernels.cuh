@@ -476,10 +476,12 @@ __device__ __forceinline__ void posterior_to_emission(const F (&beta)[MT], const
 // With w = emis(ob) .* beta:  beta'_i = sum_{j<i} b_j w_j + d_i w_i + u_i sum_{j>i} v_j w_j
 //   d ll/d b_j += (sum_{i>j} x_i) w_j      d ll/d d_j += x_j w_j
 //   d ll/d u_i += x_i sum_{j>i} v_j w_j    d ll/d v_j += (sum_{i<j} u_i x_i) w_j
-template <typename F, int MT, int T, int NT, bool ESM>
+// (TNT: threads per column of the emission table - NT for the per-thread tables, 1 for a table shared by
+// the warp, see psmc_uniform.cuh)
+template <typename F, int MT, int T, int NT, bool ESM, int TNT = NT>
 __device__ __forceinline__ void backward_site(F (&beta)[MT], const F (&x)[MT], int ob, int ob_prev,
                                               const Params<F, MT> &p, const PartnerCoef<F, MT, T, true> &pc,
-                                              const EmisTable<F, MT, NT> &et, int sub, Grad<F, MT, ESM> &g,
+                                              const EmisTable<F, MT, TNT> &et, int sub, Grad<F, MT, ESM> &g,
                                               EmisAcc<F, MT, NT> &ea) {
     F w[MT];
     et.get(ob, w);

@@ -345,6 +345,30 @@ def test_full_length_invariants(long_case):
     np.testing.assert_allclose(ll2, ll, rtol=1e-6)
 
 
+def test_forward_only_uniform_register_kernel():
+    """Forward-only evaluation of a large minibatch at M = 16 with shared parameter rows runs with the parameters
+    in uniform registers (psmc_uniform.cuh): more particles than constant-bank slots (two batches), a chunk count
+    that is not a multiple of 32, missing data; against the oracle and against the gradient kernel's ll."""
+    rng = np.random.default_rng(77)
+    data = random_data(rng, 70, 1801, het=0.08, miss=0.03)
+    pps, _, _ = orc.synth_particles(16, 131, seed=5)
+    inds = np.arange(70)[::-1].copy()
+    pa = np.broadcast_to(pps[:, None], (131, 70, 7, 16)).copy()
+    kern = make_kernel(16, data).gpu_kernels[0]
+    ll = kern.evaluate(pa, inds, False)
+    assert "psmc_uniform_forward_kernel" in kern.last_kernel_name, kern.last_kernel_name
+    ref_ll, _ = oracle_eval(data, inds, pa)
+    np.testing.assert_allclose(ll, ref_ll, rtol=LL_RTOL)
+    ll_g, _ = kern.evaluate(pa, inds, True)
+    np.testing.assert_allclose(ll, ll_g, rtol=1e-6)
+    # per-pair parameter rows cannot be warp-uniform: the register-parameter kernel scores them
+    pa2 = pa.copy()
+    pa2[3, 5, 1] *= 0.999
+    ll2 = kern.evaluate(pa2, inds, False)
+    assert "psmc_uniform" not in kern.last_kernel_name
+    np.testing.assert_allclose(np.delete(ll2.ravel(), 3 * 70 + 5), np.delete(ll.ravel(), 3 * 70 + 5), rtol=1e-6)
+
+
 def test_empty_batches(golden):
     """B = 0 or S = 0: nothing to do, correctly shaped empty results (no launch)."""
     data, _ = fixture_data(0)
