@@ -349,6 +349,41 @@ int check_handle(const phb_kernel *k) {
 // apply, try the next one".
 constexpr int kNotTaken = 1;
 
+// The constant bank is ONE per device: evaluations of different kernel objects / streams that use it are ordered
+// through a per-device event (not inside a stream capture, where an event recorded outside cannot be waited on: a
+// captured step must not run concurrently with another constant-bank evaluation on the same device).
+int constant_bank_acquire(phb_kernel *k, cudaStream_t stream, bool release) {
+    static cudaEvent_t bank_free[64] = {};
+    if (k->device >= 64) return PHB_OK;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess) cudaGetLastError();
+    if (cs != cudaStreamCaptureStatusNone) return PHB_OK;
+    if (release) {
+        if (bank_free[k->device] == nullptr) PHB_CUDA(cudaEventCreateWithFlags(&bank_free[k->device], cudaEventDisableTiming));
+        PHB_CUDA(cudaEventRecord(bank_free[k->device], stream));
+    } else if (bank_free[k->device] != nullptr) {
+        PHB_CUDA(cudaStreamWaitEvent(stream, bank_free[k->device], 0));
+    }
+    return PHB_OK;
+}
+
+// Segment transfer operators (transfer_rows_kernel) of the segments [ta.seg_first, ta.seg_first + ta.n_seg_local)
+int launch_transfer_rows(phb_kernel *k, const TransferVariant *tv, const phb::TransferArgs &ta, cudaStream_t stream) {
+    const phb::KernelArgs &a = ta.k;
+    const int M = k->M;
+    if (k->occupancy.find(tv->rows_func) == k->occupancy.end()) {
+        PHB_CUDA(cudaFuncSetAttribute(tv->rows_func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tv->smem)));
+        k->occupancy.emplace(tv->rows_func, 1);
+    }
+    if (k->dry) return PHB_OK;
+    const int64_t n_virtual = a.B * a.S * ta.n_seg_local * M;
+    phb::TransferArgs copy = ta;
+    void *kargs[] = {&copy};
+    PHB_CUDA(cudaLaunchKernel(tv->rows_func, dim3(unsigned((n_virtual + 127) / 128)), dim3(128), kargs, tv->smem, stream));
+    k->launches += 1;
+    return PHB_OK;
+}
+
 // (1) Gradient of FEW pairs (the reference's default minibatch for one genome is a single chunk: 500
 // pairs): parallel in time.  Segment transfer operators give the forward / adjoint vectors at the
 // segment boundaries (chain_boundaries_kernel), after which the segments are independent short
@@ -397,11 +432,6 @@ int try_parallel_in_time_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaS
     if ((rc = k->seg_dlog.reserve(size_t(n_pairs) * n_seg * 7 * M * sizeof(float))) != PHB_OK) return rc;
     if ((rc = k->ckpt.reserve(size_t(grid) * (gv->NT / 32) * size_t(gv->ckpt_bytes_per_warp(seg_len)))) != PHB_OK) return rc;
     if ((rc = k->gacc.reserve(size_t(grid) * gv->NT * 6 * (gv->M / gv->T) * sizeof(double))) != PHB_OK) return rc;
-    if (k->occupancy.find(tv->rows_func) == k->occupancy.end()) {
-        PHB_CUDA(cudaFuncSetAttribute(tv->rows_func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tv->smem)));
-        k->occupancy.emplace(tv->rows_func, 1);
-    }
-    if (k->dry) return PHB_OK;
     phb::TransferArgs ta{};
     ta.k = a;
     ta.k.err_flag = k->d_err;
@@ -411,10 +441,10 @@ int try_parallel_in_time_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaS
     ta.row_log2 = static_cast<double *>(k->transfer_log.ptr);
     ta.segs_per_slot = n_seg;  // one process: a single slot with all segments
     ta.n_seg_local = n_seg;
+    if ((rc = launch_transfer_rows(k, tv, ta, stream)) != PHB_OK) return rc;  // (sizes its own staging in a dry run)
+    if (k->dry) return PHB_OK;
     void *bnd_a = k->bnd_alpha.ptr, *bnd_b = k->bnd_beta.ptr;
     {
-        void *kargs[] = {&ta};
-        PHB_CUDA(cudaLaunchKernel(tv->rows_func, dim3(unsigned((n_rows_virtual + 127) / 128)), dim3(128), kargs, tv->smem, stream));
         void *bargs[] = {&ta, &bnd_a, &bnd_b};
         PHB_CUDA(cudaLaunchKernel(tv->boundaries_func, dim3(unsigned((n_pairs * M + 127) / 128)), dim3(128), bargs, 0, stream));
     }
@@ -437,7 +467,7 @@ int try_parallel_in_time_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaS
     phb::sum_segments_kernel<float><<<unsigned((n_out + 255) / 256), 256, 0, stream>>>(
         static_cast<const float *>(k->seg_dlog.ptr), n_pairs, n_seg, M, static_cast<float *>(a.dlog), a.out_mode, a);
     PHB_CUDA(cudaGetLastError());
-    k->launches += 4;
+    k->launches += 3;
     snprintf(k->last_name, sizeof k->last_name, "transfer_rows_kernel<float,M=%d> + psmc_loglik_kernel<SEG,MT=%d,T=%d> x %lld segments", M,
              gv->M / gv->T, gv->T, (long long)n_seg);
     return PHB_OK;
@@ -599,15 +629,11 @@ int try_parallel_in_time_forward(phb_kernel *k, const phb::KernelArgs &a, cudaSt
             ta.row_log2 = static_cast<double *>(k->transfer_log.ptr);
             ta.segs_per_slot = n_seg;
             ta.n_seg_local = n_seg;
-            if (k->occupancy.find(tv->rows_func) == k->occupancy.end()) {
-                PHB_CUDA(cudaFuncSetAttribute(tv->rows_func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tv->smem)));
-                k->occupancy.emplace(tv->rows_func, 1);
-            }
+            if ((rc = launch_transfer_rows(k, tv, ta, stream)) != PHB_OK) return rc;
             if (k->dry) return PHB_OK;
             void *kargs[] = {&ta};
-            PHB_CUDA(cudaLaunchKernel(tv->rows_func, dim3(unsigned((n_virtual + 127) / 128)), dim3(128), kargs, tv->smem, stream));
             PHB_CUDA(cudaLaunchKernel(tv->chain_func, dim3(unsigned((n_pairs + 63) / 64)), dim3(64), kargs, 0, stream));
-            k->launches += 2;
+            k->launches += 1;
             snprintf(k->last_name, sizeof k->last_name, "transfer_rows_kernel<float,M=%d> x %lld segments + chain_transfer_kernel",
                      tv->M, (long long)n_seg);
             return PHB_OK;
@@ -667,16 +693,13 @@ bool shard_plan(phb_kernel *k, int64_t B, int64_t S, int64_t L, int world, Shard
 }
 
 // (4a) FORWARD-ONLY evaluation of large minibatches at M = 16 whose parameter rows are shared by the chunks of a
-// particle: the same recursion with the parameters in uniform registers (psmc_uniform.cuh; +28 % measured),
-// scored in batches of kUniformSlots particles (the constant bank holds that many).
+// particle: the same recursion in the one-particle-per-warp layout of psmc_uniform.cuh (+21 % measured), scored
+// in batches of kUniformSlots particles (the constant bank holds that many).
 int try_uniform_throughput(phb_kernel *k, const phb::KernelArgs &a, bool grad, cudaStream_t stream) {
     if (grad || k->dbl || k->M != phb::kUniformM || !k->env_uniform || a.pstride_s != 0 || a.S < 64 || a.alpha_out != nullptr) return kNotTaken;
-    // The constant bank is ONE per device: evaluations of different kernel objects / streams that use it are
-    // ordered through a per-device event.  Not inside a stream capture (an event recorded outside the capture
-    // cannot be waited on there): captured calls take the register-parameter kernel.
-    static cudaEvent_t bank_free[64] = {};
-    if (k->device >= 64) return kNotTaken;
     {
+        // (inside a stream capture the register-parameter kernel is used: the launches below are several, and a
+        // captured forward-only evaluation of a large minibatch is not a case worth the constant-bank ordering)
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess) cudaGetLastError();
         if (cs != cudaStreamCaptureStatusNone) return kNotTaken;
@@ -702,15 +725,12 @@ int try_uniform_throughput(phb_kernel *k, const phb::KernelArgs &a, bool grad, c
     if (k->dry) return PHB_OK;
     phb::UniformParams *stage = static_cast<phb::UniformParams *>(k->uniform_stage.ptr);
     {
-        const int64_t n = a.B * 6 * phb::kUniformM;
+        const int64_t n = a.B * 2 * phb::kUniformM;
         phb::pack_uniform_params_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(static_cast<const float *>(a.params6), a.pstride_b, a.B, stage);
         PHB_CUDA(cudaGetLastError());
         k->launches += 1;
     }
-    if (bank_free[k->device] == nullptr)
-        PHB_CUDA(cudaEventCreateWithFlags(&bank_free[k->device], cudaEventDisableTiming));
-    else
-        PHB_CUDA(cudaStreamWaitEvent(stream, bank_free[k->device], 0));
+    if ((rc = constant_bank_acquire(k, stream, false)) != PHB_OK) return rc;
     phb::UniformArgs ua{};
     ua.k = a;
     ua.k.err_flag = k->d_err;
@@ -726,8 +746,8 @@ int try_uniform_throughput(phb_kernel *k, const phb::KernelArgs &a, bool grad, c
         PHB_CUDA(cudaLaunchKernel(func, dim3(unsigned(grid)), dim3(32), kargs, smem, stream));
         k->launches += 1;
     }
-    PHB_CUDA(cudaEventRecord(bank_free[k->device], stream));
-    snprintf(k->last_name, sizeof k->last_name, "psmc_uniform_forward_kernel<float,M=16,K=%d,fwd> (parameters in uniform registers)", K);
+    if ((rc = constant_bank_acquire(k, stream, true)) != PHB_OK) return rc;
+    snprintf(k->last_name, sizeof k->last_name, "psmc_uniform_forward_kernel<float,M=16,K=%d,fwd> (one particle per warp)", K);
     return PHB_OK;
 }
 
@@ -1676,11 +1696,7 @@ int phb_hmm_term_sharded_begin(phb_kernel *k, const double *x, int64_t B, const 
     if ((rc = phb_params_from_particles(k, x, B, epoch_widths, n_epochs, theta, k->term_params.ptr, stream)) != PHB_OK) return rc;
     const int64_t seg_lo = std::min<int64_t>(p.n_seg, int64_t(rank) * p.per_rank);
     const int64_t seg_hi = std::min<int64_t>(p.n_seg, seg_lo + p.per_rank);
-    if (k->occupancy.find(tv->rows_func) == k->occupancy.end()) {
-        PHB_CUDA(cudaFuncSetAttribute(tv->rows_func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tv->smem)));
-        k->occupancy.emplace(tv->rows_func, 1);
-    }
-    if (seg_hi <= seg_lo || k->dry) return PHB_OK;
+    if (seg_hi <= seg_lo) return PHB_OK;
     phb::TransferArgs ta{};
     phb::KernelArgs &a = ta.k;
     a.data = k->d_data;
@@ -1705,11 +1721,7 @@ int phb_hmm_term_sharded_begin(phb_kernel *k, const double *x, int64_t B, const 
     ta.slot_stride_log = int64_t(p.slot_bytes / sizeof(double));
     ta.seg_first = seg_lo;
     ta.n_seg_local = seg_hi - seg_lo;
-    const int64_t n_virtual = B * S * ta.n_seg_local * M;
-    void *kargs[] = {&ta};
-    PHB_CUDA(cudaLaunchKernel(tv->rows_func, dim3(unsigned((n_virtual + 127) / 128)), dim3(128), kargs, tv->smem, static_cast<cudaStream_t>(stream)));
-    k->launches += 1;
-    return PHB_OK;
+    return launch_transfer_rows(k, tv, ta, static_cast<cudaStream_t>(stream));
 }
 
 int phb_hmm_term_sharded_end(phb_kernel *k, const int64_t *inds, int64_t B, int64_t S, int64_t overlap, int rank, int world,

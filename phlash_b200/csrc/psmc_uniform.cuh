@@ -1,24 +1,31 @@
-// Forward-only throughput kernel with the parameters in UNIFORM REGISTERS (M = 16, float, large minibatches whose
-// six parameter rows are shared by the chunks of a particle - how the reference calls the kernel, model.py:55).
+// Forward-only throughput kernel for large minibatches at M = 16 (float) whose parameter rows are shared by the
+// chunks of a particle - how the reference calls the kernel, model.py:55.
 //
-// Why: psmc_loglik_kernel keeps b, d, u, v (64 values) in vector registers, and almost every FMA of the site
-// step reads three distinct vector registers.  That operand pattern is what bounds the kernel: a loop of the
-// same shape issues 0.72 FMA per scheduler and clock whatever the occupancy, 0.79 when the coefficients come
-// from the constant bank / uniform registers (profiles/r02_microbench3_b200.json).  Here a WARP scores 32
-// chunks of ONE particle, the particle's rows live in __constant__ memory, and because the slot index is
-// provably warp-uniform (it derives from blockIdx and the loop counter: a CTA is one warp) ptxas loads them
-// once per task with LDCU into uniform registers and uses them as the third operand of the FMAs
-// (FFMA R, R, UR, R).  64 vector registers and the per-thread emission table are gone; the emission rows sit in
-// one 192-byte table per warp.
+// Layout: a single-warp CTA scores 32 chunks of ONE particle (psmc_loglik_kernel scores consecutive particles of
+// one chunk).  With one particle per warp
+//   * the emission rows sit in ONE 192-byte table per warp instead of 192 bytes per thread,
+//   * rows b and v come from __constant__ memory through a warp-uniform slot index (psmc_loglik_kernel reads all
+//     rows from global memory into per-lane registers),
+//   * the kernel needs 149 registers and 192 bytes of shared memory per warp: 13 warps per SM.
+// The recursion is psmc_loglik_kernel's forward pass (same site function, same rescaling): the log-likelihoods
+// are bit-identical.  Measured on B200 (profiles/r02_probe_uniform_kernel.log, 124 particles x 576 chunks x
+// 50 000 bins): 17.2 ms against 20.7 ms (+21 %).
 //
-// The algorithm is exactly psmc_loglik_kernel's forward pass (same site function, same rescaling: the results are
-// bit-identical); see psmc_kernels.cuh.  __constant__ memory holds kUniformSlots particles, so a minibatch is
-// scored in batches of particles (the host copies each batch's rows device-to-device into the bank between
-// launches).  Measured on B200 (profiles/r02_probe_uniform_kernel.log, 124 particles x 576 chunks x 50 000
-// bins): forward only 16.3 ms against 20.8 ms (+28 %).  The GRADIENT build of the same idea was measured too and
-// is NOT used: with the adjoint's working set the kernel stays at 2 warps per scheduler, the dispatch stalls
-// halve (0.62 -> 0.29 per issue) but the warps then wait on their own dependency chains instead (short
-// scoreboard 0.10 -> 0.51, fixed-latency waits 0.21 -> 0.51): 77.2 ms against 71.6 ms.
+// What was tried around it (round 2) and is NOT used:
+//   * all six rows in the constant bank as FMA operands of the uniform datapath (FFMA R, R, UR, R - ptxas does
+//     this by itself once the slot index is provably uniform): a site-like loop issues 0.79 instead of 0.72 FMA
+//     per scheduler and clock that way (profiles/r02_microbench3_b200.json), and the forward-only build gained
+//     another 5 % (16.3 ms).  But ptxas keeps at most ~32 of the 64 transition values resident in uniform
+//     registers (with all 64 it re-loads them through LDCU at every site), whether it uses uniform or vector
+//     registers for them at all depends on the register pressure of the build, and 384 bytes per particle limit a
+//     launch to 128 particles, which serialises launches that do not fill the GPU on their own;
+//   * the GRADIENT build of the same layout: the dispatch stalls halve (0.62 -> 0.29 per issue) but at 2 warps per
+//     scheduler the warps then wait on their own dependency chains (short scoreboard 0.10 -> 0.51, fixed-latency
+//     waits 0.21 -> 0.51): 77.2 ms against 71.6 ms;
+//   * the segment transfer operators in this layout: no gain at S = 1 (3.21 against 3.20 ms) and a second,
+//     nearly empty round of single-warp CTAs for the ELPD shape (119 against 88 ms).
+// The constant bank holds kUniformSlots particles; larger batches are scored in several launches (the host copies
+// each batch's rows device-to-device into the bank in between).
 #pragma once
 
 #include "psmc_kernels.cuh"
@@ -26,9 +33,11 @@
 namespace phb {
 
 constexpr int kUniformM = 16;
-constexpr int kUniformSlots = 128;  // 128 x 384 B = 48 KB of the 64 KB constant bank
+// Rows b and v, 128 B per particle, so that the reference's 500 particles fit in ONE launch (504 x 128 B = 63 KB
+// of the 64 KB bank).
+constexpr int kUniformSlots = 504;
 struct UniformParams {
-    float b[kUniformM], d[kUniformM], u[kUniformM], v[kUniformM], e0[kUniformM], e1[kUniformM];
+    float b[kUniformM], v[kUniformM];
 };
 __constant__ UniformParams c_uniform_params[kUniformSlots];
 
@@ -39,12 +48,12 @@ struct UniformArgs {
     int64_t n_tasks;     // n_b * ceil(chunks / 32) upper bound (with a sub-list the kernel recomputes it)
 };
 
-// staging of the constant bank: out[b] = rows b, d, u, v, emis0, emis1 of particle b, contiguous
+// staging of the constant bank: out[b] = rows b and v of particle b, contiguous
 __global__ void pack_uniform_params_kernel(const float *__restrict__ params6, int64_t pstride_b, int64_t B, UniformParams *__restrict__ out) {
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= B * 6 * kUniformM) return;
-    const int64_t b = i / (6 * kUniformM), r = i % (6 * kUniformM);
-    reinterpret_cast<float *>(out + b)[r] = params6[b * pstride_b + r];
+    if (i >= B * 2 * kUniformM) return;
+    const int64_t b = i / (2 * kUniformM), r = i % (2 * kUniformM);
+    reinterpret_cast<float *>(out + b)[r] = params6[b * pstride_b + (r < kUniformM ? r : 2 * kUniformM + r)];  // row 0 (b), row 3 (v)
 }
 
 constexpr size_t uniform_smem_bytes() { return 3 * kUniformM * sizeof(float); }  // the warp's emission table [3][16]
@@ -68,21 +77,20 @@ template <int K> __global__ void __maxnreg__(168) psmc_uniform_forward_kernel(co
     const int64_t n_seg = (L + K - 1) / K;
 
     for (int64_t task = blockIdx.x; task < n_tasks; task += gridDim.x) {
-        const int slot = int(task / wpp);                 // warp-uniform by construction (blockIdx, loop counter)
+        const int slot = int(task / wpp);  // warp-uniform by construction (blockIdx, loop counter)
         const int64_t blk = task - int64_t(slot) * wpp;
         const UniformParams &up = c_uniform_params[slot];
-        // rows b and v stay in the constant bank / uniform registers (FMA operands); d and u are moved into
-        // vector registers (opaque moves: ptxas would otherwise re-load all 64 values through LDCU at every
-        // site instead of keeping any of them resident - there are not enough uniform registers for 64)
+        const int64_t pb = ua.first_b + slot;
+        // rows b and v from the constant bank, d and u (and the emission rows below) from global memory
+        const float *par = static_cast<const float *>(a.params6) + pb * a.pstride_b;
         Params<F, MT> p;
 #pragma unroll
         for (int k = 0; k < MT; ++k) {
             p.b[k] = up.b[k];
             p.v[k] = up.v[k];
-            asm volatile("mov.f32 %0, %1;" : "=f"(p.d[k]) : "f"(up.d[k]));
-            asm volatile("mov.f32 %0, %1;" : "=f"(p.u[k]) : "f"(up.u[k]));
+            p.d[k] = par[1 * MT + k];
+            p.u[k] = par[2 * MT + k];
         }
-        const int64_t pb = ua.first_b + slot;
         const int64_t j_raw = blk * 32 + lane;
         const bool writer = j_raw < s_eff;
         const int64_t j = writer ? j_raw : s_eff - 1;  // idle lanes shadow the last chunk
@@ -94,7 +102,7 @@ template <int K> __global__ void __maxnreg__(168) psmc_uniform_forward_kernel(co
             const int r = lane / QN, q = lane % QN;
             float tmp[W];
 #pragma unroll
-            for (int i = 0; i < W; ++i) tmp[i] = r == 0 ? up.e0[q * W + i] : (r == 1 ? up.e1[q * W + i] : 1.f);
+            for (int i = 0; i < W; ++i) tmp[i] = r < 2 ? par[(4 + r) * MT + q * W + i] : 1.f;
             sts_word(smem0 + lane * 16, tmp);
         }
         __syncwarp();
