@@ -262,12 +262,14 @@ int phb_hmm_term_finish_device(phb_kernel *k, const double *x, int64_t B, const 
  * segments that are independent once the boundary vectors are known, so the SEGMENTS are sharded instead:
  *   _plan   n_segments / slot_bytes for this call shape; n_segments == 0 means "does not apply" (double
  *           precision, M > 16, or too many pairs for the operators to pay) - shard the chunks instead;
- *   _begin  particles -> parameters, then this process's slice of the segment transfer operators, written
- *           into ITS slot (rank * slot_bytes) of `gather` (world * slot_bytes bytes of device memory);
+ *   _begin  particles -> parameters, then this process's slice of the segment transfer operators (kept in the
+ *           object) and their PRODUCT, one operator per pair, written into ITS slot (rank * slot_bytes) of
+ *           `gather` (world * slot_bytes bytes of device memory; 1 KB per pair and process at M = 16);
  *   -- the caller all-gathers `gather` in place (one NCCL call) --
- *   _end    chains all operators (float64) to the boundary vectors, runs the gradient passes over this
- *           process's segments and leaves its PARTIAL per-particle sums [B, 1 + 7 M] in `sums`; process 0 adds
- *           the log-likelihood, the pairs on marked rows (precision escalation) and subtracts the warm-up term;
+ *   _end    chains the processes' operators (float64) to the vectors entering and leaving this process's slice,
+ *           its own segment operators to the boundary vectors inside the slice, runs the gradient passes over
+ *           those segments and leaves its PARTIAL per-particle sums [B, 1 + 7 M] in `sums`; process 0 adds the
+ *           log-likelihood, the pairs on marked rows (precision escalation) and subtracts the warm-up term;
  *   -- the caller all-reduces `sums` and calls phb_hmm_term_finish_device, as in the chunk-sharded form.
  * The result equals phb_hmm_term_sums_device on one process up to floating-point summation order. */
 int phb_hmm_term_sharded_plan(phb_kernel *k, int64_t B, int64_t S, int64_t overlap, int world, int64_t *n_segments,

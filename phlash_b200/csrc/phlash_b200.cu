@@ -279,13 +279,15 @@ const SweepVariant *sweep_variant(int M, int want_T) {
 // Parallel-in-time forward evaluation (few, long pairs; see transfer_rows_kernel): float, M <= 16.
 struct TransferVariant {
     int M;
-    const void *rows_func, *chain_func, *boundaries_func;
+    const void *rows_func, *chain_func, *boundaries_func, *product_func, *sharded_boundaries_func;
     size_t smem;
 };
 template <int M> TransferVariant make_transfer() {
     return TransferVariant{M, reinterpret_cast<const void *>(&phb::transfer_rows_kernel<float, M, 128>),
                            reinterpret_cast<const void *>(&phb::chain_transfer_kernel<float, M>),
                            reinterpret_cast<const void *>(&phb::chain_boundaries_kernel<float, M>),
+                           reinterpret_cast<const void *>(&phb::chain_product_kernel<M>),
+                           reinterpret_cast<const void *>(&phb::chain_boundaries_sharded_kernel<float, M>),
                            phb::smem_bytes<float, M, 8, 128, false>()};
 }
 const TransferVariant *transfer_variant(int M) {
@@ -647,9 +649,10 @@ int try_parallel_in_time_forward(phb_kernel *k, const phb::KernelArgs &a, cudaSt
 // With S < world chunks there is nothing to shard on the chunk axis (the reference splits S <= 5 indices over
 // its devices and leaves the others idle, gpu.py:398-400).  The segments of the parallel-in-time gradient ARE
 // independent once the boundary vectors exist: every process computes the transfer operators of its own
-// slice of the segments, one all-gather makes all operators visible everywhere, every process chains them
-// (cheap, float64) and then runs the gradient passes over its own slice only; the partial per-particle sums
-// join the all-reduce that the chunk-sharded path uses as well.
+// slice of the segments and multiplies them into ONE operator per pair (float64), a small all-gather makes
+// those `world` operators per pair visible everywhere, every process chains them to the vectors entering and
+// leaving its slice, chains its own operators to the boundary vectors inside the slice and runs the gradient
+// passes over the slice; the partial per-particle sums join the all-reduce that the chunk-sharded path uses.
 struct ShardPlan {
     int64_t n_seg = 0, seg_len = 0, seg_ctas = 0, per_rank = 0;
     size_t rows_bytes = 0, slot_bytes = 0;  // per process
@@ -687,8 +690,9 @@ bool shard_plan(phb_kernel *k, int64_t B, int64_t S, int64_t L, int world, Shard
     p.per_rank = (n_seg + world - 1) / world;  // the last process may hold fewer
     p.n_seg = n_seg;
     if (n_seg < 2 * world && n_seg < 3) return false;
-    p.rows_bytes = size_t(p.per_rank) * size_t(n_pairs) * M * M * sizeof(float);
-    p.slot_bytes = p.rows_bytes + size_t(p.per_rank) * size_t(n_pairs) * M * sizeof(double);
+    // what a process contributes to the all-gather: ONE operator per pair, the product of its segment operators
+    p.rows_bytes = size_t(n_pairs) * M * M * sizeof(float);
+    p.slot_bytes = p.rows_bytes + size_t(n_pairs) * M * sizeof(double);
     return true;
 }
 
@@ -1696,7 +1700,9 @@ int phb_hmm_term_sharded_begin(phb_kernel *k, const double *x, int64_t B, const 
     if ((rc = phb_params_from_particles(k, x, B, epoch_widths, n_epochs, theta, k->term_params.ptr, stream)) != PHB_OK) return rc;
     const int64_t seg_lo = std::min<int64_t>(p.n_seg, int64_t(rank) * p.per_rank);
     const int64_t seg_hi = std::min<int64_t>(p.n_seg, seg_lo + p.per_rank);
-    if (seg_hi <= seg_lo) return PHB_OK;
+    const int64_t n_local = std::max<int64_t>(seg_hi - seg_lo, 0);
+    if ((rc = k->transfer_rows.reserve(size_t(std::max<int64_t>(n_local, 1)) * B * S * M * M * sizeof(float))) != PHB_OK) return rc;
+    if ((rc = k->transfer_log.reserve(size_t(std::max<int64_t>(n_local, 1)) * B * S * M * sizeof(double))) != PHB_OK) return rc;
     phb::TransferArgs ta{};
     phb::KernelArgs &a = ta.k;
     a.data = k->d_data;
@@ -1713,15 +1719,23 @@ int phb_hmm_term_sharded_begin(phb_kernel *k, const double *x, int64_t B, const 
     a.err_flag = k->d_err;
     ta.n_seg = p.n_seg;
     ta.seg_len = p.seg_len;
-    char *base = static_cast<char *>(gather);
-    ta.rows = reinterpret_cast<float *>(base);
-    ta.row_log2 = reinterpret_cast<double *>(base + p.rows_bytes);
+    // this process's operators stay local: segment g lives at [g - seg_lo] (slots of per_rank segments that all
+    // alias the one local buffer: g / per_rank == rank for every g of the slice)
+    ta.rows = static_cast<float *>(k->transfer_rows.ptr);
+    ta.row_log2 = static_cast<double *>(k->transfer_log.ptr);
     ta.segs_per_slot = p.per_rank;
-    ta.slot_stride_rows = int64_t(p.slot_bytes / sizeof(float));
-    ta.slot_stride_log = int64_t(p.slot_bytes / sizeof(double));
     ta.seg_first = seg_lo;
-    ta.n_seg_local = seg_hi - seg_lo;
-    return launch_transfer_rows(k, tv, ta, static_cast<cudaStream_t>(stream));
+    ta.n_seg_local = n_local;
+    if (n_local > 0 && (rc = launch_transfer_rows(k, tv, ta, static_cast<cudaStream_t>(stream))) != PHB_OK) return rc;
+    if (k->dry) return PHB_OK;
+    // ... and their product goes into this process's slot of the all-gather buffer
+    char *slot = static_cast<char *>(gather) + size_t(rank) * p.slot_bytes;
+    float *out_rows = reinterpret_cast<float *>(slot);
+    double *out_log2 = reinterpret_cast<double *>(slot + p.rows_bytes);
+    void *pargs[] = {&ta, &out_rows, &out_log2};
+    PHB_CUDA(cudaLaunchKernel(tv->product_func, dim3(unsigned((B * S * M + 127) / 128)), dim3(128), pargs, 0, static_cast<cudaStream_t>(stream)));
+    k->launches += 1;
+    return PHB_OK;
 }
 
 int phb_hmm_term_sharded_end(phb_kernel *k, const int64_t *inds, int64_t B, int64_t S, int64_t overlap, int rank, int world,
@@ -1777,15 +1791,19 @@ int phb_hmm_term_sharded_end(phb_kernel *k, const int64_t *inds, int64_t B, int6
         a.skip_flag = marked ? k->d_rowflag : nullptr;
         ta.n_seg = p.n_seg;
         ta.seg_len = p.seg_len;
-        const char *base = static_cast<const char *>(gather);
-        ta.rows = reinterpret_cast<float *>(const_cast<char *>(base));
-        ta.row_log2 = reinterpret_cast<double *>(const_cast<char *>(base) + p.rows_bytes);
+        ta.rows = static_cast<float *>(k->transfer_rows.ptr);   // this process's own operators (phb_hmm_term_sharded_begin)
+        ta.row_log2 = static_cast<double *>(k->transfer_log.ptr);
         ta.segs_per_slot = p.per_rank;
-        ta.slot_stride_rows = int64_t(p.slot_bytes / sizeof(float));
-        ta.slot_stride_log = int64_t(p.slot_bytes / sizeof(double));
+        ta.seg_first = seg_lo;
+        ta.n_seg_local = n_local;
+        const char *base = static_cast<const char *>(gather);
+        const float *rank_rows = reinterpret_cast<const float *>(base);
+        const double *rank_log2 = reinterpret_cast<const double *>(base + p.rows_bytes);
+        int64_t stride_rows = int64_t(p.slot_bytes / sizeof(float)), stride_log = int64_t(p.slot_bytes / sizeof(double));
+        int rank_arg = rank, world_arg = world;
         void *bnd_a = k->bnd_alpha.ptr, *bnd_b = k->bnd_beta.ptr;
-        void *bargs[] = {&ta, &bnd_a, &bnd_b};
-        PHB_CUDA(cudaLaunchKernel(tv->boundaries_func, dim3(unsigned((n_pairs * M + 127) / 128)), dim3(128), bargs, 0, st));
+        void *bargs[] = {&ta, &rank_rows, &rank_log2, &stride_rows, &stride_log, &rank_arg, &world_arg, &bnd_a, &bnd_b};
+        PHB_CUDA(cudaLaunchKernel(tv->sharded_boundaries_func, dim3(unsigned((n_pairs * M + 127) / 128)), dim3(128), bargs, 0, st));
         k->launches += 1;
         if (n_local > 0) {
             phb::KernelArgs sa = a;

@@ -1379,6 +1379,148 @@ template <typename F, int M> __global__ void chain_boundaries_kernel(const Trans
     }
 }
 
+// ---- time-axis sharding over processes: every process multiplies ITS segment operators into one operator per
+// pair (chain_product_kernel), only those (world operators per pair instead of G) are all-gathered, and
+// chain_boundaries_sharded_kernel chains them to the vectors entering / leaving the process's slice, then the
+// process's own segment operators to the boundary vectors inside it.
+//
+// chain_product_kernel: M lanes per pair; lane k owns ROW k of the running product, a distribution over the M
+// states with its own log2 scale (the same representation as a segment operator: rows rescaled to sum 1 +
+// row_log2), and multiplies it into the next operator exactly like the forward chain step does.
+template <int M> __global__ void chain_product_kernel(const TransferArgs ta, float *__restrict__ out_rows, double *__restrict__ out_log2) {
+    const KernelArgs &a = ta.k;
+    const int64_t n_pairs = a.B * a.S;
+    const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= n_pairs * M) return;
+    const int64_t pair = t / M;
+    const int k = int(t % M);
+    double v[M];
+    double lg_acc = 0.0;
+    if (ta.n_seg_local > 0) {
+        const int64_t g = ta.seg_first;
+        const float *rows = op_rows(ta, pair, g, n_pairs, M) + k * M;
+#pragma unroll
+        for (int j = 0; j < M; ++j) v[j] = double(rows[j]);
+        lg_acc = op_log2(ta, pair, g, n_pairs, M)[k];
+    } else {  // a process without segments contributes the identity
+#pragma unroll
+        for (int j = 0; j < M; ++j) v[j] = j == k ? 1.0 : 0.0;
+    }
+    for (int64_t g = ta.seg_first + 1; g < ta.seg_first + ta.n_seg_local; ++g) {
+        const float *rows = op_rows(ta, pair, g, n_pairs, M);
+        const double *lg = op_log2(ta, pair, g, n_pairs, M);
+        double top = -1e300;
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+            if (v[i] > 0.0 && lg[i] > top) top = lg[i];
+        double next[M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) next[j] = 0.0;
+#pragma unroll 4
+        for (int i = 0; i < M; ++i) {
+            const double w = v[i] > 0.0 ? v[i] * exp2(lg[i] - top) : 0.0;
+#pragma unroll
+            for (int j = 0; j < M; ++j) next[j] += w * double(rows[i * M + j]);
+        }
+        double tot = 0.0;
+#pragma unroll
+        for (int j = 0; j < M; ++j) tot += next[j];
+        lg_acc += top + log2(tot);
+#pragma unroll
+        for (int j = 0; j < M; ++j) v[j] = next[j] / tot;
+    }
+#pragma unroll
+    for (int j = 0; j < M; ++j) out_rows[(pair * M + k) * M + j] = float(v[j]);
+    out_log2[pair * M + k] = lg_acc;
+}
+
+// One forward chain step for the M lanes of a pair (lane k owns component k):  v <- normalised (v T),  ll2 += log2 of
+// what was divided out.  rows / lg: the operator's [M][M] rows and [M] log2 row scales.
+template <int M> __device__ __forceinline__ void chain_forward_step(double &v, double &ll2, const float *__restrict__ rows,
+                                                                    const double *__restrict__ lg_rows, int k) {
+    const double lg = lg_rows[k];
+    const double top = group_max<M>(v > 0.0 ? lg : -1e300);
+    const double w = v > 0.0 ? v * exp2(lg - top) : 0.0;
+    double next = 0.0;
+#pragma unroll
+    for (int i = 0; i < M; ++i) next += __shfl_sync(0xffffffffu, w, i, M) * double(rows[i * M + k]);
+    const double tot = group_sum<M>(next);
+    ll2 += top + log2(tot);
+    v = next / tot;
+}
+// One adjoint chain step:  v <- (T v) / max  (lane k owns row k of T)
+template <int M> __device__ __forceinline__ void chain_backward_step(double &v, const float *__restrict__ rows,
+                                                                     const double *__restrict__ lg_rows, int k) {
+    const double lg = lg_rows[k];
+    const double top = group_max<M>(lg);
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < M; ++j) acc += double(rows[k * M + j]) * __shfl_sync(0xffffffffu, v, j, M);
+    const double next = acc * exp2(lg - top);
+    v = next / group_max<M>(next);
+}
+
+// rank_rows / rank_log2: the all-gathered operators of the processes, process r at + r * rank_stride_* ([pairs][M][M]
+// floats, [pairs][M] doubles); ta: THIS process's segment operators (single slot, segment-major).  Writes the
+// boundary vectors of the segments [ta.seg_first, ta.seg_first + ta.n_seg_local] and - on every process - ll.
+// Launch with 128 threads per CTA.
+template <typename F, int M>
+__global__ void chain_boundaries_sharded_kernel(const TransferArgs ta, const float *__restrict__ rank_rows, const double *__restrict__ rank_log2,
+                                                int64_t rank_stride_rows, int64_t rank_stride_log, int rank, int world,
+                                                F *__restrict__ bnd_alpha, F *__restrict__ bnd_beta) {
+    const KernelArgs &a = ta.k;
+    const int64_t n_pairs = a.B * a.S;
+    const int64_t pair_raw = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) / M;
+    const bool writer = pair_raw < n_pairs;
+    const int64_t pair = writer ? pair_raw : n_pairs - 1;
+    const int k = threadIdx.x % M;
+    const int64_t pb = pair / a.S, ps = pair % a.S;
+    const int64_t G = ta.n_seg;
+    const F *pi_p = static_cast<const F *>(a.pi) + pb * a.pistride_b + ps * a.pistride_s;
+    F *al = bnd_alpha + pair * (G + 1) * M;
+    F *be = bnd_beta + pair * (G + 1) * M;
+    const int64_t g_lo = ta.seg_first, g_hi = ta.seg_first + ta.n_seg_local;
+    // forward over the processes: the vector entering this process's slice, and the total log-likelihood
+    double v = double(pi_p[k]);
+    double tot = group_sum<M>(v);
+    double ll2 = log2(tot);
+    v /= tot;
+    double v_in = v;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) v_in = v;
+        chain_forward_step<M>(v, ll2, rank_rows + r * rank_stride_rows + pair * M * M, rank_log2 + r * rank_stride_log + pair * M, k);
+    }
+    // backward over the processes behind this one: the adjoint vector leaving this process's slice
+    double w_out = 1.0;
+    for (int r = world - 1; r > rank; --r)
+        chain_backward_step<M>(w_out, rank_rows + r * rank_stride_rows + pair * M * M, rank_log2 + r * rank_stride_log + pair * M, k);
+    // inside the slice: this process's own segment operators
+    v = v_in;
+    double unused = 0.0;
+    if (writer) al[g_lo * M + k] = F(v);
+    for (int64_t g = g_lo; g < g_hi; ++g) {
+        chain_forward_step<M>(v, unused, op_rows(ta, pair, g, n_pairs, M), op_log2(ta, pair, g, n_pairs, M), k);
+        if (writer) al[(g + 1) * M + k] = F(v);
+    }
+    v = w_out;
+    if (writer) be[g_hi * M + k] = F(v);
+    for (int64_t g = g_hi - 1; g >= g_lo; --g) {
+        chain_backward_step<M>(v, op_rows(ta, pair, g, n_pairs, M), op_log2(ta, pair, g, n_pairs, M), k);
+        if (writer) be[g * M + k] = F(v);
+    }
+    if (writer && k == 0 && !outputs_skipped(a, ps)) {
+        double ll = ll2 * 0.69314718055994530942;
+        const int64_t row = a.inds[ps];
+        if (row < 0 || row >= a.n_rows) {
+            atomicOr(a.err_flag, 1);
+            ll = __longlong_as_double(0x7ff8000000000000LL);
+        } else if (!(ll == ll) || ll > 1e300 || ll < -1e300) {
+            atomicOr(a.err_flag, 2);
+        }
+        a.ll[pair] = a.out_mode ? a.ll[pair] - ll : ll;
+    }
+}
+
 // dlog[pair] = sum over the segments of their partial gradients (rows b .. emis1); the pi row is the
 // one of the first segment.  One thread per output entry.
 template <typename F>

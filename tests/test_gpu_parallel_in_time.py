@@ -267,10 +267,13 @@ def test_time_axis_sharding_equals_the_single_process_term(S, world):
     n_seg, slot = kern.sharded_plan(40, S, 500, world)
     assert n_seg >= world and slot > 0
     gather = torch.zeros(world * slot, dtype=torch.uint8, device=dev)
-    for rank in range(world):
+    for rank in range(world):  # every "process" leaves the product of its segment operators in its slot
         kern.sharded_begin(x, pattern, 1e-2, inds, 500, rank, world, gather)
     total = torch.zeros_like(want)
     for rank in range(world):
+        # (one kernel object plays all processes here: its own segment operators, which a real process still
+        # holds from its call to _begin, are recomputed first)
+        kern.sharded_begin(x, pattern, 1e-2, inds, 500, rank, world, gather)
         total += kern.sharded_end(inds, 40, 500, rank, world, gather)
         assert "time-sharded" in kern.last_kernel_name or rank == 0
     kern.sync()
