@@ -1733,7 +1733,7 @@ int phb_hmm_term_sharded_begin(phb_kernel *k, const double *x, int64_t B, const 
     float *out_rows = reinterpret_cast<float *>(slot);
     double *out_log2 = reinterpret_cast<double *>(slot + p.rows_bytes);
     void *pargs[] = {&ta, &out_rows, &out_log2};
-    PHB_CUDA(cudaLaunchKernel(tv->product_func, dim3(unsigned((B * S * M + 127) / 128)), dim3(128), pargs, 0, static_cast<cudaStream_t>(stream)));
+    PHB_CUDA(cudaLaunchKernel(tv->product_func, dim3(unsigned((B * S * M * M + 127) / 128)), dim3(128), pargs, 0, static_cast<cudaStream_t>(stream)));
     k->launches += 1;
     return PHB_OK;
 }

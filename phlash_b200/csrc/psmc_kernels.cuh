@@ -1384,57 +1384,7 @@ template <typename F, int M> __global__ void chain_boundaries_kernel(const Trans
 // chain_boundaries_sharded_kernel chains them to the vectors entering / leaving the process's slice, then the
 // process's own segment operators to the boundary vectors inside it.
 //
-// chain_product_kernel: M lanes per pair; lane k owns ROW k of the running product, a distribution over the M
-// states with its own log2 scale (the same representation as a segment operator: rows rescaled to sum 1 +
-// row_log2), and multiplies it into the next operator exactly like the forward chain step does.
-template <int M> __global__ void chain_product_kernel(const TransferArgs ta, float *__restrict__ out_rows, double *__restrict__ out_log2) {
-    const KernelArgs &a = ta.k;
-    const int64_t n_pairs = a.B * a.S;
-    const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t >= n_pairs * M) return;
-    const int64_t pair = t / M;
-    const int k = int(t % M);
-    double v[M];
-    double lg_acc = 0.0;
-    if (ta.n_seg_local > 0) {
-        const int64_t g = ta.seg_first;
-        const float *rows = op_rows(ta, pair, g, n_pairs, M) + k * M;
-#pragma unroll
-        for (int j = 0; j < M; ++j) v[j] = double(rows[j]);
-        lg_acc = op_log2(ta, pair, g, n_pairs, M)[k];
-    } else {  // a process without segments contributes the identity
-#pragma unroll
-        for (int j = 0; j < M; ++j) v[j] = j == k ? 1.0 : 0.0;
-    }
-    for (int64_t g = ta.seg_first + 1; g < ta.seg_first + ta.n_seg_local; ++g) {
-        const float *rows = op_rows(ta, pair, g, n_pairs, M);
-        const double *lg = op_log2(ta, pair, g, n_pairs, M);
-        double top = -1e300;
-#pragma unroll
-        for (int i = 0; i < M; ++i)
-            if (v[i] > 0.0 && lg[i] > top) top = lg[i];
-        double next[M];
-#pragma unroll
-        for (int j = 0; j < M; ++j) next[j] = 0.0;
-#pragma unroll 4
-        for (int i = 0; i < M; ++i) {
-            const double w = v[i] > 0.0 ? v[i] * exp2(lg[i] - top) : 0.0;
-#pragma unroll
-            for (int j = 0; j < M; ++j) next[j] += w * double(rows[i * M + j]);
-        }
-        double tot = 0.0;
-#pragma unroll
-        for (int j = 0; j < M; ++j) tot += next[j];
-        lg_acc += top + log2(tot);
-#pragma unroll
-        for (int j = 0; j < M; ++j) v[j] = next[j] / tot;
-    }
-#pragma unroll
-    for (int j = 0; j < M; ++j) out_rows[(pair * M + k) * M + j] = float(v[j]);
-    out_log2[pair * M + k] = lg_acc;
-}
-
-// One forward chain step for the M lanes of a pair (lane k owns component k):  v <- normalised (v T),  ll2 += log2 of
+// One forward chain step for the M lanes of a group (lane k owns component k):  v <- normalised (v T),  ll2 += log2 of
 // what was divided out.  rows / lg: the operator's [M][M] rows and [M] log2 row scales.
 template <int M> __device__ __forceinline__ void chain_forward_step(double &v, double &ll2, const float *__restrict__ rows,
                                                                     const double *__restrict__ lg_rows, int k) {
@@ -1458,6 +1408,30 @@ template <int M> __device__ __forceinline__ void chain_backward_step(double &v, 
     for (int j = 0; j < M; ++j) acc += double(rows[k * M + j]) * __shfl_sync(0xffffffffu, v, j, M);
     const double next = acc * exp2(lg - top);
     v = next / group_max<M>(next);
+}
+
+// chain_product_kernel: M x M lanes per pair; the M lanes of group r own ROW r of the running product - a
+// distribution over the M states with its own log2 scale, the same representation as a segment operator - and push
+// it through the next operator exactly like a forward chain step.  Launch with a multiple of M threads per CTA.
+template <int M> __global__ void chain_product_kernel(const TransferArgs ta, float *__restrict__ out_rows, double *__restrict__ out_log2) {
+    const KernelArgs &a = ta.k;
+    const int64_t n_pairs = a.B * a.S;
+    const int64_t t_raw = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const bool writer = t_raw < n_pairs * M * M;
+    const int64_t t = writer ? t_raw : n_pairs * M * M - 1;  // idle lanes shadow the last entry (whole groups shuffle)
+    const int64_t pair = t / (M * M);
+    const int r = int((t / M) % M), k = int(t % M);
+    double v = r == k ? 1.0 : 0.0, lg_acc = 0.0;  // a process without segments contributes the identity
+    if (ta.n_seg_local > 0) {
+        v = double(op_rows(ta, pair, ta.seg_first, n_pairs, M)[r * M + k]);
+        lg_acc = op_log2(ta, pair, ta.seg_first, n_pairs, M)[r];
+    }
+    for (int64_t g = ta.seg_first + 1; g < ta.seg_first + ta.n_seg_local; ++g)
+        chain_forward_step<M>(v, lg_acc, op_rows(ta, pair, g, n_pairs, M), op_log2(ta, pair, g, n_pairs, M), k);
+    if (writer) {
+        out_rows[(pair * M + r) * M + k] = float(v);
+        if (k == 0) out_log2[pair * M + r] = lg_acc;
+    }
 }
 
 // rank_rows / rank_log2: the all-gathered operators of the processes, process r at + r * rank_stride_* ([pairs][M][M]
