@@ -5,6 +5,7 @@
 #include "../../include/phlash_b200.h"
 #include "psmc_kernels.cuh"
 #include "psmc_params.cuh"
+#include "psmc_sform.cuh"
 #include "psmc_support.cuh"
 #include "psmc_uniform.cuh"
 
@@ -111,7 +112,7 @@ struct phb_kernel {
     int escalate = 1;
     // experiment knobs, read from the environment ONCE when the object is created (never per call):
     // PHB_NT, PHB_STORE_ALL, PHB_PARALLEL_IN_TIME, PHB_PIT_SEGMENTS
-    int env_nt = 0, env_store_all = -2, env_pit = -2, env_pit_segments = 0, env_sweep_T = 0, env_uniform = 1;
+    int env_nt = 0, env_store_all = -2, env_pit = -2, env_pit_segments = 0, env_sweep_T = 0, env_uniform = 1, env_sform = 0;
     // phb_reserve(): the dispatch runs with dry = true - every scratch buffer is sized and every kernel
     // attribute set exactly as a real call would, but nothing is launched
     bool dry = false;
@@ -194,6 +195,33 @@ const std::vector<Variant> &variants() {
     return table;
 }
 
+// Thread-per-pair kernels at M = 16 (float) on the rescaled recursion (psmc_sform.cuh): 15 % fewer executed
+// instructions, but measured SLOWER than psmc_loglik_kernel<float, 16, 1, ...> (see the header of that file), so they
+// are only selected with PHB_SFORM=1.
+const Variant *sform_variant(bool grad, bool seg) {
+    auto make = [](const void *func, bool g, size_t smem) {
+        Variant v;
+        v.M = 16;
+        v.T = 1;
+        v.K = 8;
+        v.NT = 128;
+        v.dbl = false;
+        v.grad = g;
+        v.func = func;
+        v.smem = smem;
+        v.ckpt_bytes_per_warp = [](int64_t L) { return phb::ckpt_bytes_per_warp<float, 16, 8>(L); };
+        return v;
+    };
+    static const Variant grad_v = make(reinterpret_cast<const void *>(&phb::psmc_sform_kernel<8, true, 128, 2, false>), true,
+                                       phb::sform_smem_bytes<8, 128, true>());
+    static const Variant seg_v = make(reinterpret_cast<const void *>(&phb::psmc_sform_kernel<8, true, 128, 2, true>), true,
+                                      phb::sform_smem_bytes<8, 128, true>());
+    static const Variant fwd_v = make(reinterpret_cast<const void *>(&phb::psmc_sform_kernel<8, false, 128, 3, false>), false,
+                                      phb::sform_smem_bytes<8, 128, false>());
+    return seg ? &seg_v : (grad ? &grad_v : &fwd_v);
+}
+bool is_sform(const Variant *v) { return v == sform_variant(true, false) || v == sform_variant(true, true) || v == sform_variant(false, false); }
+
 // Precision-escalation kernels of float objects: double arithmetic on float buffers (gradient path).
 const Variant *escalation_variant(int M) {
     static const std::vector<Variant> table = {
@@ -210,7 +238,7 @@ const Variant *escalation_variant(int M) {
 
 // Segment-mode builds of the throughput gradient kernel (segment passes of the two-sweep gradient once
 // the segments of all pairs fill the GPU): the fastest lane layout of every M.
-const Variant *segment_variant(int M) {
+const Variant *segment_variant_generic(int M) {
     static const std::vector<Variant> table = {
         make_variant<float, 4, 1, 16, true, 128, 4, float, true>(),   // M = 4
         make_variant<float, 8, 1, 16, true, 128, 3, float, true>(),   // M = 8
@@ -221,6 +249,11 @@ const Variant *segment_variant(int M) {
     for (const Variant &v : table)
         if (v.M == M) return &v;
     return nullptr;
+}
+
+const Variant *segment_variant(const phb_kernel *k) {
+    if (k->M == 16 && !k->dbl && k->env_sform) return sform_variant(true, true);
+    return segment_variant_generic(k->M);
 }
 
 // Store-all gradient kernels (small minibatches, see psmc_kernels.cuh): float only.
@@ -338,8 +371,9 @@ const Variant *pick_variant(const phb_kernel *k, bool grad, int64_t n_pairs) {
         last = &v;
         if (!first_fill && n_pairs * v.T >= fill) first_fill = &v;
     }
-    if (forced) return forced;  // a forced T that is not compiled for this path falls back to auto
-    return first_fill ? first_fill : last;
+    const Variant *chosen = forced ? forced : (first_fill ? first_fill : last);  // (a forced T that is not compiled falls back to auto)
+    if (chosen && chosen->M == 16 && chosen->T == 1 && !chosen->dbl && k->env_sform) return sform_variant(grad, false);
+    return chosen;
 }
 
 int check_handle(const phb_kernel *k) {
@@ -396,7 +430,7 @@ int launch_transfer_rows(phb_kernel *k, const TransferVariant *tv, const phb::Tr
 int try_parallel_in_time_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t stream, int pit_mode) {
     const int64_t n_pairs = a.B * a.S;
     const TransferVariant *tv = transfer_variant(k->M);
-    const Variant *gv = segment_variant(k->M);  // segment passes: throughput kernel in SEG mode
+    const Variant *gv = segment_variant(k);  // segment passes: throughput kernel in SEG mode
     if (!tv || !gv) return kNotTaken;
     const int M = k->M;
     const int64_t capacity = int64_t(k->num_sms) * 384;  // resident threads of the row kernel
@@ -483,7 +517,7 @@ int try_two_sweep_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t
     const StoreAllVariant *sv = nullptr;
     for (const StoreAllVariant &c : storeall_variants())
         if (c.M == k->M) sv = &c;
-    const Variant *tv = segment_variant(k->M);
+    const Variant *tv = segment_variant(k);
     if (!sv || !tv) return kNotTaken;
     if (pit_mode != 2 && n_pairs * sv->T > int64_t(k->num_sms) * 330) return kNotTaken;
     const int M = k->M;
@@ -660,7 +694,7 @@ struct ShardPlan {
 bool shard_plan(phb_kernel *k, int64_t B, int64_t S, int64_t L, int world, ShardPlan &p) {
     p = ShardPlan{};
     const TransferVariant *tv = transfer_variant(k->M);
-    const Variant *gv = segment_variant(k->M);
+    const Variant *gv = segment_variant(k);
     if (!tv || !gv || k->dbl || world < 2) return false;
     const int64_t n_pairs = B * S;
     const int M = k->M;
@@ -796,8 +830,8 @@ int launch_throughput_kernel(phb_kernel *k, phb::KernelArgs a, bool grad, cudaSt
     PHB_CUDA(cudaLaunchKernel(v->func, dim3(unsigned(grid)), dim3(v->NT), kargs, smem, stream));
     k->launches += 1;
     if (!fixed)
-        snprintf(k->last_name, sizeof k->last_name, "psmc_loglik_kernel<%s,MT=%d,T=%d,K=%d,%s,NT=%d>", v->dbl ? "double" : "float",
-                 v->M / v->T, v->T, v->K, v->grad ? "grad" : "fwd", v->NT);
+        snprintf(k->last_name, sizeof k->last_name, "%s<%s,MT=%d,T=%d,K=%d,%s,NT=%d>", is_sform(v) ? "psmc_sform_kernel" : "psmc_loglik_kernel",
+                 v->dbl ? "double" : "float", v->M / v->T, v->T, v->K, v->grad ? "grad" : "fwd", v->NT);
     return PHB_OK;
 }
 
@@ -926,6 +960,7 @@ static int new_kernel(int M, int64_t N, int64_t L, int double_precision, int dev
     if (const char *v = getenv("PHB_PIT_SEGMENTS")) k->env_pit_segments = atoi(v);
     if (const char *v = getenv("PHB_SWEEP_T")) k->env_sweep_T = atoi(v);
     if (const char *v = getenv("PHB_UNIFORM")) k->env_uniform = atoi(v);
+    if (const char *v = getenv("PHB_SFORM")) k->env_sform = atoi(v);
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&k->d_data), size_t(N) * size_t(k->pitch));
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -1428,6 +1463,9 @@ int phb_sync(phb_kernel *k) {
     if (flag) PHB_CUDA(cudaMemset(k->d_err, 0, sizeof(int)));
     if (flag & 1) return fail(PHB_E_INVALID, "index out of range: need 0 <= inds < N=%lld", (long long)k->N);
     // (reference: assert np.isfinite on the parameters, gpu.py:214; a non-finite parameter gives a non-finite ll)
+    if (flag & 4)
+        return fail(PHB_E_INVALID, "parameters outside the domain of the rescaled kernel: need v[k] > 0 for k >= 1 and emis0[k] > 0 "
+                                   "(PSMCParams.from_dm clips to [1e-20, 1 - 1e-20]; PHB_SFORM=0 selects the unscaled kernel)");
     if (flag & 2) return fail(PHB_E_INVALID, "not all parameters / results finite");
     return PHB_OK;
 }
@@ -1747,7 +1785,7 @@ int phb_hmm_term_sharded_end(phb_kernel *k, const int64_t *inds, int64_t B, int6
     ShardPlan p;
     if (!shard_plan(k, B, S, k->L, world, p)) return fail(PHB_E_INVALID, "time-axis sharding does not apply to this call");
     const TransferVariant *tv = transfer_variant(k->M);
-    const Variant *gv = segment_variant(k->M);
+    const Variant *gv = segment_variant(k);
     const int M = k->M, C = 7 * M;
     const int64_t n_pairs = B * S;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
