@@ -112,7 +112,7 @@ struct phb_kernel {
     int escalate = 1;
     // experiment knobs, read from the environment ONCE when the object is created (never per call):
     // PHB_NT, PHB_STORE_ALL, PHB_PARALLEL_IN_TIME, PHB_PIT_SEGMENTS
-    int env_nt = 0, env_store_all = -2, env_pit = -2, env_pit_segments = 0, env_sweep_T = 0, env_uniform = 1, env_sform = 0;
+    int env_nt = 0, env_store_all = -2, env_pit = -2, env_pit_segments = 0, env_sweep_tf = 0, env_sweep_tb = 0, env_uniform = 1, env_sform = 0, env_sweep_ll = 1;
     // phb_reserve(): the dispatch runs with dry = true - every scratch buffer is sized and every kernel
     // attribute set exactly as a real call would, but nothing is launched
     bool dry = false;
@@ -260,7 +260,6 @@ const Variant *segment_variant(const phb_kernel *k) {
 struct StoreAllVariant {
     int M, T, MT, NT;
     const void *func;
-    const void *sweep_func;  // forward / adjoint-only sweeps that leave the boundary vectors
     size_t smem;
 };
 template <int MT, int T, int NT, int MINB> StoreAllVariant make_storeall() {
@@ -270,7 +269,6 @@ template <int MT, int T, int NT, int MINB> StoreAllVariant make_storeall() {
     v.MT = MT;
     v.NT = NT;
     v.func = reinterpret_cast<const void *>(&phb::psmc_loglik_storeall_kernel<float, MT, T, NT, MINB>);
-    v.sweep_func = reinterpret_cast<const void *>(&phb::boundary_sweep_kernel<float, MT, T, NT, MINB>);
     v.smem = phb::smem_bytes<float, MT, 8, NT, false>();
     return v;
 }
@@ -286,27 +284,57 @@ const std::vector<StoreAllVariant> &storeall_variants() {
     return table;
 }
 
-// Lane layouts of the boundary sweeps (latency regime: one warp per scheduler, what counts is the length of
-// the dependency chain per site, not the instruction count).  PHB_SWEEP_T picks one for experiments.
+// Lane layouts of the boundary sweeps.  Latency regime: the launch ends with its slowest warp, a warp that has a
+// scheduler to itself takes ~1.2 cycles per instruction, two warps on one scheduler take twice as long.  So the
+// layout is the widest one (most lanes per pair = fewest instructions per lane and site) that still gives every
+// warp a scheduler of its own, i.e. at most one 4-warp CTA per SM; forward and adjoint sweep may differ.
+// PHB_SWEEP_TF / PHB_SWEEP_TB force a layout, PHB_SWEEP_LL=0 selects the generic site functions.
 struct SweepVariant {
-    int M, T, MT, NT;
+    int M, TF, TB, NT;
+    bool ll;
     const void *func;
     size_t smem;
 };
-template <int MT, int T, int NT, int MINB> SweepVariant make_sweep() {
-    return SweepVariant{MT * T, T, MT, NT, reinterpret_cast<const void *>(&phb::boundary_sweep_kernel<float, MT, T, NT, MINB>),
-                        phb::smem_bytes<float, MT, 8, NT, false>()};
+template <int M, int TF, int TB, int MINB, bool LL> SweepVariant make_sweep() {
+    constexpr int NT = 128;
+    return SweepVariant{M, TF, TB, NT, LL, reinterpret_cast<const void *>(&phb::boundary_sweep_kernel<float, M, TF, TB, NT, MINB, LL>),
+                        std::max(phb::sweep_smem_bytes<float, M / TF, NT>(), phb::sweep_smem_bytes<float, M / TB, NT>())};
 }
-const SweepVariant *sweep_variant(int M, int want_T) {
+const std::vector<SweepVariant> &sweep_variants() {
+    // in order of preference for each M (widest first); MINB = 2: up to 255 registers, one CTA per SM is the aim
     static const std::vector<SweepVariant> table = {
-        make_sweep<8, 2, 64, 4>(),    // M = 16, two lanes per pair
-        make_sweep<16, 1, 32, 4>(),   // M = 16, thread per pair
-        make_sweep<16, 2, 64, 4>(),   // M = 32
-        make_sweep<16, 4, 128, 2>(),  // M = 64
+        make_sweep<4, 1, 1, 2, false>(),
+        make_sweep<8, 2, 2, 2, true>(),    make_sweep<8, 2, 2, 2, false>(),
+        make_sweep<16, 4, 4, 2, true>(),   make_sweep<16, 4, 2, 2, true>(),  make_sweep<16, 2, 2, 2, true>(),
+        make_sweep<16, 4, 4, 2, false>(),  make_sweep<16, 1, 1, 2, false>(),
+        make_sweep<32, 8, 8, 2, true>(),   make_sweep<32, 8, 4, 2, true>(),  make_sweep<32, 4, 4, 2, true>(),
+        make_sweep<32, 4, 2, 2, true>(),   make_sweep<32, 2, 2, 2, true>(),  make_sweep<32, 8, 8, 2, false>(),
+        make_sweep<64, 16, 16, 2, false>(),
     };
-    for (const SweepVariant &v : table)
-        if (v.M == M && v.T == want_T) return &v;
-    return nullptr;
+    return table;
+}
+inline int64_t sweep_ctas(const SweepVariant &v, int64_t n_pairs) {
+    const int64_t pf = v.NT / v.TF, pb = v.NT / v.TB;
+    return (n_pairs + pf - 1) / pf + (n_pairs + pb - 1) / pb;
+}
+const SweepVariant *pick_sweep(const phb_kernel *k, int64_t n_pairs) {
+    // PHB_SWEEP_LL: 0 = generic site functions only, 1 = low-latency ones wherever they exist (default)
+    const bool forced = k->env_sweep_tf > 0;
+    const int want_tb = k->env_sweep_tb > 0 ? k->env_sweep_tb : k->env_sweep_tf;
+    const bool want_ll = k->env_sweep_ll != 0;
+    const SweepVariant *first = nullptr;
+    for (const SweepVariant &v : sweep_variants()) {
+        if (v.M != k->M) continue;
+        if (forced) {
+            if (v.TF == k->env_sweep_tf && v.TB == want_tb && v.ll == (k->env_sweep_ll != 0 && v.TF + v.TB > 2)) return &v;
+            continue;
+        }
+        const bool has_ll_form = v.TF + v.TB > 2 && v.M != 64;
+        if (has_ll_form && v.ll != want_ll) continue;
+        if (!first) first = &v;
+        if (sweep_ctas(v, n_pairs) <= k->num_sms) return &v;
+    }
+    return first;
 }
 
 // Parallel-in-time forward evaluation (few, long pairs; see transfer_rows_kernel): float, M <= 16.
@@ -547,18 +575,11 @@ int try_two_sweep_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t
     if (n_seg < 2) return kNotTaken;
     const int64_t n_groups = seg_ctas * n_seg;
     const int64_t grid = std::min<int64_t>(n_groups, resident);
-    // lane layout of the sweeps: the store-all table's, unless PHB_SWEEP_T names another one
-    const void *sweep_func = sv->sweep_func;
-    size_t sweep_smem = sv->smem;
-    int sweep_NT = sv->NT, sweep_T = sv->T, sweep_MT = sv->MT;
-    if (const SweepVariant *alt = sweep_variant(M, k->env_sweep_T)) {
-        sweep_func = alt->func;
-        sweep_smem = alt->smem;
-        sweep_NT = alt->NT;
-        sweep_T = alt->T;
-        sweep_MT = alt->MT;
-    }
-    const int64_t sweep_ctas = (n_pairs + sweep_NT / sweep_T - 1) / (sweep_NT / sweep_T);
+    const SweepVariant *sw = pick_sweep(k, n_pairs);
+    if (!sw || a.L >= (int64_t(1) << 31) - 16) return kNotTaken;  // (the sweeps count sites in 32 bits)
+    const void *sweep_func = sw->func;
+    const size_t sweep_smem = sw->smem;
+    const int64_t fwd_ctas = (n_pairs + sw->NT / sw->TF - 1) / (sw->NT / sw->TF);
     int rc;
     if ((rc = k->bnd_alpha.reserve(size_t(n_pairs) * (n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
     if ((rc = k->bnd_beta.reserve(size_t(n_pairs) * (n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
@@ -581,16 +602,17 @@ int try_two_sweep_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t
     sa.seg_dlog = k->seg_dlog.ptr;
     sa.seg_ctas = seg_ctas;
     sa.n_groups = n_groups;
+    sa.sweep_fwd_ctas = fwd_ctas;
     void *kargs[] = {&sa};
-    PHB_CUDA(cudaLaunchKernel(sweep_func, dim3(unsigned(2 * sweep_ctas)), dim3(sweep_NT), kargs, sweep_smem, stream));
+    PHB_CUDA(cudaLaunchKernel(sweep_func, dim3(unsigned(sweep_ctas(*sw, n_pairs))), dim3(sw->NT), kargs, sweep_smem, stream));
     PHB_CUDA(cudaLaunchKernel(tv->func, dim3(unsigned(grid)), dim3(tv->NT), kargs, tv->smem, stream));
     const int64_t n_out = n_pairs * 7 * M;
     phb::sum_segments_kernel<float><<<unsigned((n_out + 255) / 256), 256, 0, stream>>>(
         static_cast<const float *>(k->seg_dlog.ptr), n_pairs, n_seg, M, static_cast<float *>(a.dlog), a.out_mode, a);
     PHB_CUDA(cudaGetLastError());
     k->launches += 3;
-    snprintf(k->last_name, sizeof k->last_name, "boundary_sweep_kernel<float,MT=%d,T=%d> + psmc_loglik_kernel<SEG,MT=%d,T=%d> x %lld segments",
-             sweep_MT, sweep_T, tv->M / tv->T, tv->T, (long long)n_seg);
+    snprintf(k->last_name, sizeof k->last_name, "boundary_sweep_kernel<float,TF=%d,TB=%d%s> + psmc_loglik_kernel<SEG,MT=%d,T=%d> x %lld segments",
+             sw->TF, sw->TB, sw->ll ? ",LL" : "", tv->M / tv->T, tv->T, (long long)n_seg);
     return PHB_OK;
 }
 
@@ -958,7 +980,9 @@ static int new_kernel(int M, int64_t N, int64_t L, int double_precision, int dev
     if (const char *v = getenv("PHB_STORE_ALL")) k->env_store_all = atoi(v);
     if (const char *v = getenv("PHB_PARALLEL_IN_TIME")) k->env_pit = atoi(v);
     if (const char *v = getenv("PHB_PIT_SEGMENTS")) k->env_pit_segments = atoi(v);
-    if (const char *v = getenv("PHB_SWEEP_T")) k->env_sweep_T = atoi(v);
+    if (const char *v = getenv("PHB_SWEEP_TF")) k->env_sweep_tf = atoi(v);
+    if (const char *v = getenv("PHB_SWEEP_TB")) k->env_sweep_tb = atoi(v);
+    if (const char *v = getenv("PHB_SWEEP_LL")) k->env_sweep_ll = atoi(v);
     if (const char *v = getenv("PHB_UNIFORM")) k->env_uniform = atoi(v);
     if (const char *v = getenv("PHB_SFORM")) k->env_sform = atoi(v);
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&k->d_data), size_t(N) * size_t(k->pitch));

@@ -88,6 +88,7 @@ struct KernelArgs {
     int64_t seg_len;        // sites per segment (multiple of 16); the last one has L - (G - 1) seg_len
     int64_t seg_ctas;       // groups per segment: group g scores segment g / seg_ctas, so that all warps of a CTA
                             // share the segment length (the loop bounds stay uniform for the shuffles)
+    int64_t sweep_fwd_ctas; // boundary_sweep_kernel: CTAs [0, sweep_fwd_ctas) sweep forwards, the rest backwards
     const void *bnd_alpha;  // [B * S][G + 1][M] FLOAT: forward vector entering segment g (sum 1)
     const void *bnd_beta;   // [B * S][G + 1][M] FLOAT: adjoint vector behind segment g - 1 (any scale)
     void *seg_dlog;         // [B * S][segments of this launch][7][M] FLOAT
@@ -1552,31 +1553,242 @@ __device__ __forceinline__ void adjoint_only_site(F (&beta)[MT], const Params<F,
     for (int k = 0; k < MT; ++k) beta[k] = fma(p.u[k], tailq[k], beta[k]);
 }
 
-template <typename F, int MT, int T, int NT, int MINB>
-__global__ void __maxnreg__(max_regs(NT, MINB)) boundary_sweep_kernel(const KernelArgs a) {
+// ---- low-latency site functions for the sweeps (LL = true, T >= 4) ----
+// A sweep runs with about one warp per scheduler: what counts is the LENGTH of the dependency chain from
+// x(t) to x(t + 1), not the instruction count.  The generic site functions scan across the T lanes of a pair
+// with a butterfly (log2 T DEPENDENT shuffles, ~28 cycles each) and only then walk the local chains.  Here
+//   * every lane fetches the local totals of all T - 1 partners with INDEPENDENT xor shuffles (one shuffle
+//     latency) and weighs them with 0 / 1 lane masks,
+//   * everything that does not need the partners' totals - the local prefix / suffix chains, the diagonal
+//     term, the products with the emission row - is computed in the shadow of the shuffles,
+//   * behind the shuffles remain one short multiply-add chain for the offsets and two FMAs per state,
+//   * the rescaling factor of a block is applied two sites LATER (the recursion is linear: when the factor is
+//     applied does not matter), so the sum / reciprocal never sits on the chain either.
+// ~60 dependent cycles per site instead of ~120.
+//   * the emission row is addressed by (observation & 3) * row bytes - rows emis0, emis1, ones, ones, so that -1
+//     (0xff) lands on a row of ones - instead of a compare / select chain: integer instructions issue at half
+//     rate, and a lone warp feels every one of them.
+template <typename F, int MT, int NT> struct EmisTable4 {
+    static constexpr int W = Vec<F>::W;
+    static constexpr int QN = MT / W;
+    static constexpr uint32_t kRowBytes = QN * NT * 16;
+    static constexpr size_t kBytes = size_t(4) * kRowBytes;
+    uint32_t base;  // shared address of this thread's column
+    template <typename IO> __device__ __forceinline__ void fill(const IO *__restrict__ src, int M) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int q = 0; q < QN; ++q) {
+                F tmp[W];
+#pragma unroll
+                for (int i = 0; i < W; ++i) tmp[i] = r < 2 ? F(src[(4 + r) * M + q * W + i]) : F(1);
+                sts_word(base + r * kRowBytes + q * NT * 16, tmp);
+            }
+        }
+    }
+    // byte offset of the row of site j of a block of four observations
+    static __device__ __forceinline__ uint32_t row_of(uint32_t blk, int j) { return ((blk >> (8 * j)) & 3u) * kRowBytes; }
+    __device__ __forceinline__ void get(uint32_t row_off, F (&e)[MT]) const {
+#pragma unroll
+        for (int q = 0; q < QN; ++q) lds_word(base + row_off + q * NT * 16, &e[q * W]);
+    }
+};
+// MUFU.LG2 without the denormal detour of __log2f (the totals are far from denormal)
+__device__ __forceinline__ float lg2_fast(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ double lg2_fast(double x) { return log2(x); }
+
+template <typename F, int T> struct LaneMasks {
+    F before[T - 1], after[T - 1];  // partner sub ^ (o + 1) has a smaller / larger lane index than this lane
+    __device__ __forceinline__ void init(int sub) {
+#pragma unroll
+        for (int o = 1; o < T; ++o) {
+            before[o - 1] = (sub ^ o) < sub ? F(1) : F(0);
+            after[o - 1] = (sub ^ o) > sub ? F(1) : F(0);
+        }
+    }
+};
+// sum of `mine` over all T lanes of the pair, independent shuffles
+template <typename F, int T> __device__ __forceinline__ F lanes_total_flat(F mine) {
+    F s[2] = {mine, F(0)};
+#pragma unroll
+    for (int o = 1; o < T; ++o) s[o & 1] += __shfl_xor_sync(0xffffffffu, mine, o, T);
+    return s[0] + s[1];
+}
+template <typename F, int MT, int T> __device__ __forceinline__ F pair_sum_flat(const F (&x)[MT]) {
+    F part[2] = {F(0), F(0)};
+#pragma unroll
+    for (int k = 0; k < MT; ++k) part[k & 1] += x[k];
+    return lanes_total_flat<F, T>(part[0] + part[1]);
+}
+
+// The forward sweep carries the PREDICTED vector z(t) = alpha(t - 1) A (before the emission of site t) instead of
+// alpha(t): the step z <- (emis .* z) A then has the shape of the adjoint step - one product with the emission row up
+// front, nothing but two FMAs per state behind the shuffles - and needs a quarter fewer instructions than a step that
+// multiplies by the emission row last.  w = emis .* z = alpha(t) is a by-product (the segment boundaries store it).
+template <typename F, int MT, int T, int NT>
+__device__ __forceinline__ void forward_site_ll(F (&z)[MT], F (&w)[MT], const Params<F, MT> &p, const LaneMasks<F, T> &lm,
+                                                const EmisTable4<F, MT, NT> &et, uint32_t row_off) {
+    et.get(row_off, w);
+#pragma unroll
+    for (int k = 0; k < MT; ++k) w[k] *= z[k];
+    // what the partners need from this lane
+    F tu[2] = {F(0), F(0)}, tx[2] = {F(0), F(0)};
+#pragma unroll
+    for (int k = 0; k < MT; ++k) {
+        tu[k & 1] = fma(p.u[k], w[k], tu[k & 1]);
+        tx[k & 1] += w[k];
+    }
+    const F my_u = tu[0] + tu[1], my_x = tx[0] + tx[1];
+    F su[T - 1], sx[T - 1];
+#pragma unroll
+    for (int o = 1; o < T; ++o) {
+        su[o - 1] = __shfl_xor_sync(0xffffffffu, my_u, o, T);
+        sx[o - 1] = __shfl_xor_sync(0xffffffffu, my_x, o, T);
+    }
+    // in the shadow of the shuffles: the lane's own part
+    F loc[MT];
+    {
+        F lp = F(0), ls = F(0), suf[MT];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            const int k = i, j = MT - 1 - i;
+            loc[k] = fma(p.v[k], lp, p.d[k] * w[k]);
+            lp = fma(p.u[k], w[k], lp);
+            suf[j] = ls;
+            ls += w[j];
+        }
+#pragma unroll
+        for (int k = 0; k < MT; ++k) loc[k] = fma(p.b[k], suf[k], loc[k]);
+    }
+    F pre = lm.before[0] * su[0], suf_off = lm.after[0] * sx[0];
+#pragma unroll
+    for (int o = 2; o < T; ++o) {
+        pre = fma(lm.before[o - 1], su[o - 1], pre);
+        suf_off = fma(lm.after[o - 1], sx[o - 1], suf_off);
+    }
+#pragma unroll
+    for (int k = 0; k < MT; ++k) z[k] = fma(p.v[k], pre, fma(p.b[k], suf_off, loc[k]));
+}
+
+template <typename F, int MT, int T, int NT>
+__device__ __forceinline__ void adjoint_only_site_ll(F (&beta)[MT], const Params<F, MT> &p, const LaneMasks<F, T> &lm,
+                                                     const EmisTable4<F, MT, NT> &et, uint32_t row_off) {
+    F w[MT];
+    et.get(row_off, w);
+#pragma unroll
+    for (int k = 0; k < MT; ++k) w[k] *= beta[k];
+    F tq[2] = {F(0), F(0)}, tb[2] = {F(0), F(0)};
+#pragma unroll
+    for (int k = 0; k < MT; ++k) {
+        tq[k & 1] = fma(p.v[k], w[k], tq[k & 1]);
+        tb[k & 1] = fma(p.b[k], w[k], tb[k & 1]);
+    }
+    const F my_q = tq[0] + tq[1], my_b = tb[0] + tb[1];
+    F sq[T - 1], sb[T - 1];
+#pragma unroll
+    for (int o = 1; o < T; ++o) {
+        sq[o - 1] = __shfl_xor_sync(0xffffffffu, my_q, o, T);
+        sb[o - 1] = __shfl_xor_sync(0xffffffffu, my_b, o, T);
+    }
+    F loc[MT];
+    {
+        F lb = F(0), lq = F(0), tailq[MT];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            const int k = i, j = MT - 1 - i;
+            loc[k] = fma(p.d[k], w[k], lb);
+            lb = fma(p.b[k], w[k], lb);
+            tailq[j] = lq;
+            lq = fma(p.v[j], w[j], lq);
+        }
+#pragma unroll
+        for (int k = 0; k < MT; ++k) loc[k] = fma(p.u[k], tailq[k], loc[k]);
+    }
+    F off_q = lm.after[0] * sq[0], off_b = lm.before[0] * sb[0];
+#pragma unroll
+    for (int o = 2; o < T; ++o) {
+        off_q = fma(lm.after[o - 1], sq[o - 1], off_q);
+        off_b = fma(lm.before[o - 1], sb[o - 1], off_b);
+    }
+#pragma unroll
+    for (int k = 0; k < MT; ++k) beta[k] = fma(p.u[k], off_q, loc[k] + off_b);
+}
+
+// Shared memory of a sweep CTA: the larger of the two emission tables.
+template <typename F, int MT, int NT> constexpr size_t sweep_smem_bytes() {
+    return smem_bytes<F, MT, 8, NT, false>() > EmisTable4<F, MT, NT>::kBytes ? smem_bytes<F, MT, 8, NT, false>() : EmisTable4<F, MT, NT>::kBytes;
+}
+
+// One step of either kind through a common interface: Site<LL>::forward / ::adjoint.
+template <typename F, int MT, int T, int NT, bool LL> struct SweepSite;
+template <typename F, int MT, int T, int NT> struct SweepSite<F, MT, T, NT, true> {
+    EmisTable4<F, MT, NT> et;
+    LaneMasks<F, T> lm;
+    __device__ __forceinline__ void init(uint32_t smem0, const F *par, int M, const Params<F, MT> &, int sub) {
+        et.base = smem0 + threadIdx.x * 16;
+        et.fill(par, M);
+        lm.init(sub);
+    }
+    // (z-form: x is the predicted vector, w receives alpha of this site)
+    __device__ __forceinline__ void forward(F (&x)[MT], F (&w)[MT], const Params<F, MT> &p, uint32_t blk, int j, int) const {
+        forward_site_ll<F, MT, T, NT>(x, w, p, lm, et, EmisTable4<F, MT, NT>::row_of(blk, j));
+    }
+    __device__ __forceinline__ void adjoint(F (&beta)[MT], const Params<F, MT> &p, uint32_t blk, int j, int) const {
+        adjoint_only_site_ll<F, MT, T, NT>(beta, p, lm, et, EmisTable4<F, MT, NT>::row_of(blk, j));
+    }
+    static __device__ __forceinline__ F total(const F (&x)[MT]) { return pair_sum_flat<F, MT, T>(x); }
+};
+template <typename F, int MT, int T, int NT> struct SweepSite<F, MT, T, NT, false> {
+    EmisTable<F, MT, NT> et;
+    PartnerCoef<F, MT, T, false> pc;
+    __device__ __forceinline__ void init(uint32_t smem0, const F *par, int M, const Params<F, MT> &p, int sub) {
+        constexpr int W = Vec<F>::W;
+        et.ones = smem0;
+        et.base = smem0 + ((EmisTable<F, MT, NT>::kOnesRow ? 0 : 1) + threadIdx.x) * 16;
+        if constexpr (!EmisTable<F, MT, NT>::kOnesRow) {
+            if (threadIdx.x == 0) {
+                F one[W];
+#pragma unroll
+                for (int i = 0; i < W; ++i) one[i] = F(1);
+                sts_word(smem0, one);
+            }
+            __syncthreads();
+        }
+        et.fill(par, M);
+        pc.init(p, sub);
+    }
+    // (x is alpha itself; w is a copy for the common interface)
+    __device__ __forceinline__ void forward(F (&x)[MT], F (&w)[MT], const Params<F, MT> &p, uint32_t blk, int j, int sub) const {
+        forward_site<F, MT, T, false, NT>(x, p, pc, et, ObsWords<8>::byte_of(blk, j), sub);
+#pragma unroll
+        for (int k = 0; k < MT; ++k) w[k] = x[k];
+    }
+    __device__ __forceinline__ void adjoint(F (&beta)[MT], const Params<F, MT> &p, uint32_t blk, int j, int sub) const {
+        adjoint_only_site<F, MT, T, NT>(beta, p, et, ObsWords<8>::byte_of(blk, j), sub);
+    }
+    static __device__ __forceinline__ F total(const F (&x)[MT]) { return pair_sum<F, MT, T>(x); }
+};
+
+// DIR: 0 = forward sweep, 1 = adjoint sweep (compile-time, so that a kernel holding two lane layouts carries one
+// direction of each).  The block loops count in 32 bits and carry as little bookkeeping as possible: about a
+// quarter of the time of the first version went into 64-bit index arithmetic, the predicated fp64 accumulation of
+// the log-likelihood and the select chain of the emission row (profiles/r02_ncu_sweep_summary.md).
+template <typename F, int MT, int T, int NT, bool LL, int DIR>
+__device__ __forceinline__ void boundary_sweep_body(const KernelArgs &a, const int64_t cta) {
+    static_assert(!LL || T >= 2, "the low-latency site functions need partner lanes");
+    static_assert(kNorm == 4, "one 32-bit word of observations per block");
     constexpr int M = MT * T;
     constexpr int PW = 32 / T;
     constexpr int kWarps = NT / 32;
-    constexpr int W = Vec<F>::W;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const uint32_t smem0 = smem_base_addr();
-    EmisTable<F, MT, NT> et;
-    et.ones = smem0;
-    et.base = smem0 + ((EmisTable<F, MT, NT>::kOnesRow ? 0 : 1) + threadIdx.x) * 16;
-    if constexpr (!EmisTable<F, MT, NT>::kOnesRow) {
-        if (threadIdx.x == 0) {
-            F one[W];
-#pragma unroll
-            for (int i = 0; i < W; ++i) one[i] = F(1);
-            sts_word(smem0, one);
-        }
-        __syncthreads();
-    }
     const int sub = lane % T;
     const int lp = lane / T;
-    const bool backwards = (blockIdx.x & 1) != 0;
-    const int64_t cta = blockIdx.x >> 1;
+    constexpr bool backwards = DIR != 0;
     const int64_t n_pairs = a.B * a.S;
     const int64_t pair_raw = (cta * kWarps + warp) * PW + lp;
     const bool writer = pair_raw < n_pairs;
@@ -1585,68 +1797,80 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) boundary_sweep_kernel(const Kern
     const F *par = static_cast<const F *>(a.params6) + pb * a.pstride_b + ps * a.pstride_s + sub * MT;
     Params<F, MT> p;
     p.load(par, M);
-    et.fill(par, M);
-    PartnerCoef<F, MT, T, false> pc;
-    pc.init(p, sub);
+    SweepSite<F, MT, T, NT, LL> site;
+    site.init(smem_base_addr(), par, M, p, sub);
     int64_t row = a.inds[ps];
     const bool bad_row = row < 0 || row >= a.n_rows;
     if (bad_row) row = 0;
-    const int8_t *obs = a.data + row * a.pitch;
-    const int64_t G = a.seg_count;
-    const int64_t n_blocks = (a.L + kNorm - 1) / kNorm;
+    // rows start on 16-byte boundaries and are padded to whole 16-byte words
+    const uint32_t *obs = reinterpret_cast<const uint32_t *>(a.data + row * a.pitch);
+    const int G = int(a.seg_count);
+    const int L = int(a.L);              // (the host takes this path for L < 2^31 only)
+    const int full_blocks = L / kNorm;   // the ragged tail, if any, is block number full_blocks
+    const int tail = L - full_blocks * kNorm;
+    const int seg_blocks = int(a.seg_len) / kNorm;  // segment lengths are multiples of 16
     F *bnd = static_cast<F *>(const_cast<void *>(backwards ? a.bnd_beta : a.bnd_alpha)) + pair * (G + 1) * M + sub * MT;
 
-    if (!backwards) {
+    if constexpr (!backwards) {
         const F *pi_p = static_cast<const F *>(a.pi) + pb * a.pistride_b + ps * a.pistride_s + sub * MT;
         F x[MT];
 #pragma unroll
         for (int k = 0; k < MT; ++k) x[k] = pi_p[k];
-        double ll = 0.0;
-        F acc;
+        double ll;
         {
             const F tot = pair_sum<F, MT, T>(x);
-            acc = log2_of<F>(tot);
+            ll = double(log2_of<F>(tot));
 #pragma unroll
             for (int k = 0; k < MT; ++k) {
                 x[k] = x[k] / tot;
                 if (writer) bnd[k] = x[k];
             }
         }
-        uint32_t blk_next = __ldg(reinterpret_cast<const unsigned int *>(obs));
-        int64_t next_boundary = a.seg_len;  // (a running counter: no 64-bit division in the loop)
-        for (int64_t blk_i = 0; blk_i < n_blocks; ++blk_i) {
-            const int64_t t0 = blk_i * kNorm;
+        // LL: the factor of a block is applied in the middle of the NEXT one - its sum and reciprocal have two sites
+        // to arrive; otherwise at once
+        F inv_pending = F(1);
+        F w[MT];  // alpha of the last site
+        if constexpr (LL) site.forward(x, w, p, 0xffffffffu, 0, sub);  // z(0) = pi A: a step with the emission row of ones
+        uint32_t blk_next = __ldg(obs);
+        int to_boundary = seg_blocks;  // blocks until the next segment boundary
+        const int last_word = (L - 1) / kNorm;
+        for (int bi = 0; bi < full_blocks; ++bi) {
             const uint32_t blk = blk_next;
-            if (blk_i + 1 < n_blocks) blk_next = __ldg(reinterpret_cast<const unsigned int *>(obs + t0 + kNorm));
-            // (one decision per block, not per site: a lone warp pays ~10 cycles for every branch)
-            if (t0 + kNorm <= a.L) {
+            blk_next = __ldg(obs + min(bi + 1, last_word));
 #pragma unroll
-                for (int j = 0; j < kNorm; ++j) forward_site<F, MT, T, false, NT>(x, p, pc, et, ObsWords<8>::byte_of(blk, j), sub);
-            } else {
-                for (int j = 0; j < int(a.L - t0); ++j) forward_site<F, MT, T, false, NT>(x, p, pc, et, ObsWords<8>::byte_of(blk, j), sub);
-            }
-            const F tot = pair_sum<F, MT, T>(x);
-            const F inv = fast_rcp<F>(tot);
+            for (int j = 0; j < kNorm; ++j) {
+                if (LL && j == kNorm / 2) {
 #pragma unroll
-            for (int k = 0; k < MT; ++k) x[k] *= inv;
-            acc += log2_of<F>(tot);
-            if ((blk_i & 3) == 3) {
-                ll += double(acc);
-                acc = F(0);
+                    for (int k = 0; k < MT; ++k) x[k] *= inv_pending;
+                }
+                site.forward(x, w, p, blk, j, sub);
             }
-            if (t0 + kNorm == next_boundary) {
-                // the vector entering the next segment (approximately normalised: good enough, the
-                // segment kernel rescales)
+            const F tot = site.total(x);
+            inv_pending = fast_rcp<F>(tot);
+            if constexpr (!LL) {
+#pragma unroll
+                for (int k = 0; k < MT; ++k) x[k] *= inv_pending;
+            }
+            ll += double(lg2_fast(tot));
+            if (--to_boundary == 0) {
+                // the vector entering the next segment (approximately normalised - in LL mode short of this
+                // block's factor, the decay over four sites: good enough, the segment kernel rescales)
                 bnd += M;
-                next_boundary += a.seg_len;
-                if (t0 + kNorm < a.L && writer) {
+                to_boundary = seg_blocks;
+                if ((bi + 1) * kNorm < L && writer) {
 #pragma unroll
-                    for (int k = 0; k < MT; ++k) bnd[k] = x[k];
+                    for (int k = 0; k < MT; ++k) bnd[k] = w[k];
                 }
             }
         }
-        // the reciprocal above is approximate: the last total is not exactly 1
-        ll = (ll + double(acc) + double(log2_of<F>(pair_sum<F, MT, T>(x)))) * 0.69314718055994530942;
+        if constexpr (LL) {
+#pragma unroll
+            for (int k = 0; k < MT; ++k) x[k] *= inv_pending;
+        }
+        for (int j = 0; j < tail; ++j) site.forward(x, w, p, blk_next, j, sub);
+        // the reciprocals are approximate: the last total is not exactly 1.  (LL: sum z(L) = sum alpha(L - 1) because
+        // the rows of A sum to one - to within 6e-8 in fp32, which is 6e-8 ABSOLUTE on the log-likelihood.)
+        ll = (ll + double(log2_of<F>(pair_sum<F, MT, T>(x)))) * 0.69314718055994530942;
         if (!(ll == ll) || ll > 1e300 || ll < -1e300) {
             if (sub == 0) atomicOr(a.err_flag, 2);
         }
@@ -1660,35 +1884,69 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) boundary_sweep_kernel(const Kern
 #pragma unroll
         for (int k = 0; k < MT; ++k) {
             beta[k] = F(1);
-            if (writer) bnd[G * M + k] = F(1);  // behind the last segment: the end of the chunk
+            if (writer) bnd[int64_t(G) * M + k] = F(1);  // behind the last segment: the end of the chunk
         }
-        uint32_t blk_next = __ldg(reinterpret_cast<const unsigned int *>(obs + (n_blocks - 1) * kNorm));
-        int64_t next_boundary = (G - 1) * a.seg_len;  // start of the last segment
-        bnd += G * M;
-        for (int64_t blk_i = n_blocks - 1; blk_i >= 0; --blk_i) {
-            const int64_t t0 = blk_i * kNorm;
-            const uint32_t blk = blk_next;
-            if (blk_i > 0) blk_next = __ldg(reinterpret_cast<const unsigned int *>(obs + t0 - kNorm));
-            if (t0 + kNorm <= a.L) {
+        bnd += int64_t(G) * M;
+        F inv_pending = F(1);
+        if (tail > 0) {
+            const uint32_t blk = __ldg(obs + full_blocks);
+            for (int j = tail - 1; j >= 0; --j) site.adjoint(beta, p, blk, j, sub);
+            inv_pending = fast_rcp<F>(site.total(beta));
+            if constexpr (!LL) {
 #pragma unroll
-                for (int j = kNorm - 1; j >= 0; --j) adjoint_only_site<F, MT, T, NT>(beta, p, et, ObsWords<8>::byte_of(blk, j), sub);
-            } else {
-                for (int j = int(a.L - t0) - 1; j >= 0; --j) adjoint_only_site<F, MT, T, NT>(beta, p, et, ObsWords<8>::byte_of(blk, j), sub);
+                for (int k = 0; k < MT; ++k) beta[k] *= inv_pending;
             }
-            const F inv = fast_rcp<F>(pair_sum<F, MT, T>(beta));
+        }
+        // blocks until the start of the last segment, counted from the last full block
+        int to_boundary = full_blocks - (G - 1) * seg_blocks;
+        if (to_boundary == 0) {  // the last segment is the ragged tail alone
+            bnd -= M;
+            to_boundary = seg_blocks;
+            if (full_blocks > 0 && writer) {
 #pragma unroll
-            for (int k = 0; k < MT; ++k) beta[k] *= inv;
-            if (t0 == next_boundary) {
+                for (int k = 0; k < MT; ++k) bnd[k] = beta[k];
+            }
+        }
+        uint32_t blk_next = full_blocks > 0 ? __ldg(obs + full_blocks - 1) : 0u;
+        for (int bi = full_blocks - 1; bi >= 0; --bi) {
+            const uint32_t blk = blk_next;
+            blk_next = __ldg(obs + max(bi - 1, 0));
+#pragma unroll
+            for (int j = kNorm - 1; j >= 0; --j) {
+                if (LL && j == kNorm / 2 - 1) {
+#pragma unroll
+                    for (int k = 0; k < MT; ++k) beta[k] *= inv_pending;
+                }
+                site.adjoint(beta, p, blk, j, sub);
+            }
+            inv_pending = fast_rcp<F>(site.total(beta));
+            if constexpr (!LL) {
+#pragma unroll
+                for (int k = 0; k < MT; ++k) beta[k] *= inv_pending;
+            }
+            if (--to_boundary == 0) {
                 // the adjoint vector behind the previous segment (any scale)
                 bnd -= M;
-                next_boundary -= a.seg_len;
-                if (t0 > 0 && writer) {
+                to_boundary = seg_blocks;
+                if (bi > 0 && writer) {
 #pragma unroll
                     for (int k = 0; k < MT; ++k) bnd[k] = beta[k];
                 }
             }
         }
     }
+}
+
+// Both sweeps in one launch: CTAs [0, sweep_fwd_ctas) run the forward sweep with TF lanes per pair, the others the
+// adjoint sweep with TB lanes per pair.  The layouts are chosen on the host so that, whenever possible, every warp
+// has a scheduler of its own (4 x 148 of them): two warps on one scheduler are issue bound and take twice as long
+// per site, and the launch ends with its slowest warp.
+template <typename F, int M, int TF, int TB, int NT, int MINB, bool LL>
+__global__ void __maxnreg__(max_regs(NT, MINB)) boundary_sweep_kernel(const KernelArgs a) {
+    if (int64_t(blockIdx.x) < a.sweep_fwd_ctas)
+        boundary_sweep_body<F, M / TF, TF, NT, LL && (TF >= 2), 0>(a, blockIdx.x);
+    else
+        boundary_sweep_body<F, M / TB, TB, NT, LL && (TB >= 2), 1>(a, int64_t(blockIdx.x) - a.sweep_fwd_ctas);
 }
 
 // ---------------------------------------------------------------------------------------------

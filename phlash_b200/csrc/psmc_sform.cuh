@@ -32,8 +32,8 @@
 // step in transfer_rows_kernel (three warps per scheduler) lost 4 % as well.
 //
 // Accuracy.  delta = fl(d e0) carries a SYSTEMATIC relative error of up to 6e-8 on the stay weight of a state, which
-// the gradient amplifies by two orders of magnitude (tests/test_scaled_recursion_math.py); measured against the fp64
-// oracle at 50 000 bins: ll 1.4e-7, gradient 1.2e-5 - inside the 1e-5 / 1e-4 bars, where psmc_loglik_kernel is at
+// the gradient amplifies by two orders of magnitude (tests/test_scaled_recursion_math.py); measured against the
+// fp64 CPU restatement at 50 000 bins: ll 1.4e-7, gradient 1.2e-5 - inside the 1e-5 / 1e-4 bars, where psmc_loglik_kernel is at
 // 1e-7 / 1.4e-6.
 //
 // Domain: v_k > 0 for k >= 1 and emis0_k > 0 (PSMCParams.from_dm clips everything to [1e-20, 1 - 1e-20],

@@ -232,6 +232,49 @@ def test_two_sweep_gradient_matches_oracle(M, L):
     assert np.all(dlog[:, :, 0, -1] == 0) and np.all(dlog[:, :, 2, -1] == 0) and np.all(dlog[:, :, 3, 0] == 0)
 
 
+@pytest.mark.parametrize("M,TF,TB,LL", [(8, 2, 2, 1), (8, 2, 2, 0), (16, 4, 4, 1), (16, 4, 2, 1), (16, 2, 2, 1),
+                                        (16, 4, 4, 0), (16, 1, 1, 0), (32, 8, 8, 1), (32, 8, 4, 1), (32, 4, 4, 1), (32, 4, 2, 1),
+                                        (32, 2, 2, 1), (32, 8, 8, 0)])
+def test_every_sweep_lane_layout(M, TF, TB, LL, monkeypatch):
+    """The sweeps choose their lane layout (lanes per pair, separately for the forward and the adjoint
+    direction, generic or low-latency site functions) by the number of pairs; every layout is forced here
+    through the experiment knobs, which are read when the kernel object is created."""
+    from test_gpu_parity import GRAD_RTOL, grad_close, oracle_eval
+
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    L = 2_531  # ragged last block, ragged last segment
+    data = rows_with_missing(3, L, seed=M + TF + 7 * TB)
+    pps, _, _ = orc.synth_particles(M, 37, seed=9)  # pairs do not fill the last warp of either direction
+    inds = np.array([1, 2, 0])
+    pa = np.broadcast_to(pps[:, None], (37, len(inds), 7, M)).copy()
+    ref_ll, ref_dlog = oracle_eval(data, inds, pa)
+    monkeypatch.setenv("PHB_SWEEP_TF", str(TF))
+    monkeypatch.setenv("PHB_SWEEP_TB", str(TB))
+    monkeypatch.setenv("PHB_SWEEP_LL", str(LL))
+    kern = _PSMCKernelBase(M, data)
+    kern.set_parallel_in_time(2)
+    ll, dlog = kern.evaluate(pa, inds, True)
+    want = f"boundary_sweep_kernel<float,TF={TF},TB={TB}" + (",LL>" if LL else ">")
+    assert want in kern.last_kernel_name, kern.last_kernel_name
+    np.testing.assert_allclose(ll, ref_ll, rtol=LL_RTOL)
+    grad_close(dlog, ref_dlog, GRAD_RTOL, f"sweep layout TF={TF} TB={TB} LL={LL}, M={M}")
+
+
+def test_sweep_layout_gives_every_warp_a_scheduler():
+    """2 500 pairs (the reference's S = 5 with 500 particles) at M = 16: four lanes per pair in both
+    directions would need 158 four-warp CTAs for 148 SMs; the picker narrows the adjoint sweep instead."""
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    data = rows_with_missing(4, 12_000, seed=5)
+    pps, _, _ = orc.synth_particles(16, 1, seed=4)
+    kern = _PSMCKernelBase(16, data)
+    for n_chunks, expect in ((1500, "TF=4,TB=4,LL"), (2500, "TF=4,TB=2,LL"), (4000, "TF=2,TB=2,LL"), (6000, "TF=1,TB=1>")):
+        pa = np.broadcast_to(pps[:1, None], (1, n_chunks, 7, 16)).copy()
+        kern.evaluate(pa, np.zeros(n_chunks, dtype=np.int64), True)
+        assert expect in kern.last_kernel_name, (n_chunks, kern.last_kernel_name)
+
+
 def test_two_sweep_is_chosen_between_operators_and_store_all():
     from phlash_b200.gpu import _PSMCKernelBase
 
