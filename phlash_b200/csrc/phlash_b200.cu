@@ -102,6 +102,7 @@ struct phb_kernel {
     DeviceBuffer term_io;                                     // device copies of the host entry's buffers
     DeviceBuffer transfer_rows, transfer_log;                 // parallel-in-time forward evaluation
     DeviceBuffer bnd_alpha, bnd_beta, seg_dlog;               // ... and gradient
+    DeviceBuffer sweep_ckpt;                                  // checkpoints left by the forward sweep for the segment passes
     DeviceBuffer uniform_stage;                               // parameter rows packed for the constant bank (psmc_uniform.cuh)
     int parallel_in_time = -1;  // -1 auto, 0 never, 1 whenever possible
     int store_all_mode = -1;  // -1 auto, 0 never, 1 whenever a store-all variant exists
@@ -112,7 +113,7 @@ struct phb_kernel {
     int escalate = 1;
     // experiment knobs, read from the environment ONCE when the object is created (never per call):
     // PHB_NT, PHB_STORE_ALL, PHB_PARALLEL_IN_TIME, PHB_PIT_SEGMENTS
-    int env_nt = 0, env_store_all = -2, env_pit = -2, env_pit_segments = 0, env_sweep_tf = 0, env_sweep_tb = 0, env_uniform = 1, env_sform = 0, env_sweep_ll = 1;
+    int env_nt = 0, env_store_all = -2, env_pit = -2, env_pit_segments = 0, env_sweep_tf = 0, env_sweep_tb = 0, env_uniform = 1, env_sform = 0, env_sweep_ll = 1, env_sweep_ckpt = 1;
     // phb_reserve(): the dispatch runs with dry = true - every scratch buffer is sized and every kernel
     // attribute set exactly as a real call would, but nothing is launched
     bool dry = false;
@@ -586,6 +587,12 @@ int try_two_sweep_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t
     if ((rc = k->seg_dlog.reserve(size_t(n_pairs) * n_seg * 7 * M * sizeof(float))) != PHB_OK) return rc;
     if ((rc = k->ckpt.reserve(size_t(grid) * (tv->NT / 32) * size_t(tv->ckpt_bytes_per_warp(seg_len)))) != PHB_OK) return rc;
     if ((rc = k->gacc.reserve(size_t(grid) * tv->NT * 6 * (tv->M / tv->T) * sizeof(double))) != PHB_OK) return rc;
+    // checkpoints of the segment passes, written by the forward sweep (64 B per pair and 8 sites: 1 GB for 2 500
+    // pairs of 50 500 sites); PHB_SWEEP_CKPT=0 or a budget of 8 GB leaves the segment passes to make their own
+    const int64_t ck_count = (a.L + tv->K - 1) / tv->K + 1;
+    const size_t ck_bytes = size_t(n_pairs) * ck_count * M * sizeof(float);
+    const bool ext_ck = k->env_sweep_ckpt != 0 && !is_sform(tv) && ck_bytes <= (size_t(8) << 30);
+    if (ext_ck && (rc = k->sweep_ckpt.reserve(ck_bytes)) != PHB_OK) return rc;
     if (k->occupancy.find(sweep_func) == k->occupancy.end()) {
         PHB_CUDA(cudaFuncSetAttribute(sweep_func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sweep_smem)));
         k->occupancy.emplace(sweep_func, 1);
@@ -603,6 +610,9 @@ int try_two_sweep_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t
     sa.seg_ctas = seg_ctas;
     sa.n_groups = n_groups;
     sa.sweep_fwd_ctas = fwd_ctas;
+    sa.ext_ck = ext_ck ? k->sweep_ckpt.ptr : nullptr;
+    sa.ext_ck_count = ck_count;
+    sa.ext_ck_blocks = tv->K / 4;
     void *kargs[] = {&sa};
     PHB_CUDA(cudaLaunchKernel(sweep_func, dim3(unsigned(sweep_ctas(*sw, n_pairs))), dim3(sw->NT), kargs, sweep_smem, stream));
     PHB_CUDA(cudaLaunchKernel(tv->func, dim3(unsigned(grid)), dim3(tv->NT), kargs, tv->smem, stream));
@@ -983,6 +993,7 @@ static int new_kernel(int M, int64_t N, int64_t L, int double_precision, int dev
     if (const char *v = getenv("PHB_SWEEP_TF")) k->env_sweep_tf = atoi(v);
     if (const char *v = getenv("PHB_SWEEP_TB")) k->env_sweep_tb = atoi(v);
     if (const char *v = getenv("PHB_SWEEP_LL")) k->env_sweep_ll = atoi(v);
+    if (const char *v = getenv("PHB_SWEEP_CKPT")) k->env_sweep_ckpt = atoi(v);
     if (const char *v = getenv("PHB_UNIFORM")) k->env_uniform = atoi(v);
     if (const char *v = getenv("PHB_SFORM")) k->env_sform = atoi(v);
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&k->d_data), size_t(N) * size_t(k->pitch));
@@ -993,7 +1004,7 @@ static int new_kernel(int M, int64_t N, int64_t L, int double_precision, int dev
     }
     for (DeviceBuffer *b : {&k->params, &k->inds, &k->ll, &k->dlog, &k->ckpt, &k->gacc, &k->xall, &k->sall, &k->split, &k->term_params,
                             &k->term_ll, &k->term_dlog, &k->term_sums, &k->term_io, &k->transfer_rows, &k->transfer_log, &k->bnd_alpha,
-                            &k->bnd_beta, &k->seg_dlog, &k->uniform_stage})
+                            &k->bnd_beta, &k->seg_dlog, &k->uniform_stage, &k->sweep_ckpt})
         b->counter = &k->allocations;
     if ((e = cudaStreamCreateWithFlags(&k->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaMalloc(reinterpret_cast<void **>(&k->d_iteration), sizeof(unsigned long long))) != cudaSuccess ||
@@ -1258,6 +1269,7 @@ void phb_destroy(phb_kernel *k) {
     k->bnd_beta.release();
     k->seg_dlog.release();
     k->uniform_stage.release();
+    k->sweep_ckpt.release();
     if (k->d_rowflag) cudaFree(k->d_rowflag);
     if (k->d_data) cudaFree(k->d_data);
     if (k->d_err) cudaFree(k->d_err);
@@ -1639,6 +1651,14 @@ int phb_loglik_warmup_host(phb_kernel *k, const void *params7, const int64_t *in
     return phb_sync(k);
 }
 
+}  // extern "C"
+// one warp per particle (forward) or per (particle, direction) (VJP), see psmc_params.cuh
+template <bool VJP> static void launch_params_kernel(const phb::ParamsArgs &a, int64_t n_items, cudaStream_t stream) {
+    const int per_cta = phb::params_items_per_cta(a.M);
+    phb::psmc_params_warp_kernel<VJP><<<unsigned((n_items + per_cta - 1) / per_cta), phb::params_warps_per_cta(a.M) * 32, phb::params_smem_bytes(a.M), stream>>>(a);
+}
+extern "C" {
+
 static int fill_params_args(phb_kernel *k, const double *x, int64_t B, const int32_t *epoch_widths, int n_epochs,
                             double theta, phb::ParamsArgs &a) {
     if (int rc = check_handle(k)) return rc;
@@ -1671,8 +1691,7 @@ int phb_params_from_particles(phb_kernel *k, const double *x, int64_t B, const i
     PHB_CUDA(cudaSetDevice(k->device));
     a.params7 = params7;
     if (k->dry) return PHB_OK;
-    const int threads = 64;
-    phb::psmc_params_forward_kernel<<<unsigned((B + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    launch_params_kernel<false>(a, B, static_cast<cudaStream_t>(stream));
     PHB_CUDA(cudaGetLastError());
     k->launches += 1;
     return PHB_OK;
@@ -1688,9 +1707,7 @@ int phb_params_vjp(phb_kernel *k, const double *x, int64_t B, const int32_t *epo
     a.cotangent = cotangent;
     a.grad_x = grad_x;
     if (k->dry) return PHB_OK;
-    const int threads = 64;
-    const int64_t n = B * a.P;
-    phb::psmc_params_vjp_kernel<<<unsigned((n + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    launch_params_kernel<true>(a, B * a.P, static_cast<cudaStream_t>(stream));
     PHB_CUDA(cudaGetLastError());
     k->launches += 1;
     return PHB_OK;
@@ -1974,8 +1991,7 @@ int phb_hmm_term_finish_device(phb_kernel *k, const double *x, int64_t B, const 
         pa.cot_stride = stride;
         pa.scale = weight;
         pa.grad_x = grad_x;
-        const int64_t n = B * pa.P;
-        phb::psmc_params_vjp_kernel<<<unsigned((n + threads - 1) / threads), threads, 0, st>>>(pa);
+        launch_params_kernel<true>(pa, B * pa.P, st);
         PHB_CUDA(cudaGetLastError());
         k->launches += 1;
     }

@@ -92,6 +92,12 @@ struct KernelArgs {
     const void *bnd_alpha;  // [B * S][G + 1][M] FLOAT: forward vector entering segment g (sum 1)
     const void *bnd_beta;   // [B * S][G + 1][M] FLOAT: adjoint vector behind segment g - 1 (any scale)
     void *seg_dlog;         // [B * S][segments of this launch][7][M] FLOAT
+    // Two-sweep path: the forward sweep also leaves the forward vector entering every K-site group (K = the
+    // checkpoint spacing of the gradient kernel that runs the segment passes), so that those start with the adjoint
+    // pass right away instead of re-running the forward recursion for their checkpoints.  nullptr = they make their own.
+    void *ext_ck;           // [B * S][ext_ck_count][M] FLOAT, record m = vector after site K m - 1 (record 0 unused)
+    int64_t ext_ck_count;   // ceil(L / K) + 1
+    int ext_ck_blocks;      // K / kNorm
 };
 
 // Pair enumeration of the store-all kernel: b major, position in the (sub-)list minor.  (psmc_loglik_kernel
@@ -694,13 +700,19 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                              : pi_g + pb * a.pistride_b + ps * a.pistride_s + sub * MT;
 
         // ------------------------------------------------------------------ pass 1: forward
+        // (segment mode after the sweeps: the checkpoints and the vector behind the segment are already there)
+        const IO *ext_ck = nullptr;
+        if constexpr (SEG) {
+            if (a.ext_ck != nullptr)
+                ext_ck = static_cast<const IO *>(a.ext_ck) + (chunk_pair * a.ext_ck_count + pseg * (a.seg_len / K)) * M + sub * MT;
+        }
         F x[MT];
 #pragma unroll
-        for (int k = 0; k < MT; ++k) x[k] = F(pi_p[k]);
+        for (int k = 0; k < MT; ++k) x[k] = F((ext_ck != nullptr ? pi_p + M : pi_p)[k]);
         double ll = 0.0;
         ObsWords<K> ow_next;
-        ow_next.load(obs, 0);
-        for (int64_t seg = 0; seg < n_seg; ++seg) {
+        if (ext_ck == nullptr) ow_next.load(obs, 0);
+        for (int64_t seg = 0; seg < (ext_ck != nullptr ? 0 : n_seg); ++seg) {
             if (GRAD && seg > 0) {
 #pragma unroll
                 for (int q = 0; q < QN; ++q) ck[(seg * QN + q) * 32] = pack(&x[q * W]);
@@ -784,7 +796,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                 const ObsWords<K> ow = ow_ahead;
                 if (seg > 0) {
                     ow_ahead.load(obs, (seg - 1) * K);
-                    if (seg > 1) prefetch_l2(&ck[(seg - 1) * QN * 32]);
+                    if (seg > 1) prefetch_l2(ext_ck != nullptr ? static_cast<const void *>(ext_ck + (seg - 1) * M) : &ck[(seg - 1) * QN * 32]);
                 }
                 const int len = int(min(int64_t(K), L - seg * K));
                 // re-run the forward steps of this segment, keeping every input vector
@@ -792,6 +804,9 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                 if (seg == 0) {
 #pragma unroll
                     for (int k = 0; k < MT; ++k) xs[k] = F(pi_p[k]);
+                } else if (ext_ck != nullptr) {
+#pragma unroll
+                    for (int k = 0; k < MT; ++k) xs[k] = F(ext_ck[seg * M + k]);
                 } else {
 #pragma unroll
                     for (int q = 0; q < QN; ++q) unpack<F>(ck[(seg * QN + q) * 32], &xs[q * W]);
@@ -1833,6 +1848,9 @@ __device__ __forceinline__ void boundary_sweep_body(const KernelArgs &a, const i
         if constexpr (LL) site.forward(x, w, p, 0xffffffffu, 0, sub);  // z(0) = pi A: a step with the emission row of ones
         uint32_t blk_next = __ldg(obs);
         int to_boundary = seg_blocks;  // blocks until the next segment boundary
+        // checkpoints for the segment passes: the vector after every K-th site (any scale), see KernelArgs::ext_ck
+        F *ckp = a.ext_ck != nullptr && writer ? static_cast<F *>(a.ext_ck) + (pair * a.ext_ck_count + 1) * M + sub * MT : nullptr;
+        int to_ck = a.ext_ck_blocks;
         const int last_word = (L - 1) / kNorm;
         for (int bi = 0; bi < full_blocks; ++bi) {
             const uint32_t blk = blk_next;
@@ -1852,6 +1870,15 @@ __device__ __forceinline__ void boundary_sweep_body(const KernelArgs &a, const i
                 for (int k = 0; k < MT; ++k) x[k] *= inv_pending;
             }
             ll += double(lg2_fast(tot));
+            if (--to_ck == 0) {
+                to_ck = a.ext_ck_blocks;
+                if (ckp != nullptr) {
+#pragma unroll
+                    for (int q = 0; q < MT / Vec<F>::W; ++q)
+                        *reinterpret_cast<typename Vec<F>::type *>(ckp + q * Vec<F>::W) = pack(&w[q * Vec<F>::W]);
+                    ckp += M;
+                }
+            }
             if (--to_boundary == 0) {
                 // the vector entering the next segment (approximately normalised - in LL mode short of this
                 // block's factor, the decay over four sites: good enough, the segment kernel rescales)
@@ -1868,6 +1895,13 @@ __device__ __forceinline__ void boundary_sweep_body(const KernelArgs &a, const i
             for (int k = 0; k < MT; ++k) x[k] *= inv_pending;
         }
         for (int j = 0; j < tail; ++j) site.forward(x, w, p, blk_next, j, sub);
+        if (writer) {
+            // behind the last segment: the vector after the last site (the segment passes that take their checkpoints
+            // from this sweep close their adjoint vector against it)
+            F *last = static_cast<F *>(const_cast<void *>(a.bnd_alpha)) + (pair * (G + 1) + G) * M + sub * MT;
+#pragma unroll
+            for (int k = 0; k < MT; ++k) last[k] = w[k];
+        }
         // the reciprocals are approximate: the last total is not exactly 1.  (LL: sum z(L) = sum alpha(L - 1) because
         // the rows of A sum to one - to within 6e-8 in fp32, which is 6e-8 ABSOLUTE on the log-likelihood.)
         ll = (ll + double(log2_of<F>(pair_sum<F, MT, T>(x)))) * 0.69314718055994530942;

@@ -9,9 +9,9 @@
 // The reference builds the dense M x M matrix (an O(M^3) masked product for the upper triangle,
 // transition.py:69-83) and then reads three diagonals and the first row off it
 // (params.py:45-50).  Only those O(M) entries are computed here, and only ROW 0 of the cumulative
-// 3x3 products (transition.py:51-56) is carried, so the state per thread is O(1).
+// 3x3 products (transition.py:51-56) is carried.
 //
-// Differentiation: forward mode with ONE tangent direction per thread (Dual: value + derivative
+// Differentiation: forward mode with ONE tangent direction per warp (Dual: value + derivative
 // w.r.t. x[dir]); a launch over (particle, direction) gives the whole Jacobian, contracted on the
 // fly with the incoming cotangent.  Selections (where / clip / isclose guards) pass the tangent of
 // the selected branch and zero where a value is clipped, like JAX.
@@ -66,8 +66,12 @@ __device__ __forceinline__ Dual expm1inv(Dual x) {
     return 1.0 / dexpm1(x);
 }
 
-// row0 <- row0 * expQ(r, c, n = 2)   (transition.py:9-34; only the product with a row is needed)
-__device__ __forceinline__ void apply_expQ(Dual (&row)[3], Dual r, Dual c) {
+// expQ(r, c, n = 2) (transition.py:9-34): the four entries that are not implied by unit row sums
+struct ExpQ {
+    Dual p11, p12, p21, p22;
+};
+__device__ __forceinline__ ExpQ identity_expQ() { return ExpQ{mk(1.0), mk(0.0), mk(0.0), mk(1.0)}; }
+__device__ __forceinline__ ExpQ expQ_matrix(Dual r, Dual c) {
     const double n = 2.0;
     const Dual disc = dsqrt((c * n) * (c * n) - 2.0 * c * (n - 2.0) * r + r * r) / 2.0;
     const Dual mean = (r + c * n) / 2.0;
@@ -80,142 +84,18 @@ __device__ __forceinline__ void apply_expQ(Dual (&row)[3], Dual r, Dual c) {
     } else {
         t2 = (dexp(disc - mean) - dexp(-(disc + mean))) / 2.0 / disc;
     }
-    const Dual p11 = t1 - half * t2, p12 = r * t2, p21 = c * t2, p22 = t1 + half * t2;
-    const Dual p13 = 1.0 - p11 - p12, p23 = 1.0 - p21 - p22;
+    return ExpQ{t1 - half * t2, r * t2, c * t2, t1 + half * t2};
+}
+// row <- row * P  (the third row of P is (0, 0, 1))
+__device__ __forceinline__ void apply_expQ(Dual (&row)[3], const ExpQ &m) {
+    const Dual p13 = 1.0 - m.p11 - m.p12, p23 = 1.0 - m.p21 - m.p22;
     const Dual a = row[0], b = row[1];
-    row[0] = a * p11 + b * p21;
-    row[1] = a * p12 + b * p22;
+    row[0] = a * m.p11 + b * m.p21;
+    row[1] = a * m.p12 + b * m.p22;
     row[2] = a * p13 + b * p23 + row[2];
 }
 
 constexpr int kMaxM = 64;
-
-// Everything for one particle and one tangent direction.  out[g * M + m] (value and tangent).
-// widths: epoch widths of the PSMC pattern (sum = M); x: [2 + n_epochs + 1]; dir < 0: no tangent.
-__device__ inline void particle_to_params(const double *x, int dir, const int *widths, int n_epochs, int M,
-                                          double theta, Dual *out /* [7 * M] */) {
-    auto in = [&](int i) { return mk(x[i], i == dir ? 1.0 : 0.0); };
-    // ---- MCMCParams.to_dm (params.py:94-131)
-    const Dual t1 = dexp(in(0));
-    const Dual tM = t1 + dexp(in(1));
-    const Dual log_ratio = mk(log(tM.v / t1.v), tM.d / tM.v - t1.d / t1.v);
-    Dual t[kMaxM], c[kMaxM];
-    t[0] = mk(0.0);
-    for (int i = 1; i < M; ++i) {
-        // geomspace(t1, tM, M - 1)[i - 1]; end points exact like numpy
-        if (i == 1) t[i] = t1;
-        else if (i == M - 1) t[i] = tM;
-        else t[i] = t1 * dexp(log_ratio * (double(i - 1) / double(M - 2)));
-    }
-    {
-        int m = 0;
-        for (int e = 0; e < n_epochs; ++e) {
-            const Dual z = in(2 + e);
-            // softplus(z) = log1p(exp(z)), derivative sigmoid(z)
-            const double sp = z.v > 30.0 ? z.v : log1p(exp(z.v));
-            const Dual ce = mk(sp, z.d / (1.0 + exp(-z.v)));
-            for (int w = 0; w < widths[e]; ++w) c[m++] = ce;
-        }
-    }
-    Dual rho;
-    {
-        const Dual z = in(2 + n_epochs);
-        const double sg = 1.0 / (1.0 + exp(-z.v));
-        rho = mk(theta * (0.1 + 9.9 * sg), theta * 9.9 * sg * (1.0 - sg) * z.d);
-    }
-    // ---- SizeHistory.ect (size_history.py:170-193)
-    Dual ect[kMaxM];
-    for (int k = 0; k < M - 1; ++k) {
-        const Dual dt = t[k + 1] - t[k];
-        if (close_to_zero(c[k].v)) ect[k] = (t[k] + t[k + 1]) / 2.0;
-        else if (isinf(c[k].v) || c[k].v > 100.0) ect[k] = t[k];
-        else ect[k] = 1.0 / c[k] + t[k] - dt * expm1inv(c[k] * dt);
-    }
-    ect[M - 1] = t[M - 1] + 1.0 / c[M - 1];
-    for (int k = 0; k < M; ++k) ect[k] = dmax(ect[k], 1e-20);
-    // ---- emissions and pi (params.py:36-43, size_history.py:123-138)
-    const double lo = 1e-20, hi = 1.0 - 1e-20;
-    for (int k = 0; k < M; ++k) {
-        const Dual ue = theta * ect[k];
-        out[4 * M + k] = dclip(dexp(-ue), lo, hi);
-        out[5 * M + k] = dclip(-dexpm1(-ue), lo, hi);
-    }
-    {
-        // surv = [S_0, ..., S_{M-2}, 0] with S_k = exp(-sum_{i<=k} c_i dt_i);  pi[i] = surv[i-1] - surv[i]
-        // for i >= 1 and pi[0] = 1 - sum of the others
-        Dual hazard = mk(0.0), prev = mk(0.0), rest = mk(0.0);
-        for (int k = 0; k < M - 1; ++k) {
-            hazard = hazard + c[k] * (t[k + 1] - t[k]);
-            const Dual s_k = dexp(-hazard);
-            if (k >= 1) {
-                out[6 * M + k] = prev - s_k;
-                rest = rest + out[6 * M + k];
-            }
-            prev = s_k;
-        }
-        out[6 * M + (M - 1)] = prev;  // S_{M-2} - 0
-        rest = rest + prev;
-        out[6 * M + 0] = 1.0 - rest;
-        for (int k = 0; k < M; ++k) out[6 * M + k] = dclip(out[6 * M + k], lo, hi);
-    }
-    // ---- transition bands (transition.py:37-85 restricted to what params.py:45-50 reads)
-    Dual row[3] = {mk(1.0), mk(0.0), mk(0.0)};
-    Dual sub[kMaxM], diag[kMaxM], p_float[kMaxM], p_pass[kMaxM], p_coal[kMaxM];
-    Dual at_t2 = mk(0.0);  // P_t[k][0, 2]
-    for (int k = 0; k < M; ++k) {
-        // first half of interval k: t_k -> ect_k at rate c_k
-        {
-            const Dual step = ect[k] - t[k];
-            if (!close_to_zero(step.v)) apply_expQ(row, 2.0 * step * rho, step * c[k]);
-        }
-        const Dual e0 = row[0], e1 = row[1], e2 = row[2];
-        Dual back, stay;
-        if (k < M - 1) {
-            const Dual left = (t[k + 1] - ect[k]) * c[k];
-            back = -dexpm1(-left);
-            stay = dexp(-left);
-        } else {
-            back = mk(1.0);
-            stay = mk(0.0);
-        }
-        diag[k] = e0 + e1 * back + e2 - at_t2;
-        p_float[k] = dclip(e1 * stay, 1e-8, 1.0 - 1e-8);
-        if (k < M - 1) {
-            const Dual dtc = (t[k + 1] - t[k]) * c[k];
-            p_pass[k] = dclip(dexp(-dtc), 1e-8, 1.0 - 1e-8);
-            p_coal[k] = dclip(-dexpm1(-dtc), 1e-8, 1.0 - 1e-8);
-            // second half: ect_k -> t_{k+1}
-            const Dual step = t[k + 1] - ect[k];
-            if (!close_to_zero(step.v)) apply_expQ(row, 2.0 * step * rho, step * c[k]);
-            sub[k] = row[2] - at_t2;  // every entry below the diagonal in column k
-            at_t2 = row[2];
-        } else {
-            p_pass[k] = dclip(mk(0.0), 1e-8, 1.0 - 1e-8);
-            p_coal[k] = dclip(mk(1.0), 1e-8, 1.0 - 1e-8);
-            // absorbing step: P_t[M][0, 2] = total mass of the row
-            sub[k] = (row[0] + row[1] + row[2]) - at_t2;
-        }
-    }
-    // ---- PSMCParams.from_dm (params.py:44-55): clip A, then b, d, u, v
-    for (int k = 0; k < M; ++k) {
-        out[0 * M + k] = k < M - 1 ? dclip(sub[k], lo, hi) : mk(0.0);
-        out[1 * M + k] = dclip(diag[k], lo, hi);
-    }
-    // first row of A above the diagonal: A[0, j] = p_float[0] * prod_{0<l<j} p_pass[l] * p_coal[j]
-    Dual run = p_float[0];
-    const Dual a01 = dclip(run * p_coal[1], lo, hi);
-    out[3 * M + 0] = mk(0.0);
-    out[2 * M + (M - 1)] = mk(0.0);
-    for (int j = 1; j < M; ++j) {
-        const Dual a0j = dclip(run * p_coal[j], lo, hi);
-        out[3 * M + j] = a0j / a01;  // v[j]
-        run = run * p_pass[j];
-    }
-    for (int i = 0; i < M - 1; ++i) {
-        const Dual sup = dclip(p_float[i] * p_coal[i + 1], lo, hi);  // A[i, i+1]
-        out[2 * M + i] = sup / out[3 * M + i + 1];                   // u[i] = A[i, i+1] / v[i+1]
-    }
-}
 
 struct ParamsArgs {
     const double *x;     // [B, P]
@@ -236,40 +116,229 @@ struct ParamsArgs {
     double scale;
 };
 
-// one thread per particle
-__global__ void psmc_params_forward_kernel(const ParamsArgs a) {
-    const int64_t b = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (b >= a.B) return;
-    Dual out[7 * kMaxM];
-    particle_to_params(a.x + b * a.P, -1, a.widths, a.n_epochs, a.M, a.theta, out);
-    const int n = 7 * a.M;
-    if (a.out_double) {
-        double *dst = static_cast<double *>(a.params7) + b * n;
-        for (int i = 0; i < n; ++i) dst[i] = out[i].v;
-    } else {
-        float *dst = static_cast<float *>(a.params7) + b * n;
-        for (int i = 0; i < n; ++i) dst[i] = float(out[i].v);
-    }
-}
+// One group of LPI = min(32, M rounded up to a power of two) lanes per particle (forward) or per (particle, tangent
+// direction) (VJP) - a whole warp from M = 32 on, two items per warp at M = 16; lane l of the group owns states
+// l, l + 32.
+//
+// The expensive part of the construction - two 3x3 matrix exponentials per state, each a square root and four
+// double-precision exponentials on dual numbers - does not depend on the other states: the lanes compute them side by
+// side.  What is sequential (the running row of the cumulative 3x3 products, the cumulative hazard, the running
+// product of the pass probabilities) is a walk over M states with a handful of multiply-adds each; every lane walks
+// it redundantly from shared memory.  The first version ran the whole chain in one thread per particle / direction:
+// 0.10 + 0.13 ms of every likelihood step, a fifth of the step on eight GPUs (profiles/r02_launches_step_S1.csv).
+constexpr int kParamArrays = 22;   // Dual arrays of M entries per warp, see the offsets below
+constexpr int kStatesPerLane = kMaxM / 32;
+inline int params_lanes_per_item(int M) { return M >= 32 ? 32 : M > 8 ? 16 : M > 4 ? 8 : 4; }
+inline int params_warps_per_cta(int M) { return M > 32 ? 2 : 4; }
+inline int params_items_per_cta(int M) { return params_warps_per_cta(M) * (32 / params_lanes_per_item(M)); }
+inline size_t params_smem_bytes(int M) { return size_t(params_items_per_cta(M)) * kParamArrays * M * sizeof(Dual); }
 
-// one thread per (particle, direction): grad_x[b, p] = sum_{g,m} cot[g,m] * d log(theta[g,m]) / d x_p
-__global__ void psmc_params_vjp_kernel(const ParamsArgs a) {
-    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (idx >= a.B * a.P) return;
-    const int64_t b = idx / a.P;
-    const int dir = int(idx % a.P);
-    Dual out[7 * kMaxM];
-    particle_to_params(a.x + b * a.P, dir, a.widths, a.n_epochs, a.M, a.theta, out);
-    const int n = 7 * a.M;
-    double acc = 0.0;
-    for (int i = 0; i < n; ++i) {
-        double cot;
-        if (a.cot_stride > 0) cot = static_cast<const double *>(a.cotangent)[b * a.cot_stride + 1 + i];
-        else cot = a.out_double ? static_cast<const double *>(a.cotangent)[b * n + i]
-                                : double(static_cast<const float *>(a.cotangent)[b * n + i]);
-        if (out[i].v != 0.0) acc += cot * out[i].d / out[i].v;
+template <bool VJP> __global__ void psmc_params_warp_kernel(const ParamsArgs a) {
+    extern __shared__ __align__(16) unsigned char params_smem[];
+    const int M = a.M, n_epochs = a.n_epochs;
+    const int lpi = M >= 32 ? 32 : M > 8 ? 16 : M > 4 ? 8 : 4;  // lanes per item
+    const int lane = threadIdx.x % lpi, slot = threadIdx.x / lpi;
+    const int64_t n_items = VJP ? a.B * a.P : a.B;
+    const int64_t item_raw = int64_t(blockIdx.x) * (blockDim.x / lpi) + slot;
+    const bool valid = item_raw < n_items;
+    const int64_t item = valid ? item_raw : n_items - 1;  // idle groups shadow the last item (the warp synchronises as a whole)
+    const int64_t b = VJP ? item / a.P : item;
+    const int dir = VJP ? int(item % a.P) : -1;
+    const double theta = a.theta;
+    const double *x = a.x + b * a.P;
+    auto in = [&](int i) { return mk(x[i], i == dir ? 1.0 : 0.0); };
+    Dual *sm = reinterpret_cast<Dual *>(params_smem) + size_t(slot) * kParamArrays * M;
+    Dual *T_ = sm, *C_ = sm + M, *HZ = sm + 2 * M, *PP = sm + 3 * M, *PC = sm + 4 * M, *PPFX = sm + 5 * M, *E0 = sm + 6 * M,
+         *E1 = sm + 7 * M, *E2 = sm + 8 * M, *R2 = sm + 9 * M, *PF = sm + 10 * M, *SV = sm + 11 * M, *V_ = sm + 12 * M,
+         *P1 = sm + 13 * M /* [4][M] */, *P2 = sm + 17 * M /* [4][M] */;
+    // (22 = 13 + 4 + 4 + 1 spare)
+
+    // ---- MCMCParams.to_dm (params.py:94-131): every lane computes the scalars, its own states of t and c
+    const Dual t1 = dexp(in(0));
+    const Dual tM = t1 + dexp(in(1));
+    const Dual log_ratio = mk(log(tM.v / t1.v), tM.d / tM.v - t1.d / t1.v);
+    Dual rho;
+    {
+        const Dual z = in(2 + n_epochs);
+        const double sg = 1.0 / (1.0 + exp(-z.v));
+        rho = mk(theta * (0.1 + 9.9 * sg), theta * 9.9 * sg * (1.0 - sg) * z.d);
     }
-    a.grad_x[idx] = a.cot_stride > 0 ? a.scale * acc : acc;
+    for (int k = lane; k < M; k += 32) {
+        // geomspace(t1, tM, M - 1)[k - 1]; end points exact like numpy
+        Dual tk;
+        if (k == 0) tk = mk(0.0);
+        else if (k == 1) tk = t1;
+        else if (k == M - 1) tk = tM;
+        else tk = t1 * dexp(log_ratio * (double(k - 1) / double(M - 2)));
+        T_[k] = tk;
+        int e = 0, upto = a.widths[0];
+        while (k >= upto && e + 1 < n_epochs) upto += a.widths[++e];
+        const Dual z = in(2 + e);
+        // softplus(z) = log1p(exp(z)), derivative sigmoid(z)
+        const double sp = z.v > 30.0 ? z.v : log1p(exp(z.v));
+        C_[k] = mk(sp, z.d / (1.0 + exp(-z.v)));
+    }
+    __syncwarp();
+
+    // ---- per state: ect (size_history.py:170-193), emissions (params.py:36-43), the two half-interval
+    //      exponentials and the pass / coalescence probabilities of the interval (transition.py:37-85)
+    const double lo = 1e-20, hi = 1.0 - 1e-20;
+    Dual out[kStatesPerLane][7];
+    Dual back[kStatesPerLane], stay[kStatesPerLane];
+#pragma unroll
+    for (int s = 0; s < kStatesPerLane; ++s) {
+        const int k = lane + 32 * s;
+        if (k >= M) continue;
+        const Dual tk = T_[k], ck = C_[k];
+        const bool last = k == M - 1;
+        const Dual tk1 = last ? tk : T_[k + 1];
+        Dual ect;
+        if (last) {
+            ect = tk + 1.0 / ck;
+        } else {
+            const Dual dt = tk1 - tk;
+            if (close_to_zero(ck.v)) ect = (tk + tk1) / 2.0;
+            else if (isinf(ck.v) || ck.v > 100.0) ect = tk;
+            else ect = 1.0 / ck + tk - dt * expm1inv(ck * dt);
+        }
+        ect = dmax(ect, 1e-20);
+        const Dual ue = theta * ect;
+        out[s][4] = dclip(dexp(-ue), lo, hi);
+        out[s][5] = dclip(-dexpm1(-ue), lo, hi);
+        // first half of the interval: t_k -> ect_k at rate c_k
+        ExpQ m1 = identity_expQ();
+        {
+            const Dual step = ect - tk;
+            if (!close_to_zero(step.v)) m1 = expQ_matrix(2.0 * step * rho, step * ck);
+        }
+        P1[0 * M + k] = m1.p11, P1[1 * M + k] = m1.p12, P1[2 * M + k] = m1.p21, P1[3 * M + k] = m1.p22;
+        ExpQ m2 = identity_expQ();
+        if (!last) {
+            const Dual left = (tk1 - ect) * ck;
+            back[s] = -dexpm1(-left);
+            stay[s] = dexp(-left);
+            const Dual dtc = (tk1 - tk) * ck;
+            HZ[k] = dtc;
+            PP[k] = dclip(dexp(-dtc), 1e-8, 1.0 - 1e-8);
+            PC[k] = dclip(-dexpm1(-dtc), 1e-8, 1.0 - 1e-8);
+            // second half: ect_k -> t_{k+1}
+            const Dual step = tk1 - ect;
+            if (!close_to_zero(step.v)) m2 = expQ_matrix(2.0 * step * rho, step * ck);
+        } else {
+            back[s] = mk(1.0);
+            stay[s] = mk(0.0);
+            HZ[k] = mk(0.0);
+            PP[k] = dclip(mk(0.0), 1e-8, 1.0 - 1e-8);
+            PC[k] = dclip(mk(1.0), 1e-8, 1.0 - 1e-8);
+        }
+        P2[0 * M + k] = m2.p11, P2[1 * M + k] = m2.p12, P2[2 * M + k] = m2.p21, P2[3 * M + k] = m2.p22;
+    }
+    __syncwarp();
+
+    // ---- the sequential part, walked by every lane: row 0 of the cumulative products (E0..E2 after the first half
+    //      of interval k, R2 = its third entry after the second half), the cumulative hazard, the running product of
+    //      the pass probabilities (PPFX[j] = prod_{0 < l < j} p_pass[l])
+    {
+        Dual row[3] = {mk(1.0), mk(0.0), mk(0.0)};
+        Dual hazard = mk(0.0), run = mk(1.0);
+        for (int k = 0; k < M; ++k) {
+            apply_expQ(row, ExpQ{P1[0 * M + k], P1[1 * M + k], P1[2 * M + k], P1[3 * M + k]});
+            const Dual r0 = row[0], r1 = row[1], r2 = row[2];
+            if (k < M - 1) apply_expQ(row, ExpQ{P2[0 * M + k], P2[1 * M + k], P2[2 * M + k], P2[3 * M + k]});
+            hazard = hazard + HZ[k];
+            const Dual run_k = run;
+            if (k >= 1) run = run * PP[k];
+            if (lane == 0) {
+                E0[k] = r0, E1[k] = r1, E2[k] = r2;
+                R2[k] = row[2];
+                SV[k] = hazard;  // the survival function is exponentiated below, in parallel
+                PPFX[k] = run_k;
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- per state again: transition bands, survival
+#pragma unroll
+    for (int s = 0; s < kStatesPerLane; ++s) {
+        const int k = lane + 32 * s;
+        if (k >= M) continue;
+        const Dual e0 = E0[k], e1 = E1[k], e2 = E2[k];
+        const Dual at_t2 = k > 0 ? R2[k - 1] : mk(0.0);  // P_t[k][0, 2]
+        const Dual diag = e0 + e1 * back[s] + e2 - at_t2;
+        PF[k] = dclip(e1 * stay[s], 1e-8, 1.0 - 1e-8);
+        // every entry below the diagonal in column k; absorbing last step: the total mass of the row
+        const Dual sub = k < M - 1 ? R2[k] - at_t2 : (e0 + e1 + e2) - at_t2;
+        // ---- PSMCParams.from_dm (params.py:44-55): clip A, then b, d, u, v
+        out[s][0] = k < M - 1 ? dclip(sub, lo, hi) : mk(0.0);
+        out[s][1] = dclip(diag, lo, hi);
+    }
+    // survival S_k = exp(-hazard up to interval k) in place (each entry is read and written by its own lane)
+    for (int k = lane; k < M - 1; k += 32) SV[k] = dexp(-SV[k]);
+    __syncwarp();
+
+    // ---- pi (size_history.py:123-138): pi[i] = S_{i-1} - S_i, pi[M-1] = S_{M-2}, pi[0] = 1 - sum of the others
+    Dual rest = mk(0.0);
+    for (int k = 1; k < M - 1; ++k) rest = rest + (SV[k - 1] - SV[k]);
+    rest = rest + SV[M - 2];
+    // first row of A above the diagonal: A[0, j] = p_float[0] * prod_{0<l<j} p_pass[l] * p_coal[j]
+    const Dual a01 = dclip(PF[0] * PC[1], lo, hi);
+#pragma unroll
+    for (int s = 0; s < kStatesPerLane; ++s) {
+        const int k = lane + 32 * s;
+        if (k >= M) continue;
+        Dual pi;
+        if (k == 0) pi = 1.0 - rest;
+        else if (k == M - 1) pi = SV[M - 2];
+        else pi = SV[k - 1] - SV[k];
+        out[s][6] = dclip(pi, lo, hi);
+        Dual v = mk(0.0);
+        if (k >= 1) v = dclip(PF[0] * PPFX[k] * PC[k], lo, hi) / a01;
+        out[s][3] = v;
+        V_[k] = v;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < kStatesPerLane; ++s) {
+        const int k = lane + 32 * s;
+        if (k >= M) continue;
+        // u[i] = A[i, i+1] / v[i+1]
+        out[s][2] = k < M - 1 ? dclip(PF[k] * PC[k + 1], lo, hi) / V_[k + 1] : mk(0.0);
+    }
+
+    // ---- results
+    if constexpr (!VJP) {
+#pragma unroll
+        for (int s = 0; s < kStatesPerLane; ++s) {
+            const int k = lane + 32 * s;
+            if (k >= M || !valid) continue;
+#pragma unroll
+            for (int g = 0; g < 7; ++g) {
+                if (a.out_double) static_cast<double *>(a.params7)[(b * 7 + g) * M + k] = out[s][g].v;
+                else static_cast<float *>(a.params7)[(b * 7 + g) * M + k] = float(out[s][g].v);
+            }
+        }
+    } else {
+        // grad_x[b, dir] = sum_{g,m} cot[g,m] * d log(theta[g,m]) / d x_dir
+        double acc = 0.0;
+        const int n = 7 * M;
+#pragma unroll
+        for (int s = 0; s < kStatesPerLane; ++s) {
+            const int k = lane + 32 * s;
+            if (k >= M) continue;
+#pragma unroll
+            for (int g = 0; g < 7; ++g) {
+                const int i = g * M + k;
+                double cot;
+                if (a.cot_stride > 0) cot = static_cast<const double *>(a.cotangent)[b * a.cot_stride + 1 + i];
+                else cot = a.out_double ? static_cast<const double *>(a.cotangent)[b * n + i]
+                                        : double(static_cast<const float *>(a.cotangent)[b * n + i]);
+                if (out[s][g].v != 0.0) acc += cot * out[s][g].d / out[s][g].v;
+            }
+        }
+        for (int o = lpi / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0 && valid) a.grad_x[item] = a.cot_stride > 0 ? a.scale * acc : acc;
+    }
 }
 
 // Per-particle sums over the chunks of a minibatch (the HMM term is additive over chunks once the

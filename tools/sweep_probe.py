@@ -57,7 +57,7 @@ for M, S, TF, TB, LL in CASES:
     per = {}
     for ev in prof.key_averages():
         name = ev.key
-        for tag in ("boundary_sweep", "psmc_loglik_kernel", "storeall", "transfer_rows", "chain_boundaries", "params_forward", "params_vjp"):
+        for tag in ("boundary_sweep", "psmc_loglik_kernel", "storeall", "transfer_rows", "chain_boundaries", "params_warp_kernel<false>", "params_warp_kernel<true>", "params_warp"):
             if tag in name:
                 per[tag] = round(per.get(tag, 0.0) + ev.device_time_total / 3 / 1000.0, 3)
     print(json.dumps({"M": M, "S": S, "forced": [TF, TB, LL], "step_ms": round(step_ms, 3), "kernels_ms": per, "value0": float(v[0]),
