@@ -552,6 +552,7 @@ constexpr int kNorm = 4;  // the forward vector is rescaled after every kNorm-th
 // observation / checkpoint load would see L2 or DRAM latency; a hint one segment ahead costs no
 // registers.
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // Observations of one K-site segment packed in 64-bit words (K = 8 or 16).
 template <int K> struct ObsWords {
@@ -796,7 +797,16 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                 const ObsWords<K> ow = ow_ahead;
                 if (seg > 0) {
                     ow_ahead.load(obs, (seg - 1) * K);
-                    if (seg > 1) prefetch_l2(ext_ck != nullptr ? static_cast<const void *>(ext_ck + (seg - 1) * M) : &ck[(seg - 1) * QN * 32]);
+                    if (seg > 1) {
+                        if (ext_ck != nullptr) {
+                            // this thread's record of the next group: MT values, one 32-byte sector per 8
+#pragma unroll
+                            for (int q = 0; q < (MT * int(sizeof(F)) + 31) / 32; ++q)
+                                prefetch_l1(reinterpret_cast<const char *>(ext_ck + (seg - 1) * M) + q * 32);
+                        } else {
+                            prefetch_l2(&ck[(seg - 1) * QN * 32]);
+                        }
+                    }
                 }
                 const int len = int(min(int64_t(K), L - seg * K));
                 // re-run the forward steps of this segment, keeping every input vector
@@ -805,8 +815,9 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
 #pragma unroll
                     for (int k = 0; k < MT; ++k) xs[k] = F(pi_p[k]);
                 } else if (ext_ck != nullptr) {
+                    // (16-byte aligned: records are M values long, a lane's part MT, both multiples of 4)
 #pragma unroll
-                    for (int k = 0; k < MT; ++k) xs[k] = F(ext_ck[seg * M + k]);
+                    for (int q = 0; q < QN; ++q) unpack<F>(reinterpret_cast<const V *>(ext_ck + seg * M)[q], &xs[q * W]);
                 } else {
 #pragma unroll
                     for (int q = 0; q < QN; ++q) unpack<F>(ck[(seg * QN + q) * 32], &xs[q * W]);
@@ -1645,19 +1656,22 @@ template <typename F, int MT, int T> __device__ __forceinline__ F pair_sum_flat(
 // front, nothing but two FMAs per state behind the shuffles - and needs a quarter fewer instructions than a step that
 // multiplies by the emission row last.  w = emis .* z = alpha(t) is a by-product (the segment boundaries store it).
 template <typename F, int MT, int T, int NT>
-__device__ __forceinline__ void forward_site_ll(F (&z)[MT], F (&w)[MT], const Params<F, MT> &p, const LaneMasks<F, T> &lm,
-                                                const EmisTable4<F, MT, NT> &et, uint32_t row_off) {
-    et.get(row_off, w);
+// (w comes in holding the emission row of the site - the caller loads it, one site ahead across block boundaries)
+__device__ __forceinline__ void forward_site_ll(F (&z)[MT], F (&w)[MT], const Params<F, MT> &p, const LaneMasks<F, T> &lm) {
 #pragma unroll
     for (int k = 0; k < MT; ++k) w[k] *= z[k];
-    // what the partners need from this lane
-    F tu[2] = {F(0), F(0)}, tx[2] = {F(0), F(0)};
+    // the lane's own prefix / suffix chains; their ends are what the partners need from this lane (a lone warp is
+    // bound by its instruction count: separate, shorter chains for the totals cost 2 MT instructions more)
+    F lp[MT + 1], ls[MT + 1];
+    lp[0] = F(0);
+    ls[MT] = F(0);
 #pragma unroll
-    for (int k = 0; k < MT; ++k) {
-        tu[k & 1] = fma(p.u[k], w[k], tu[k & 1]);
-        tx[k & 1] += w[k];
+    for (int i = 0; i < MT; ++i) {
+        const int k = i, j = MT - 1 - i;
+        lp[k + 1] = fma(p.u[k], w[k], lp[k]);
+        ls[j] = ls[j + 1] + w[j];
     }
-    const F my_u = tu[0] + tu[1], my_x = tx[0] + tx[1];
+    const F my_u = lp[MT], my_x = ls[0];
     F su[T - 1], sx[T - 1];
 #pragma unroll
     for (int o = 1; o < T; ++o) {
@@ -1666,19 +1680,8 @@ __device__ __forceinline__ void forward_site_ll(F (&z)[MT], F (&w)[MT], const Pa
     }
     // in the shadow of the shuffles: the lane's own part
     F loc[MT];
-    {
-        F lp = F(0), ls = F(0), suf[MT];
 #pragma unroll
-        for (int i = 0; i < MT; ++i) {
-            const int k = i, j = MT - 1 - i;
-            loc[k] = fma(p.v[k], lp, p.d[k] * w[k]);
-            lp = fma(p.u[k], w[k], lp);
-            suf[j] = ls;
-            ls += w[j];
-        }
-#pragma unroll
-        for (int k = 0; k < MT; ++k) loc[k] = fma(p.b[k], suf[k], loc[k]);
-    }
+    for (int k = 0; k < MT; ++k) loc[k] = fma(p.b[k], ls[k + 1], fma(p.v[k], lp[k], p.d[k] * w[k]));
     F pre = lm.before[0] * su[0], suf_off = lm.after[0] * sx[0];
 #pragma unroll
     for (int o = 2; o < T; ++o) {
@@ -1690,19 +1693,20 @@ __device__ __forceinline__ void forward_site_ll(F (&z)[MT], F (&w)[MT], const Pa
 }
 
 template <typename F, int MT, int T, int NT>
-__device__ __forceinline__ void adjoint_only_site_ll(F (&beta)[MT], const Params<F, MT> &p, const LaneMasks<F, T> &lm,
-                                                     const EmisTable4<F, MT, NT> &et, uint32_t row_off) {
-    F w[MT];
-    et.get(row_off, w);
+// (w comes in holding the emission row of the site)
+__device__ __forceinline__ void adjoint_only_site_ll(F (&beta)[MT], F (&w)[MT], const Params<F, MT> &p, const LaneMasks<F, T> &lm) {
 #pragma unroll
     for (int k = 0; k < MT; ++k) w[k] *= beta[k];
-    F tq[2] = {F(0), F(0)}, tb[2] = {F(0), F(0)};
+    F lb[MT + 1], lq[MT + 1];
+    lb[0] = F(0);
+    lq[MT] = F(0);
 #pragma unroll
-    for (int k = 0; k < MT; ++k) {
-        tq[k & 1] = fma(p.v[k], w[k], tq[k & 1]);
-        tb[k & 1] = fma(p.b[k], w[k], tb[k & 1]);
+    for (int i = 0; i < MT; ++i) {
+        const int k = i, j = MT - 1 - i;
+        lb[k + 1] = fma(p.b[k], w[k], lb[k]);
+        lq[j] = fma(p.v[j], w[j], lq[j + 1]);
     }
-    const F my_q = tq[0] + tq[1], my_b = tb[0] + tb[1];
+    const F my_q = lq[0], my_b = lb[MT];
     F sq[T - 1], sb[T - 1];
 #pragma unroll
     for (int o = 1; o < T; ++o) {
@@ -1710,19 +1714,8 @@ __device__ __forceinline__ void adjoint_only_site_ll(F (&beta)[MT], const Params
         sb[o - 1] = __shfl_xor_sync(0xffffffffu, my_b, o, T);
     }
     F loc[MT];
-    {
-        F lb = F(0), lq = F(0), tailq[MT];
 #pragma unroll
-        for (int i = 0; i < MT; ++i) {
-            const int k = i, j = MT - 1 - i;
-            loc[k] = fma(p.d[k], w[k], lb);
-            lb = fma(p.b[k], w[k], lb);
-            tailq[j] = lq;
-            lq = fma(p.v[j], w[j], lq);
-        }
-#pragma unroll
-        for (int k = 0; k < MT; ++k) loc[k] = fma(p.u[k], tailq[k], loc[k]);
-    }
+    for (int k = 0; k < MT; ++k) loc[k] = fma(p.u[k], lq[k + 1], fma(p.d[k], w[k], lb[k]));
     F off_q = lm.after[0] * sq[0], off_b = lm.before[0] * sb[0];
 #pragma unroll
     for (int o = 2; o < T; ++o) {
@@ -1749,13 +1742,44 @@ template <typename F, int MT, int T, int NT> struct SweepSite<F, MT, T, NT, true
         lm.init(sub);
     }
     // (z-form: x is the predicted vector, w receives alpha of this site)
+    __device__ __forceinline__ void row(uint32_t blk, int j, F (&e)[MT]) const { et.get(EmisTable4<F, MT, NT>::row_of(blk, j), e); }
     __device__ __forceinline__ void forward(F (&x)[MT], F (&w)[MT], const Params<F, MT> &p, uint32_t blk, int j, int) const {
-        forward_site_ll<F, MT, T, NT>(x, w, p, lm, et, EmisTable4<F, MT, NT>::row_of(blk, j));
+        row(blk, j, w);
+        forward_site_ll<F, MT, T, NT>(x, w, p, lm);
     }
     __device__ __forceinline__ void adjoint(F (&beta)[MT], const Params<F, MT> &p, uint32_t blk, int j, int) const {
-        adjoint_only_site_ll<F, MT, T, NT>(beta, p, lm, et, EmisTable4<F, MT, NT>::row_of(blk, j));
+        F w[MT];
+        row(blk, j, w);
+        adjoint_only_site_ll<F, MT, T, NT>(beta, w, p, lm);
     }
     static __device__ __forceinline__ F total(const F (&x)[MT]) { return pair_sum_flat<F, MT, T>(x); }
+};
+
+// The sum of a vector over the pair, split in two: issue() leaves the lane's own part and the partners' parts (the
+// shuffles are in flight), finish() adds them up.  The sweeps issue at the end of a block and finish after the first
+// site of the NEXT block: a lone warp issues in order, and the shuffle -> add -> reciprocal -> logarithm -> double
+// chain at the end of the block body stalled it for ~45 cycles per block.
+template <typename F, int MT, int T> struct PendingTotal {
+    F own, part[T > 1 ? T - 1 : 1];
+    __device__ __forceinline__ void one() {
+        own = F(1);
+#pragma unroll
+        for (int o = 1; o < T; ++o) part[o - 1] = F(0);
+    }
+    __device__ __forceinline__ void issue(const F (&x)[MT]) {
+        F a[2] = {F(0), F(0)};
+#pragma unroll
+        for (int k = 0; k < MT; ++k) a[k & 1] += x[k];
+        own = a[0] + a[1];
+#pragma unroll
+        for (int o = 1; o < T; ++o) part[o - 1] = __shfl_xor_sync(0xffffffffu, own, o, T);
+    }
+    __device__ __forceinline__ F finish() const {
+        F a[2] = {own, F(0)};
+#pragma unroll
+        for (int o = 1; o < T; ++o) a[o & 1] += part[o - 1];
+        return a[0] + a[1];
+    }
 };
 template <typename F, int MT, int T, int NT> struct SweepSite<F, MT, T, NT, false> {
     EmisTable<F, MT, NT> et;
@@ -1849,35 +1873,56 @@ __device__ __forceinline__ void boundary_sweep_body(const KernelArgs &a, const i
         uint32_t blk_next = __ldg(obs);
         int to_boundary = seg_blocks;  // blocks until the next segment boundary
         // checkpoints for the segment passes: the vector after every K-th site (any scale), see KernelArgs::ext_ck
-        F *ckp = a.ext_ck != nullptr && writer ? static_cast<F *>(a.ext_ck) + (pair * a.ext_ck_count + 1) * M + sub * MT : nullptr;
-        int to_ck = a.ext_ck_blocks;
+        // (the pointer is made opaque so that it stays in registers: re-deriving it from the kernel arguments put a
+        // constant-bank load and its dependants - ~40 exposed cycles for a lone warp - in front of every store)
+        F *ckp = static_cast<F *>(a.ext_ck) + (pair * a.ext_ck_count + 1) * M + sub * MT;
+        asm volatile("" : "+l"(ckp));
+        const bool ck_on = a.ext_ck != nullptr && writer;
+        int to_ck = a.ext_ck_blocks;  // (0 without checkpoints: the counter below never comes back to zero)
         const int last_word = (L - 1) / kNorm;
+        // LL: software pipelining by hand across the block boundary (the compiler does not move work over the loop's
+        // back edge, and a lone warp waits in order): the emission row of a block's first site is loaded at the end of
+        // the block before, and the sum over the pair started at the end of a block is finished after the first
+        // site of the next one (PendingTotal)
+        PendingTotal<F, MT, T> pend;
+        pend.one();
+        F e_first[MT];
+        if constexpr (LL) site.row(blk_next, 0, e_first);
         for (int bi = 0; bi < full_blocks; ++bi) {
             const uint32_t blk = blk_next;
             blk_next = __ldg(obs + min(bi + 1, last_word));
+            if constexpr (LL) {
 #pragma unroll
-            for (int j = 0; j < kNorm; ++j) {
-                if (LL && j == kNorm / 2) {
-#pragma unroll
-                    for (int k = 0; k < MT; ++k) x[k] *= inv_pending;
-                }
-                site.forward(x, w, p, blk, j, sub);
-            }
-            const F tot = site.total(x);
-            inv_pending = fast_rcp<F>(tot);
-            if constexpr (!LL) {
+                for (int k = 0; k < MT; ++k) w[k] = e_first[k];
+                forward_site_ll<F, MT, T, NT>(x, w, p, site.lm);
+                const F tot = pend.finish();
+                inv_pending = fast_rcp<F>(tot);
+                const F lg = lg2_fast(tot);
+                site.forward(x, w, p, blk, 1, sub);
 #pragma unroll
                 for (int k = 0; k < MT; ++k) x[k] *= inv_pending;
+                site.forward(x, w, p, blk, 2, sub);
+                site.forward(x, w, p, blk, 3, sub);
+                ll += double(lg);
+                pend.issue(x);
+                site.row(blk_next, 0, e_first);
+            } else {
+#pragma unroll
+                for (int j = 0; j < kNorm; ++j) site.forward(x, w, p, blk, j, sub);
+                const F tot = site.total(x);
+                inv_pending = fast_rcp<F>(tot);
+#pragma unroll
+                for (int k = 0; k < MT; ++k) x[k] *= inv_pending;
+                ll += double(lg2_fast(tot));
             }
-            ll += double(lg2_fast(tot));
             if (--to_ck == 0) {
                 to_ck = a.ext_ck_blocks;
-                if (ckp != nullptr) {
+                if (ck_on) {
 #pragma unroll
                     for (int q = 0; q < MT / Vec<F>::W; ++q)
                         *reinterpret_cast<typename Vec<F>::type *>(ckp + q * Vec<F>::W) = pack(&w[q * Vec<F>::W]);
-                    ckp += M;
                 }
+                ckp += M;
             }
             if (--to_boundary == 0) {
                 // the vector entering the next segment (approximately normalised - in LL mode short of this
@@ -1891,6 +1936,9 @@ __device__ __forceinline__ void boundary_sweep_body(const KernelArgs &a, const i
             }
         }
         if constexpr (LL) {
+            const F tot = pend.finish();
+            inv_pending = fast_rcp<F>(tot);
+            ll += double(lg2_fast(tot));
 #pragma unroll
             for (int k = 0; k < MT; ++k) x[k] *= inv_pending;
         }
@@ -1922,11 +1970,15 @@ __device__ __forceinline__ void boundary_sweep_body(const KernelArgs &a, const i
         }
         bnd += int64_t(G) * M;
         F inv_pending = F(1);
+        PendingTotal<F, MT, T> pend;
+        pend.one();
         if (tail > 0) {
             const uint32_t blk = __ldg(obs + full_blocks);
             for (int j = tail - 1; j >= 0; --j) site.adjoint(beta, p, blk, j, sub);
-            inv_pending = fast_rcp<F>(site.total(beta));
-            if constexpr (!LL) {
+            if constexpr (LL) {
+                pend.issue(beta);
+            } else {
+                inv_pending = fast_rcp<F>(site.total(beta));
 #pragma unroll
                 for (int k = 0; k < MT; ++k) beta[k] *= inv_pending;
             }
@@ -1942,19 +1994,25 @@ __device__ __forceinline__ void boundary_sweep_body(const KernelArgs &a, const i
             }
         }
         uint32_t blk_next = full_blocks > 0 ? __ldg(obs + full_blocks - 1) : 0u;
+        F e_first[MT];  // emission row of the first site (number 3) of the next block, see the forward sweep
+        if constexpr (LL) site.row(blk_next, kNorm - 1, e_first);
         for (int bi = full_blocks - 1; bi >= 0; --bi) {
             const uint32_t blk = blk_next;
             blk_next = __ldg(obs + max(bi - 1, 0));
+            if constexpr (LL) {
+                adjoint_only_site_ll<F, MT, T, NT>(beta, e_first, p, site.lm);
+                inv_pending = fast_rcp<F>(pend.finish());
+                site.adjoint(beta, p, blk, 2, sub);
 #pragma unroll
-            for (int j = kNorm - 1; j >= 0; --j) {
-                if (LL && j == kNorm / 2 - 1) {
+                for (int k = 0; k < MT; ++k) beta[k] *= inv_pending;
+                site.adjoint(beta, p, blk, 1, sub);
+                site.adjoint(beta, p, blk, 0, sub);
+                pend.issue(beta);
+                site.row(blk_next, kNorm - 1, e_first);
+            } else {
 #pragma unroll
-                    for (int k = 0; k < MT; ++k) beta[k] *= inv_pending;
-                }
-                site.adjoint(beta, p, blk, j, sub);
-            }
-            inv_pending = fast_rcp<F>(site.total(beta));
-            if constexpr (!LL) {
+                for (int j = kNorm - 1; j >= 0; --j) site.adjoint(beta, p, blk, j, sub);
+                inv_pending = fast_rcp<F>(site.total(beta));
 #pragma unroll
                 for (int k = 0; k < MT; ++k) beta[k] *= inv_pending;
             }
