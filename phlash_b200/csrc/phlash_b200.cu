@@ -463,7 +463,9 @@ int try_parallel_in_time_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaS
     if (!tv || !gv) return kNotTaken;
     const int M = k->M;
     const int64_t capacity = int64_t(k->num_sms) * 384;  // resident threads of the row kernel
-    if (pit_mode != 1 && n_pairs * M * 10 > capacity * 3) return kNotTaken;
+    // (break-even against the two sweeps, 3.3 ms at 50 500 sites: 1.8 ms of operator work per 500 pairs at M = 16,
+    // profiles/r02_probe_sweep_layouts_v7.log: 1 000 pairs take 5.0 ms through the operators, 4.4 ms through the sweeps)
+    if (pit_mode != 1 && n_pairs * M * 4 > capacity) return kNotTaken;
     int occ = 0;
     {
         auto it = k->occupancy.find(gv->func);
@@ -566,6 +568,8 @@ int try_two_sweep_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t
     if (occ < 1) return kNotTaken;
     const int64_t resident = int64_t(occ) * k->num_sms;
     const int64_t seg_ctas = chunk_major_groups(tv, a.B, a.S);  // groups per segment
+    // (short rows - the 500-site warm-up launch of the whole-term entries - stay with the store-all kernel: cut into
+    // segments of 64+ sites they take 0.09 instead of 0.14 ms, which did not show in the step time)
     const int64_t min_seg = pit_mode == 2 ? 64 : 1024;
     int64_t n_seg = std::min(std::max<int64_t>(resident / seg_ctas, 2), a.L / min_seg);
     if (k->env_pit_segments > 0) n_seg = std::min<int64_t>(k->env_pit_segments, a.L / 64);  // experiments
@@ -874,10 +878,12 @@ int launch_one(phb_kernel *k, phb::KernelArgs a, bool grad, cudaStream_t stream,
     const int sa_mode = k->env_store_all != -2 ? k->env_store_all : k->store_all_mode;
     const int pit_mode = k->env_pit != -2 ? k->env_pit : k->parallel_in_time;
     const bool free_choice = !fixed && !k->dbl && k->force_T == 0;
+    // (a store-all kernel asked for by name wins over the automatic choice of a parallel-in-time path)
+    const bool pit_allowed = pit_mode != 0 && sa_mode != 0 && !(sa_mode == 1 && pit_mode != 1 && pit_mode != 2);
     int rc = kNotTaken;
-    if (free_choice && grad && pit_mode != 0 && pit_mode != 2 && sa_mode != 0 && a.s_list == nullptr)
+    if (free_choice && grad && pit_allowed && pit_mode != 2 && a.s_list == nullptr)
         rc = try_parallel_in_time_gradient(k, a, stream, pit_mode);
-    if (rc == kNotTaken && free_choice && grad && pit_mode != 0 && pit_mode != 1 && sa_mode != 0 && a.s_list == nullptr)
+    if (rc == kNotTaken && free_choice && grad && pit_allowed && pit_mode != 1 && a.s_list == nullptr)
         rc = try_two_sweep_gradient(k, a, stream, pit_mode);
     if (pit_only) return rc;
     if (rc == kNotTaken && free_choice && grad && sa_mode != 0) rc = try_store_all(k, a, stream, sa_mode);

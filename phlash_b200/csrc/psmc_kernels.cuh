@@ -1870,7 +1870,9 @@ __device__ __forceinline__ void boundary_sweep_body(const KernelArgs &a, const i
         F inv_pending = F(1);
         F w[MT];  // alpha of the last site
         if constexpr (LL) site.forward(x, w, p, 0xffffffffu, 0, sub);  // z(0) = pi A: a step with the emission row of ones
+        // observation words are requested TWO blocks ahead: one block (~500 cycles) does not cover a miss in L1
         uint32_t blk_next = __ldg(obs);
+        uint32_t blk_next2 = __ldg(obs + min(1, (L - 1) / kNorm));
         int to_boundary = seg_blocks;  // blocks until the next segment boundary
         // checkpoints for the segment passes: the vector after every K-th site (any scale), see KernelArgs::ext_ck
         // (the pointer is made opaque so that it stays in registers: re-deriving it from the kernel arguments put a
@@ -1890,7 +1892,8 @@ __device__ __forceinline__ void boundary_sweep_body(const KernelArgs &a, const i
         if constexpr (LL) site.row(blk_next, 0, e_first);
         for (int bi = 0; bi < full_blocks; ++bi) {
             const uint32_t blk = blk_next;
-            blk_next = __ldg(obs + min(bi + 1, last_word));
+            blk_next = blk_next2;
+            blk_next2 = __ldg(obs + min(bi + 2, last_word));
             if constexpr (LL) {
 #pragma unroll
                 for (int k = 0; k < MT; ++k) w[k] = e_first[k];
@@ -1994,11 +1997,13 @@ __device__ __forceinline__ void boundary_sweep_body(const KernelArgs &a, const i
             }
         }
         uint32_t blk_next = full_blocks > 0 ? __ldg(obs + full_blocks - 1) : 0u;
+        uint32_t blk_next2 = __ldg(obs + max(full_blocks - 2, 0));
         F e_first[MT];  // emission row of the first site (number 3) of the next block, see the forward sweep
         if constexpr (LL) site.row(blk_next, kNorm - 1, e_first);
         for (int bi = full_blocks - 1; bi >= 0; --bi) {
             const uint32_t blk = blk_next;
-            blk_next = __ldg(obs + max(bi - 1, 0));
+            blk_next = blk_next2;
+            blk_next2 = __ldg(obs + max(bi - 2, 0));
             if constexpr (LL) {
                 adjoint_only_site_ll<F, MT, T, NT>(beta, e_first, p, site.lm);
                 inv_pending = fast_rcp<F>(pend.finish());
