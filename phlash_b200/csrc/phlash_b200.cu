@@ -103,6 +103,7 @@ struct phb_kernel {
     DeviceBuffer transfer_rows, transfer_log;                 // parallel-in-time forward evaluation
     DeviceBuffer bnd_alpha, bnd_beta, seg_dlog;               // ... and gradient
     DeviceBuffer sweep_ckpt;                                  // checkpoints left by the forward sweep for the segment passes
+    DeviceBuffer warm_ll;                                     // log-likelihood of the fused warm-up term
     DeviceBuffer uniform_stage;                               // parameter rows packed for the constant bank (psmc_uniform.cuh)
     int parallel_in_time = -1;  // -1 auto, 0 never, 1 whenever possible
     int store_all_mode = -1;  // -1 auto, 0 never, 1 whenever a store-all variant exists
@@ -113,7 +114,8 @@ struct phb_kernel {
     int escalate = 1;
     // experiment knobs, read from the environment ONCE when the object is created (never per call):
     // PHB_NT, PHB_STORE_ALL, PHB_PARALLEL_IN_TIME, PHB_PIT_SEGMENTS
-    int env_nt = 0, env_store_all = -2, env_pit = -2, env_pit_segments = 0, env_sweep_tf = 0, env_sweep_tb = 0, env_uniform = 1, env_sform = 0, env_sweep_ll = 1, env_sweep_ckpt = 1;
+    int env_nt = 0, env_store_all = -2, env_pit = -2, env_pit_segments = 0, env_sweep_tf = 0, env_sweep_tb = 0, env_uniform = 1, env_sform = 0, env_sweep_ll = 1, env_sweep_ckpt = 1, env_fuse_warmup = 1;
+    bool warm_fused = false;  // the last parallel-in-time gradient launch scored the warm-up term too (KernelArgs::warm_len)
     // phb_reserve(): the dispatch runs with dry = true - every scratch buffer is sized and every kernel
     // attribute set exactly as a real call would, but nothing is launched
     bool dry = false;
@@ -449,6 +451,22 @@ int launch_transfer_rows(phb_kernel *k, const TransferVariant *tv, const phb::Tr
     return PHB_OK;
 }
 
+// Does the warm-up term (a.warm_len sites, see KernelArgs) ride along with the segment passes?  Its groups must be
+// RESIDENT next to the real ones: as a second round they would add 500 dependent sites at the throughput kernel's
+// 0.8 us per site, more than the 0.14 ms launch they replace.  With many segments one is given up for that (each
+// of the others grows by 1 / n_seg); with few (S = 5: 14) the separate launch stays.
+static bool plan_fused_warmup(const phb_kernel *k, const phb::KernelArgs &a, const Variant *v, int64_t seg_ctas, int64_t resident,
+                              int64_t *n_seg) {
+    if (a.warm_len <= 0 || k->env_fuse_warmup == 0 || a.skip_flag != nullptr || a.s_list != nullptr || a.out_mode != 0 || is_sform(v))
+        return false;
+    if ((*n_seg + 1) * seg_ctas <= resident) return true;
+    if (*n_seg >= 20 && *n_seg * seg_ctas <= resident) {
+        *n_seg -= 1;
+        return true;
+    }
+    return false;
+}
+
 // (1) Gradient of FEW pairs (the reference's default minibatch for one genome is a single chunk: 500
 // pairs): parallel in time.  Segment transfer operators give the forward / adjoint vectors at the
 // segment boundaries (chain_boundaries_kernel), after which the segments are independent short
@@ -486,19 +504,24 @@ int try_parallel_in_time_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaS
     if (pit_mode == 1) n_seg = std::max<int64_t>(n_seg, std::min<int64_t>(3, a.L / min_seg));
     if (k->env_pit_segments > 0) n_seg = std::min<int64_t>(k->env_pit_segments, a.L / 64);  // experiments
     if (n_seg < 3) return kNotTaken;
+    bool warm = plan_fused_warmup(k, a, gv, seg_ctas, resident, &n_seg);
     const int64_t seg_len = ((a.L + n_seg - 1) / n_seg + 15) / 16 * 16;
     n_seg = (a.L + seg_len - 1) / seg_len;
+    warm = warm && a.warm_len <= seg_len;
+    const int64_t n_slots = n_seg + (warm ? 1 : 0);  // partial gradients per pair
     const int64_t n_rows_virtual = n_pairs * n_seg * M;
-    const int64_t n_groups = seg_ctas * n_seg;
+    const int64_t n_groups = seg_ctas * n_slots;
     const int64_t grid = std::min<int64_t>(n_groups, resident);
     int rc;
     if ((rc = k->transfer_rows.reserve(size_t(n_rows_virtual) * M * sizeof(float))) != PHB_OK) return rc;
     if ((rc = k->transfer_log.reserve(size_t(n_rows_virtual) * sizeof(double))) != PHB_OK) return rc;
     if ((rc = k->bnd_alpha.reserve(size_t(n_pairs) * (n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
     if ((rc = k->bnd_beta.reserve(size_t(n_pairs) * (n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
-    if ((rc = k->seg_dlog.reserve(size_t(n_pairs) * n_seg * 7 * M * sizeof(float))) != PHB_OK) return rc;
+    if ((rc = k->seg_dlog.reserve(size_t(n_pairs) * n_slots * 7 * M * sizeof(float))) != PHB_OK) return rc;
     if ((rc = k->ckpt.reserve(size_t(grid) * (gv->NT / 32) * size_t(gv->ckpt_bytes_per_warp(seg_len)))) != PHB_OK) return rc;
     if ((rc = k->gacc.reserve(size_t(grid) * gv->NT * 6 * (gv->M / gv->T) * sizeof(double))) != PHB_OK) return rc;
+    if (warm && (rc = k->warm_ll.reserve(size_t(n_pairs) * sizeof(double))) != PHB_OK) return rc;
+    k->warm_fused = warm;
     phb::TransferArgs ta{};
     ta.k = a;
     ta.k.err_flag = k->d_err;
@@ -526,17 +549,19 @@ int try_parallel_in_time_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaS
     sa.seg_dlog = k->seg_dlog.ptr;
     sa.seg_ctas = seg_ctas;
     sa.n_groups = n_groups;
+    sa.warm_len = warm ? a.warm_len : 0;
+    sa.warm_ll = warm ? static_cast<double *>(k->warm_ll.ptr) : nullptr;
     {
         void *kargs[] = {&sa};
         PHB_CUDA(cudaLaunchKernel(gv->func, dim3(unsigned(grid)), dim3(gv->NT), kargs, gv->smem, stream));
     }
     const int64_t n_out = n_pairs * 7 * M;
     phb::sum_segments_kernel<float><<<unsigned((n_out + 255) / 256), 256, 0, stream>>>(
-        static_cast<const float *>(k->seg_dlog.ptr), n_pairs, n_seg, M, static_cast<float *>(a.dlog), a.out_mode, a);
+        static_cast<const float *>(k->seg_dlog.ptr), n_pairs, n_seg, M, static_cast<float *>(a.dlog), a.out_mode, sa);
     PHB_CUDA(cudaGetLastError());
     k->launches += 3;
-    snprintf(k->last_name, sizeof k->last_name, "transfer_rows_kernel<float,M=%d> + psmc_loglik_kernel<SEG,MT=%d,T=%d> x %lld segments", M,
-             gv->M / gv->T, gv->T, (long long)n_seg);
+    snprintf(k->last_name, sizeof k->last_name, "transfer_rows_kernel<float,M=%d> + psmc_loglik_kernel<SEG,MT=%d,T=%d> x %lld segments%s", M,
+             gv->M / gv->T, gv->T, (long long)n_seg, warm ? " + warm-up term" : "");
     return PHB_OK;
 }
 
@@ -575,10 +600,13 @@ int try_two_sweep_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t
     if (k->env_pit_segments > 0) n_seg = std::min<int64_t>(k->env_pit_segments, a.L / 64);  // experiments
     // measured at B = 500, L = 50 000, M = 16 (profiles/r01_probe_parallel_in_time.log)
     if (n_seg < (pit_mode == 2 ? 2 : 6)) return kNotTaken;
+    bool warm = plan_fused_warmup(k, a, tv, seg_ctas, resident, &n_seg);
     const int64_t seg_len = ((a.L + n_seg - 1) / n_seg + 15) / 16 * 16;
     n_seg = (a.L + seg_len - 1) / seg_len;
     if (n_seg < 2) return kNotTaken;
-    const int64_t n_groups = seg_ctas * n_seg;
+    warm = warm && a.warm_len <= seg_len;
+    const int64_t n_slots = n_seg + (warm ? 1 : 0);  // partial gradients per pair
+    const int64_t n_groups = seg_ctas * n_slots;
     const int64_t grid = std::min<int64_t>(n_groups, resident);
     const SweepVariant *sw = pick_sweep(k, n_pairs);
     if (!sw || a.L >= (int64_t(1) << 31) - 16) return kNotTaken;  // (the sweeps count sites in 32 bits)
@@ -588,7 +616,8 @@ int try_two_sweep_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t
     int rc;
     if ((rc = k->bnd_alpha.reserve(size_t(n_pairs) * (n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
     if ((rc = k->bnd_beta.reserve(size_t(n_pairs) * (n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
-    if ((rc = k->seg_dlog.reserve(size_t(n_pairs) * n_seg * 7 * M * sizeof(float))) != PHB_OK) return rc;
+    if ((rc = k->seg_dlog.reserve(size_t(n_pairs) * n_slots * 7 * M * sizeof(float))) != PHB_OK) return rc;
+    if (warm && (rc = k->warm_ll.reserve(size_t(n_pairs) * sizeof(double))) != PHB_OK) return rc;
     if ((rc = k->ckpt.reserve(size_t(grid) * (tv->NT / 32) * size_t(tv->ckpt_bytes_per_warp(seg_len)))) != PHB_OK) return rc;
     if ((rc = k->gacc.reserve(size_t(grid) * tv->NT * 6 * (tv->M / tv->T) * sizeof(double))) != PHB_OK) return rc;
     // checkpoints of the segment passes, written by the forward sweep (64 B per pair and 8 sites: 1 GB for 2 500
@@ -601,6 +630,7 @@ int try_two_sweep_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t
         PHB_CUDA(cudaFuncSetAttribute(sweep_func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sweep_smem)));
         k->occupancy.emplace(sweep_func, 1);
     }
+    k->warm_fused = warm;
     if (k->dry) return PHB_OK;
     phb::KernelArgs sa = a;
     sa.err_flag = k->d_err;
@@ -617,16 +647,18 @@ int try_two_sweep_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaStream_t
     sa.ext_ck = ext_ck ? k->sweep_ckpt.ptr : nullptr;
     sa.ext_ck_count = ck_count;
     sa.ext_ck_blocks = tv->K / 4;
+    sa.warm_len = warm ? a.warm_len : 0;
+    sa.warm_ll = warm ? static_cast<double *>(k->warm_ll.ptr) : nullptr;
     void *kargs[] = {&sa};
     PHB_CUDA(cudaLaunchKernel(sweep_func, dim3(unsigned(sweep_ctas(*sw, n_pairs))), dim3(sw->NT), kargs, sweep_smem, stream));
     PHB_CUDA(cudaLaunchKernel(tv->func, dim3(unsigned(grid)), dim3(tv->NT), kargs, tv->smem, stream));
     const int64_t n_out = n_pairs * 7 * M;
     phb::sum_segments_kernel<float><<<unsigned((n_out + 255) / 256), 256, 0, stream>>>(
-        static_cast<const float *>(k->seg_dlog.ptr), n_pairs, n_seg, M, static_cast<float *>(a.dlog), a.out_mode, a);
+        static_cast<const float *>(k->seg_dlog.ptr), n_pairs, n_seg, M, static_cast<float *>(a.dlog), a.out_mode, sa);
     PHB_CUDA(cudaGetLastError());
     k->launches += 3;
-    snprintf(k->last_name, sizeof k->last_name, "boundary_sweep_kernel<float,TF=%d,TB=%d%s> + psmc_loglik_kernel<SEG,MT=%d,T=%d> x %lld segments",
-             sw->TF, sw->TB, sw->ll ? ",LL" : "", tv->M / tv->T, tv->T, (long long)n_seg);
+    snprintf(k->last_name, sizeof k->last_name, "boundary_sweep_kernel<float,TF=%d,TB=%d%s> + psmc_loglik_kernel<SEG,MT=%d,T=%d> x %lld segments%s",
+             sw->TF, sw->TB, sw->ll ? ",LL" : "", tv->M / tv->T, tv->T, (long long)n_seg, warm ? " + warm-up term" : "");
     return PHB_OK;
 }
 
@@ -1000,6 +1032,7 @@ static int new_kernel(int M, int64_t N, int64_t L, int double_precision, int dev
     if (const char *v = getenv("PHB_SWEEP_TB")) k->env_sweep_tb = atoi(v);
     if (const char *v = getenv("PHB_SWEEP_LL")) k->env_sweep_ll = atoi(v);
     if (const char *v = getenv("PHB_SWEEP_CKPT")) k->env_sweep_ckpt = atoi(v);
+    if (const char *v = getenv("PHB_FUSE_WARMUP")) k->env_fuse_warmup = atoi(v);
     if (const char *v = getenv("PHB_UNIFORM")) k->env_uniform = atoi(v);
     if (const char *v = getenv("PHB_SFORM")) k->env_sform = atoi(v);
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&k->d_data), size_t(N) * size_t(k->pitch));
@@ -1010,7 +1043,7 @@ static int new_kernel(int M, int64_t N, int64_t L, int double_precision, int dev
     }
     for (DeviceBuffer *b : {&k->params, &k->inds, &k->ll, &k->dlog, &k->ckpt, &k->gacc, &k->xall, &k->sall, &k->split, &k->term_params,
                             &k->term_ll, &k->term_dlog, &k->term_sums, &k->term_io, &k->transfer_rows, &k->transfer_log, &k->bnd_alpha,
-                            &k->bnd_beta, &k->seg_dlog, &k->uniform_stage, &k->sweep_ckpt})
+                            &k->bnd_beta, &k->seg_dlog, &k->uniform_stage, &k->sweep_ckpt, &k->warm_ll})
         b->counter = &k->allocations;
     if ((e = cudaStreamCreateWithFlags(&k->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaMalloc(reinterpret_cast<void **>(&k->d_iteration), sizeof(unsigned long long))) != cudaSuccess ||
@@ -1276,6 +1309,7 @@ void phb_destroy(phb_kernel *k) {
     k->seg_dlog.release();
     k->uniform_stage.release();
     k->sweep_ckpt.release();
+    k->warm_ll.release();
     if (k->d_rowflag) cudaFree(k->d_rowflag);
     if (k->d_data) cudaFree(k->d_data);
     if (k->d_err) cudaFree(k->d_err);
@@ -1338,7 +1372,7 @@ int phb_set_threads_per_pair(phb_kernel *k, int threads_per_pair) {
 static int device_eval(phb_kernel *k, const void *params6, int64_t params_stride_b, int64_t params_stride_s,
                        const void *pi, int64_t pi_stride_b, int64_t pi_stride_s, const int64_t *inds, int64_t B,
                        int64_t S, int want_grad, double *ll, void *dlog, cudaStream_t stream, int64_t n_sites,
-                       int out_mode) {
+                       int out_mode, int64_t warm_len = 0) {
     if (int rc = check_handle(k)) return rc;
     if (B < 0 || S < 0) return fail(PHB_E_INVALID, "negative batch shape");
     if (B == 0 || S == 0) return PHB_OK;
@@ -1364,6 +1398,8 @@ static int device_eval(phb_kernel *k, const void *params6, int64_t params_stride
     a.dlog = want_grad ? dlog : nullptr;
     a.alpha_out = nullptr;
     a.out_mode = out_mode;
+    a.warm_len = want_grad ? warm_len : 0;  // (a request: a parallel-in-time gradient path may honour it, see warm_fused)
+    k->warm_fused = false;
     return launch(k, a, want_grad != 0, stream);
 }
 
@@ -1385,9 +1421,11 @@ int phb_loglik_warmup_device(phb_kernel *k, const void *params7, const int64_t *
     const void *pi = base + size_t(6) * M * k->elem();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // LL over warm-up + chunk, started from the particle's stationary pi ...
-    int rc = device_eval(k, params7, 7 * M, 0, pi, 7 * M, 0, inds, B, S, want_grad, ll, dlog, st, k->L, 0);
+    int rc = device_eval(k, params7, 7 * M, 0, pi, 7 * M, 0, inds, B, S, want_grad, ll, dlog, st, k->L, 0, overlap);
     if (rc != PHB_OK || overlap == 0) return rc;
-    // ... minus LL over the warm-up bins alone (same stream: ordered after the first launch)
+    // ... minus LL over the warm-up bins alone: either the first call scored them as one more segment of its
+    // segment passes (small minibatches, see KernelArgs::warm_len) or a second launch on the same stream does
+    if (k->warm_fused) return PHB_OK;
     return device_eval(k, params7, 7 * M, 0, pi, 7 * M, 0, inds, B, S, want_grad, ll, dlog, st, overlap, 1);
 }
 
@@ -1839,18 +1877,23 @@ int phb_hmm_term_sharded_end(phb_kernel *k, const int64_t *inds, int64_t B, int6
     const int64_t seg_lo = std::min<int64_t>(p.n_seg, int64_t(rank) * p.per_rank);
     const int64_t seg_hi = std::min<int64_t>(p.n_seg, seg_lo + p.per_rank);
     const int64_t n_local = seg_hi - seg_lo;
-    const int64_t n_groups = p.seg_ctas * n_local;
     const int64_t occ = k->occupancy[gv->func];
+    const bool marked = !k->dbl && k->escalate && k->n_flagged > 0;
+    // process 0 scores the warm-up term as one more segment of its slice when its groups stay resident (KernelArgs::warm_len)
+    const bool warm = rank == 0 && overlap > 0 && n_local > 0 && !marked && k->env_fuse_warmup != 0 && !is_sform(gv) &&
+                      overlap <= p.seg_len && p.seg_ctas * (n_local + 1) <= occ * k->num_sms;
+    const int64_t n_slots = n_local + (warm ? 1 : 0);
+    const int64_t n_groups = p.seg_ctas * n_slots;
     const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(n_groups, occ * k->num_sms));
     int rc;
     if ((rc = k->term_ll.reserve(size_t(n_pairs) * sizeof(double))) != PHB_OK) return rc;
     if ((rc = k->term_dlog.reserve(size_t(n_pairs) * C * k->elem())) != PHB_OK) return rc;
     if ((rc = k->bnd_alpha.reserve(size_t(n_pairs) * (p.n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
     if ((rc = k->bnd_beta.reserve(size_t(n_pairs) * (p.n_seg + 1) * M * sizeof(float))) != PHB_OK) return rc;
-    if ((rc = k->seg_dlog.reserve(size_t(n_pairs) * std::max<int64_t>(n_local, 1) * C * sizeof(float))) != PHB_OK) return rc;
+    if ((rc = k->seg_dlog.reserve(size_t(n_pairs) * std::max<int64_t>(n_slots, 1) * C * sizeof(float))) != PHB_OK) return rc;
+    if (warm && (rc = k->warm_ll.reserve(size_t(n_pairs) * sizeof(double))) != PHB_OK) return rc;
     if ((rc = k->ckpt.reserve(size_t(grid) * (gv->NT / 32) * size_t(gv->ckpt_bytes_per_warp(p.seg_len)))) != PHB_OK) return rc;
     if ((rc = k->gacc.reserve(size_t(grid) * gv->NT * 6 * (gv->M / gv->T) * sizeof(double))) != PHB_OK) return rc;
-    const bool marked = !k->dbl && k->escalate && k->n_flagged > 0;
     if (marked && (rc = k->split.reserve((size_t(2) * S + 2) * sizeof(int32_t))) != PHB_OK) return rc;
     if (!k->dry) {
         // every process contributes zero where it has nothing to say (ll: process 0 only; marked rows: process 0's
@@ -1903,6 +1946,8 @@ int phb_hmm_term_sharded_end(phb_kernel *k, const int64_t *inds, int64_t B, int6
             sa.seg_dlog = k->seg_dlog.ptr;
             sa.seg_ctas = p.seg_ctas;
             sa.n_groups = n_groups;
+            sa.warm_len = warm ? overlap : 0;
+            sa.warm_ll = warm ? static_cast<double *>(k->warm_ll.ptr) : nullptr;
             void *kargs[] = {&sa};
             PHB_CUDA(cudaLaunchKernel(gv->func, dim3(unsigned(grid)), dim3(gv->NT), kargs, gv->smem, st));
             const int64_t n_out = n_pairs * C;
@@ -1911,8 +1956,8 @@ int phb_hmm_term_sharded_end(phb_kernel *k, const int64_t *inds, int64_t B, int6
             PHB_CUDA(cudaGetLastError());
             k->launches += 2;
         }
-        snprintf(k->last_name, sizeof k->last_name, "time-sharded %d/%d: transfer_rows_kernel<float,M=%d> + psmc_loglik_kernel<SEG> x %lld of %lld segments",
-                 rank, world, M, (long long)n_local, (long long)p.n_seg);
+        snprintf(k->last_name, sizeof k->last_name, "time-sharded %d/%d: transfer_rows_kernel<float,M=%d> + psmc_loglik_kernel<SEG> x %lld of %lld segments%s",
+                 rank, world, M, (long long)n_local, (long long)p.n_seg, warm ? " + warm-up term" : "");
     }
     if (rank == 0) {
         // process 0 owns: the log-likelihood (chain_boundaries_kernel wrote it everywhere: the others drop theirs below),
@@ -1945,7 +1990,7 @@ int phb_hmm_term_sharded_end(phb_kernel *k, const int64_t *inds, int64_t B, int6
             part.s_count = counts + 1;
             if ((rc = launch_one(k, part, true, st, esc)) != PHB_OK) return rc;
         }
-        if (overlap > 0) {
+        if (overlap > 0 && !warm) {
             a.L = overlap;
             a.out_mode = 1;
             if ((rc = launch(k, a, true, st)) != PHB_OK) return rc;

@@ -98,6 +98,12 @@ struct KernelArgs {
     void *ext_ck;           // [B * S][ext_ck_count][M] FLOAT, record m = vector after site K m - 1 (record 0 unused)
     int64_t ext_ck_count;   // ceil(L / K) + 1
     int ext_ck_blocks;      // K / kNorm
+    // Fused warm-up term (phb_loglik_warmup_*: LL of the whole row minus LL of its first warm_len sites): the segment
+    // passes score the first warm_len sites as ONE MORE segment per chunk - started from pi itself, closed with a
+    // vector of ones, its partial gradient in the slot behind the real segments - and sum_segments_kernel subtracts it.
+    // The 500 dependent sites of the warm-up then cost no launch of their own.  0 = no warm-up term.
+    int64_t warm_len;
+    double *warm_ll;        // [B * S] log-likelihood of the first warm_len sites
 };
 
 // Pair enumeration of the store-all kernel: b major, position in the (sub-)list minor.  (psmc_loglik_kernel
@@ -673,8 +679,10 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
     // uniform and the shuffles need no reconvergence guards
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         // SEG: group -> (segment of the chunk, group within the segment); L = sites of that segment
-        const int64_t pseg = SEG ? a.seg_first + grp / a.seg_ctas : 0;
-        const int64_t L = SEG ? min(a.seg_len, a.L - pseg * a.seg_len) : a.L;
+        const int64_t n_real = a.seg_local ? a.seg_local : a.seg_count;        // segments scored by this launch
+        const bool warm = SEG && a.warm_len > 0 && grp / a.seg_ctas == n_real;  // the groups of the warm-up term
+        const int64_t pseg = SEG ? (warm ? 0 : a.seg_first + grp / a.seg_ctas) : 0;
+        const int64_t L = SEG ? (warm ? a.warm_len : min(a.seg_len, a.L - pseg * a.seg_len)) : a.L;
         const int64_t n_seg = (L + K - 1) / K;
         const int64_t pair_raw = ((SEG ? grp % a.seg_ctas : grp) * kWarps + warp) * PW + lp;
         const bool writer = pair_raw < n_pairs;
@@ -684,7 +692,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
         const int64_t ps = (!SEG && a.s_list) ? int64_t(a.s_list[slot]) : slot;
         const int64_t chunk_pair = pb * a.S + ps;  // index into ll / dlog ([B, S]) and the boundary vectors
         int64_t pair = chunk_pair;
-        if constexpr (SEG) pair = chunk_pair * (a.seg_local ? a.seg_local : a.seg_count) + (pseg - a.seg_first);  // slot in seg_dlog
+        if constexpr (SEG) pair = chunk_pair * (n_real + (a.warm_len > 0 ? 1 : 0)) + grp / a.seg_ctas;  // slot in seg_dlog
         Params<F, MT> p;
         p.load(params6 + pb * a.pstride_b + ps * a.pstride_s + sub * MT, M);
         et.fill(params6 + pb * a.pstride_b + ps * a.pstride_s + sub * MT, M);
@@ -697,14 +705,14 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
             row = 0;
         }
         const int8_t *obs = a.data + row * a.pitch + (SEG ? pseg * a.seg_len : 0);
-        const IO *pi_p = SEG ? static_cast<const IO *>(a.bnd_alpha) + (chunk_pair * (a.seg_count + 1) + pseg) * M + sub * MT
-                             : pi_g + pb * a.pistride_b + ps * a.pistride_s + sub * MT;
+        const IO *pi_p = (SEG && !warm) ? static_cast<const IO *>(a.bnd_alpha) + (chunk_pair * (a.seg_count + 1) + pseg) * M + sub * MT
+                                        : pi_g + pb * a.pistride_b + ps * a.pistride_s + sub * MT;
 
         // ------------------------------------------------------------------ pass 1: forward
         // (segment mode after the sweeps: the checkpoints and the vector behind the segment are already there)
         const IO *ext_ck = nullptr;
         if constexpr (SEG) {
-            if (a.ext_ck != nullptr)
+            if (a.ext_ck != nullptr && !warm)
                 ext_ck = static_cast<const IO *>(a.ext_ck) + (chunk_pair * a.ext_ck_count + pseg * (a.seg_len / K)) * M + sub * MT;
         }
         F x[MT];
@@ -755,6 +763,8 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
         if (bad_row) ll = __longlong_as_double(0x7ff8000000000000LL);
         if constexpr (!SEG) {
             if (writer && sub == 0) a.ll[pair] = a.out_mode ? a.ll[pair] - ll : ll;
+        } else {
+            if (warm && writer && sub == 0) a.warm_ll[chunk_pair] = ll;
         }
         if (!SEG && writer && a.alpha_out != nullptr) {
             IO *ao = static_cast<IO *>(a.alpha_out) + pair * M + sub * MT;
@@ -774,7 +784,7 @@ __global__ void __maxnreg__(max_regs(NT, MINB)) psmc_loglik_kernel(const KernelA
                 F dot = F(0);
 #pragma unroll
                 for (int k = 0; k < MT; ++k) {
-                    beta[k] = bb[k];
+                    beta[k] = warm ? F(1) : bb[k];  // (the warm-up term ends after its last site: a vector of ones)
                     dot = fma(beta[k], x[k], dot);
                 }
                 dot = F(1) / lanes_total<F, T>(dot);
@@ -1533,12 +1543,17 @@ __global__ void sum_segments_kernel(const F *__restrict__ seg_dlog, int64_t n_pa
     const int64_t pair = i / (7 * M);
     const int64_t rm = i % (7 * M);
     if (outputs_skipped(a, pair % a.S)) return;
-    const F *src = seg_dlog + pair * G * 7 * M + rm;
+    const bool warm = a.warm_len > 0;  // one more slot per pair: the warm-up term, to be subtracted
+    const F *src = seg_dlog + pair * (G + (warm ? 1 : 0)) * 7 * M + rm;
     // (G = segments of this launch; the pi row belongs to the chunk's first segment: zero from a launch that
     // does not hold it, i.e. under time-axis sharding)
     double acc = (rm < 6 * M || a.seg_first == 0) ? double(src[0]) : 0.0;
     if (rm < 6 * M)
         for (int64_t g = 1; g < G; ++g) acc += double(src[g * 7 * M]);
+    if (warm) {
+        acc -= double(src[G * 7 * M]);
+        if (rm == 0) a.ll[pair] -= a.warm_ll[pair];
+    }
     dlog[i] = out_mode ? F(double(dlog[i]) - acc) : F(acc);
 }
 

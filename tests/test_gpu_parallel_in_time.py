@@ -154,6 +154,7 @@ def test_gradient_dispatch_and_warmup_composition(golden):
     kern = _PSMCKernelBase(16, data)
     inds = np.array([3])
     ll, dlog = kern.evaluate_warmup(pps, inds, ov, True)
+    assert "warm-up term" in kern.last_kernel_name          # scored as one more segment, no second launch
     pa = np.broadcast_to(pps[:, None], (6, 1, 7, 16)).copy()
     kern.evaluate(pa, inds, True)
     assert "segments" in kern.last_kernel_name              # 6 pairs x 12 100 sites
@@ -168,6 +169,39 @@ def test_gradient_dispatch_and_warmup_composition(golden):
     scale = np.abs(dlog_s).max(axis=-1, keepdims=True)
     scale_full = np.abs(full).max(axis=-1, keepdims=True)
     assert (np.abs(dlog - dlog_s) <= GRAD_RTOL * (np.abs(dlog_s) + 1e-3 * scale) + 2e-6 * scale_full).all()
+
+
+@pytest.mark.parametrize("B,S,path", [(6, 1, "transfer_rows"), (300, 3, "boundary_sweep")])
+def test_fused_warmup_term_matches_oracle(B, S, path, monkeypatch):
+    """LL(whole row) - LL(first `ov` sites) and its gradient when the warm-up term rides along with the segment
+    passes (operator path and two-sweep path), against the oracle's difference and against the two-launch form."""
+    from test_gpu_parity import GRAD_RTOL, oracle_eval
+
+    from phlash_b200.gpu import _PSMCKernelBase
+
+    ov, L = 132, 8_000  # (ov is not a multiple of the checkpoint spacing)
+    data = rows_with_missing(4, ov + L, seed=31 + S)
+    pps, _, _ = orc.synth_particles(16, B, seed=5)
+    pps = pps.astype(np.float32).astype(np.float64)
+    inds = np.arange(S) + 1
+    pa = np.broadcast_to(pps[:, None], (B, S, 7, 16)).copy()
+    full_ll, full_dlog = oracle_eval(data, inds, pa)
+    warm_ll, warm_dlog = oracle_eval(np.ascontiguousarray(data[:, :ov]), inds, pa)
+    kern = _PSMCKernelBase(16, data)
+    ll, dlog = kern.evaluate_warmup(pps, inds, ov, True)
+    assert path in kern.last_kernel_name and "warm-up term" in kern.last_kernel_name, kern.last_kernel_name
+    np.testing.assert_allclose(ll, full_ll - warm_ll, rtol=2e-6)
+    # a DIFFERENCE of two gradients: fp32 round-off is relative to the un-cancelled size
+    want = full_dlog - warm_dlog
+    scale = np.abs(want).max(axis=-1, keepdims=True)
+    scale_full = np.abs(full_dlog).max(axis=-1, keepdims=True)
+    assert (np.abs(dlog - want) <= GRAD_RTOL * (np.abs(want) + 1e-3 * scale) + 2e-6 * scale_full).all()
+    monkeypatch.setenv("PHB_FUSE_WARMUP", "0")
+    two = _PSMCKernelBase(16, data)
+    ll2, dlog2 = two.evaluate_warmup(pps, inds, ov, True)
+    assert "warm-up term" not in two.last_kernel_name
+    np.testing.assert_allclose(ll, ll2, rtol=1e-6)
+    assert (np.abs(dlog - dlog2) <= 2e-5 * (np.abs(dlog2) + 1e-3 * scale) + 2e-6 * scale_full).all()
 
 
 def test_per_pair_parameter_blocks_and_subtracting_launch():
