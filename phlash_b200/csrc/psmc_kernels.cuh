@@ -28,13 +28,18 @@
 //
 // Kernels in this file:
 //   psmc_loglik_kernel            the throughput kernel described above (loglik, or loglik + gradient);
-//                                 SEG = true: the same passes over the segments of a chunk
+//                                 SEG = true: the same passes over the segments of a chunk (optionally with the
+//                                 checkpoints left by the forward sweep, and with the warm-up term of the
+//                                 whole-term entries as one more segment)
 //   psmc_loglik_storeall_kernel   gradient of small minibatches: every forward vector kept in HBM
 //   transfer_rows_kernel,         parallel in time for FEW pairs: segment transfer operators, chained in
 //   chain_transfer_kernel,        float64 to the log-likelihood (forward only) or to the forward / adjoint
-//   chain_boundaries_kernel       vectors at the segment boundaries (gradient)
-//   boundary_sweep_kernel         the same boundary vectors from two sequential sweeps side by side
-//   sum_segments_kernel           adds the partial gradients of the segments
+//   chain_boundaries_kernel,      vectors at the segment boundaries (gradient); chain_product_kernel /
+//   chain_product_kernel, ..._sharded_kernel   the same with the segments sharded over processes
+//   boundary_sweep_kernel         the same boundary vectors from two sequential sweeps side by side: the latency
+//                                 path (one warp per scheduler), with its own lane layouts per direction,
+//                                 low-latency site functions and hand-pipelined block loops
+//   sum_segments_kernel           adds the partial gradients of the segments (and subtracts the warm-up term)
 //   flag_long_runs_kernel,        precision escalation: rows with long runs of identical observations
 //   split_minibatch_kernel        are scored in double
 //   chunk_het_kernel, validate_params_kernel   data chunking / input validation
