@@ -498,7 +498,9 @@ int try_parallel_in_time_gradient(phb_kernel *k, const phb::KernelArgs &a, cudaS
     if (occ < 1) return kNotTaken;
     const int64_t resident = int64_t(occ) * k->num_sms;
     const int64_t seg_ctas = chunk_major_groups(gv, a.B, a.S);  // groups per segment
-    const int64_t min_seg = pit_mode == 1 ? 64 : 1024;
+    // (segments of >= 512 sites: at S = 1 that is 73 segments + the warm-up term = every resident group slot; with
+    // the 1024 of round 1 a third of the slots stayed empty: 2.88 -> 2.67 ms)
+    const int64_t min_seg = pit_mode == 1 ? 64 : 512;
     // as many segments as keep every group of the segment passes resident at once
     int64_t n_seg = std::min(resident / seg_ctas, a.L / min_seg);
     if (pit_mode == 1) n_seg = std::max<int64_t>(n_seg, std::min<int64_t>(3, a.L / min_seg));

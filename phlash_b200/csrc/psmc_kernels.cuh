@@ -1381,14 +1381,32 @@ template <typename F, int M> __global__ void chain_boundaries_kernel(const Trans
     double ll2 = log2(tot);
     v /= tot;
     if (writer) al[k] = F(v);
+    // (the chain is sequential over the segments: the operator of the NEXT segment is requested while this one is
+    // applied, otherwise every step waits for L2)
+    float col[M];  // column k of the segment's operator
+    double lg_col = 0.0;
+    {
+        const float *rows = op_rows(ta, pair, 0, n_pairs, M);
+#pragma unroll
+        for (int i = 0; i < M; ++i) col[i] = rows[i * M + k];
+        lg_col = op_log2(ta, pair, 0, n_pairs, M)[k];
+    }
     for (int64_t g = 0; g < G; ++g) {
-        const float *rows = op_rows(ta, pair, g, n_pairs, M);
-        const double lg = op_log2(ta, pair, g, n_pairs, M)[k];
+        float cur[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) cur[i] = col[i];
+        const double lg = lg_col;
+        if (g + 1 < G) {
+            const float *rows = op_rows(ta, pair, g + 1, n_pairs, M);
+#pragma unroll
+            for (int i = 0; i < M; ++i) col[i] = rows[i * M + k];
+            lg_col = op_log2(ta, pair, g + 1, n_pairs, M)[k];
+        }
         const double top = group_max<M>(v > 0.0 ? lg : -1e300);
         const double w = v > 0.0 ? v * exp2(lg - top) : 0.0;
         double next = 0.0;
 #pragma unroll
-        for (int i = 0; i < M; ++i) next += __shfl_sync(0xffffffffu, w, i, M) * double(rows[i * M + k]);
+        for (int i = 0; i < M; ++i) next += __shfl_sync(0xffffffffu, w, i, M) * double(cur[i]);
         tot = group_sum<M>(next);
         ll2 += top + log2(tot);
         v = next / tot;
@@ -1397,13 +1415,27 @@ template <typename F, int M> __global__ void chain_boundaries_kernel(const Trans
     // adjoint boundaries: beta_g[i] = 2^lg_i sum_j T_g[i, j] beta_{g+1}[j], kept at maximum 1 (lane k owns row k)
     v = 1.0;
     if (writer) be[G * M + k] = F(1);
+    {
+        const float *rows = op_rows(ta, pair, G - 1, n_pairs, M);
+#pragma unroll
+        for (int j = 0; j < M; ++j) col[j] = rows[k * M + j];  // (row k now)
+        lg_col = op_log2(ta, pair, G - 1, n_pairs, M)[k];
+    }
     for (int64_t g = G - 1; g >= 0; --g) {
-        const float *rows = op_rows(ta, pair, g, n_pairs, M);
-        const double lg = op_log2(ta, pair, g, n_pairs, M)[k];
+        float cur[M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) cur[j] = col[j];
+        const double lg = lg_col;
+        if (g > 0) {
+            const float *rows = op_rows(ta, pair, g - 1, n_pairs, M);
+#pragma unroll
+            for (int j = 0; j < M; ++j) col[j] = rows[k * M + j];
+            lg_col = op_log2(ta, pair, g - 1, n_pairs, M)[k];
+        }
         const double top = group_max<M>(lg);
         double acc = 0.0;
 #pragma unroll
-        for (int j = 0; j < M; ++j) acc += double(rows[k * M + j]) * __shfl_sync(0xffffffffu, v, j, M);
+        for (int j = 0; j < M; ++j) acc += double(cur[j]) * __shfl_sync(0xffffffffu, v, j, M);
         const double next = acc * exp2(lg - top);
         v = next / group_max<M>(next);
         if (writer) be[g * M + k] = F(v);
