@@ -272,10 +272,11 @@ def e2e_small(kern, M, B, n_rows):
     return out
 
 
-def elpd_step(local_rank, M=16, B=500):
+def elpd_step(local_rank, M=16, B=500, rank=0, world=1):
     """The reference's ELPD evaluation (mcmc.py:213-238): forward-only HMM term of all particles over one
     un-chunked held-out contig (2.5 M bins = a 250 Mb chromosome at 100 bp), through the one-call entry;
-    with the parallel-in-time path (automatic) and with the sequential kernel."""
+    with the parallel-in-time path (automatic) and with the sequential kernel.  With several processes the
+    particles are sharded (one all-reduce of a scalar) and the time is the maximum over the ranks."""
     import torch
 
     from benchdata import synth
@@ -286,20 +287,31 @@ def elpd_step(local_rank, M=16, B=500):
     tk = model.elpd_kernel(M, synth.het_matrix(1, n_bins, seed=101), device=local_rank)
     xs = np.load(os.path.join(ROOT, "benchdata", f"particles_M{M}.npz"))["xs"][:B]
     x = torch.tensor(xs, dtype=torch.float64, device=dev)
-    out = {"particles": B, "test_contigs": 1, "bins": n_bins,
-           "path": "transfer_rows_kernel + chain_transfer_kernel (parallel in time), then the 1-bin warm-up term"}
+    out = {"particles": B, "test_contigs": 1, "bins": n_bins, "world": world,
+           "path": "transfer_rows_kernel + chain_transfer_kernel (parallel in time), then the 1-bin warm-up term"
+                   + ("; particles sharded over the processes" if world > 1 else "")}
     for name, mode in (("ms", -1), ("ms_sequential_kernel", 0)):
+        if mode == 0 and world > 1:
+            continue
         tk.set_parallel_in_time(mode)
         for _ in range(2):
-            e = model.elpd_hmm_term(tk, x, PATTERNS[M], THETA)
+            e = model.elpd_hmm_term(tk, x, PATTERNS[M], THETA, rank=rank, world=world)
         torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(3):
-            e = model.elpd_hmm_term(tk, x, PATTERNS[M], THETA)
+            e = model.elpd_hmm_term(tk, x, PATTERNS[M], THETA, rank=rank, world=world)
         e1.record()
         e1.synchronize()
-        out[name] = e0.elapsed_time(e1) / 3
+        t = torch.tensor([e0.elapsed_time(e1) / 3], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[name] = float(t)
+        out["elpd"] = float(e)
         assert bool(torch.isfinite(e))
     return out
 
@@ -607,6 +619,12 @@ def main():
                 small = e2e_small(kern_full, M, B, kern_full._N)
             except Exception as e:
                 small = {"unavailable": repr(e)[:200]}
+    elpd = None
+    if not args.skip_baselines and M == 16:
+        try:
+            elpd = elpd_step(local_rank, rank=rank, world=world)
+        except Exception as e:  # an extra, never allowed to take the benchmark down
+            elpd = {"unavailable": repr(e)[:200]}
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         k_ms = float(np.mean(kernel_ms))
@@ -660,11 +678,8 @@ def main():
             line["svgd_harness"] = svgd
         if small is not None:
             line["e2e_small"] = small
-        if not args.skip_baselines and world == 1 and M == 16:
-            try:
-                line["elpd_step"] = elpd_step(local_rank)
-            except Exception as e:  # an extra, never allowed to take the benchmark down
-                line["elpd_step"] = {"unavailable": repr(e)[:200]}
+        if elpd is not None:
+            line["elpd_step"] = elpd
         if not args.skip_baselines:
             cpu_rows = np.ascontiguousarray(chunks_full[:595, OVERLAP:])
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline(cpu_rows, pps).items() if k != "seconds_per_step"}

@@ -122,7 +122,7 @@ def fit_loop(chunks: np.ndarray, x0, pattern: str, theta: float, update: Callabl
             side.synchronize()
             torch.cuda.synchronize(dev)
             assert bool(torch.isfinite(x).all()), "non-finite particle (mcmc.py:281-285)"
-            e = float(model.elpd_hmm_term(test_kern, x, pattern, theta))
+            e = float(model.elpd_hmm_term(test_kern, x, pattern, theta, rank=rank, world=world))  # particles sharded
             ema = e if ema is None else 0.9 * ema + 0.1 * e
             result.elpd_trace.append(ema)
             if best is None or ema > best[1]:

@@ -83,15 +83,31 @@ def elpd_kernel(M: int, test_het, double_precision: bool = False, device: int = 
     return _PSMCKernelBase(M, full, double_precision=double_precision, device=device)
 
 
-def elpd_hmm_term(test_kern, x, pattern: str, theta: float):
+def elpd_hmm_term(test_kern, x, pattern: str, theta: float, rank: int = 0, world: int = 1):
     """HMM part of the expected log-predictive density: mean over particles of log_density with
     c = (0, 1, 1) over all test contigs (mcmc.py:221-236; the AFS part stays with the caller).
-    Forward only: no gradient is formed."""
+    Forward only: no gradient is formed.
+
+    With one process per GPU (``world`` > 1, process group initialised by the caller) the PARTICLES are sharded:
+    the evaluation is parallel in time through segment transfer operators, i.e. M times the arithmetic of a plain
+    forward pass whatever the number of pairs (88 ms for 500 particles x 2.5 M bins on one GPU, as much as thirty
+    S = 1 steps), so every process scores its block of the particles and one all-reduce of a scalar joins them."""
     import torch
 
     inds = torch.arange(test_kern._N, dtype=torch.int64, device=x.device)
-    value, _ = test_kern.hmm_term(x, pattern, theta, inds, 1, 1.0, grad=False)
-    return value.mean()
+    B = int(x.shape[0])
+    if world <= 1:
+        value, _ = test_kern.hmm_term(x, pattern, theta, inds, 1, 1.0, grad=False)
+        return value.mean()
+    import torch.distributed as dist
+
+    lo, hi = shard_bounds(B, rank, world)
+    total = torch.zeros((), dtype=torch.float64, device=x.device)
+    if hi > lo:
+        value, _ = test_kern.hmm_term(x[lo:hi].contiguous(), pattern, theta, inds, 1, 1.0, grad=False)
+        total = value.sum()
+    dist.all_reduce(total)
+    return total / B
 
 
 def downsample_chunks(chunks, minibatch_size: int, niter: int, rng):

@@ -33,6 +33,11 @@ def _worker(rank, world, port, chunks, xs, pattern, cases, out_dir):
         if rank == world - 1:  # (process 0's last launch is the warm-up term it subtracts)
             np.savez(os.path.join(out_dir, f"{name}.npz"), value=value.cpu().numpy(), grad=grad.cpu().numpy(),
                      kernel=np.array(kern.last_kernel_name))
+    # the ELPD (forward only, un-chunked test contig) with the particles sharded over the processes
+    test_kern = model.elpd_kernel(16, chunks[:2, 500:30_500], device=rank)
+    e = model.elpd_hmm_term(test_kern, x, pattern, 1e-2, rank=rank, world=world)
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "elpd.npz"), elpd=float(e))
     dist.destroy_process_group()
 
 
@@ -63,3 +68,7 @@ def test_sharded_step_equals_single_process(tmp_path):
         np.testing.assert_allclose(got["value"], want_v, rtol=1e-6)
         scale = np.abs(want_g).max(-1, keepdims=True)
         assert np.all(np.abs(got["grad"] - want_g) <= 2e-4 * np.abs(want_g) + 1e-5 * scale), name
+    from phlash_b200 import model
+
+    want = float(model.elpd_hmm_term(model.elpd_kernel(16, chunks[:2, 500:30_500]), x, pattern, 1e-2))
+    np.testing.assert_allclose(float(np.load(tmp_path / "elpd.npz")["elpd"]), want, rtol=1e-9)
