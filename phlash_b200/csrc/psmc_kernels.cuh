@@ -1596,8 +1596,8 @@ __global__ void sum_segments_kernel(const F *__restrict__ seg_dlog, int64_t n_pa
 
 // For MORE pairs than the operators pay for (the reference's default minibatch of 5 chunks: 2 500
 // pairs, still far too few to fill the GPU) the boundary vectors come from two SEQUENTIAL sweeps that run
-// side by side instead: even CTAs run the plain forward recursion and leave the forward vector at every
-// segment boundary (and the log-likelihood), odd CTAs run the adjoint recursion without any gradient
+// side by side instead: the first CTAs run the plain forward recursion and leave the forward vector at every
+// segment boundary (and the log-likelihood), the others run the adjoint recursion without any gradient
 // bookkeeping, beta <- A (emis .* beta), from the end of the chunk and leave the adjoint vectors.  Each
 // is one dependent pass of the cheap kind (~110 ns per site); the expensive gradient passes then run over
 // all segments at once (psmc_loglik_kernel, SEG mode) as in the operator variant.
