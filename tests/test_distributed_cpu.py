@@ -86,3 +86,41 @@ def test_two_ranks_reproduce_the_single_rank_sum(n_chunks):
         ll, dlog = out[rank]
         np.testing.assert_allclose(ll, whole_ll.numpy().sum(1), rtol=1e-12)
         np.testing.assert_allclose(dlog, whole_dlog.numpy().sum(1), rtol=1e-10, atol=1e-14)
+
+
+class _FakeElpdKernel:
+    """Stands in for the ELPD kernel object: hmm_term(x, ...) -> one value per particle (a fixed function of x)."""
+
+    _N = 3
+
+    def hmm_term(self, x, pattern, theta, inds, overlap, weight, grad=False):
+        assert not grad and int(inds.shape[0]) == self._N
+        return (x * x).sum(dim=1) * weight - theta, None
+
+
+def _elpd_worker(rank, world, port, xs, out):
+    from phlash_b200 import model
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        e = model.elpd_hmm_term(_FakeElpdKernel(), torch.tensor(xs), "14*1+1*2", 0.25, rank=rank, world=world)
+        out[rank] = float(e)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_particles", [7, 1])  # 1 particle: rank 1 scores nothing
+def test_elpd_with_particles_sharded_over_two_ranks(n_particles):
+    """model.elpd_hmm_term shards the PARTICLES over the processes (the ELPD is a mean over particles, mcmc.py:221-236):
+    every rank ends up with the single-process value."""
+    from phlash_b200 import model
+
+    xs = np.random.default_rng(3).normal(size=(n_particles, 5))
+    want = float(model.elpd_hmm_term(_FakeElpdKernel(), torch.tensor(xs), "14*1+1*2", 0.25))
+    manager = mp.Manager()
+    out = manager.dict()
+    mp.spawn(_elpd_worker, args=(2, _free_port(), xs, out), nprocs=2, join=True)
+    for rank in (0, 1):
+        np.testing.assert_allclose(out[rank], want, rtol=1e-13)
